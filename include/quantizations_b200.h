@@ -1,0 +1,122 @@
+/*
+ * include/quantizations_b200.h -- C ABI of libquantizations_b200.so
+ *
+ * B200-native (sm_100a) 4-bit weight-only Linear engine.  This header is the drop-in boundary for the hot path of
+ * kkbwilldo/quantizations (reference at /root/reference): every entry point below replaces one function the
+ * reference's FFI binds (its CPython module `kbkim_lib`, pythonInterface.cpp:154-161) or extends it with the
+ * dtype / stream arguments the reference hard-codes.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  All pointers are DEVICE pointers unless stated otherwise.
+ *  - The caller owns every buffer; nothing is allocated, freed or retained (as in the reference).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what the reference uses
+ *    for every launch, ops.cu:82-94,125-127,170).  All calls are asynchronous and CUDA-graph capturable.
+ *  - Every function returns 0 on success, a cudaError_t value (> 0) if the launch failed, or a negative
+ *    Q4_ERR_* code for invalid arguments.  (The reference's functions return void and check nothing; a caller
+ *    that ignores the int gets the reference behaviour.)  q4_error_string() decodes both ranges.
+ *  - Packed 4-bit layout, absmax layout and the double-quant ("nested") statistics are exactly the reference's
+ *    (core.py:536-576): byte i holds element 2i in its HIGH nibble and 2i+1 in its LOW nibble; absmax[b] covers
+ *    elements [b*blocksize, (b+1)*blocksize) of the flattened [N, K] weight.
+ */
+#ifndef QUANTIZATIONS_B200_H
+#define QUANTIZATIONS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q4_ABI_VERSION 1
+
+/* element types of activations / dense weights */
+enum { Q4_F32 = 0, Q4_F16 = 1, Q4_BF16 = 2 };
+/* quantisation data types; 0/1 are the reference's DataType_t (ops.cuh:6-10), NF4 is new */
+enum { Q4_GENERAL8BIT = 0, Q4_FP4 = 1, Q4_NF4 = 2 };
+/* argument errors (negative so they never collide with cudaError_t) */
+enum {
+    Q4_ERR_BLOCKSIZE = -1, /* blocksize not in {64,128,256,512,1024,2048,4096} (core.py:350,408,549,603) */
+    Q4_ERR_DTYPE = -2,     /* unknown element type */
+    Q4_ERR_QUANT_TYPE = -3, /* unknown quant type (core.py:533,608 raise NotImplementedError) */
+    Q4_ERR_SHAPE = -4,     /* negative size, odd K, n != 1 ... */
+    Q4_ERR_NULL = -5,      /* required pointer is NULL */
+    Q4_ERR_ALIGN = -6,     /* pointer alignment insufficient for the vectorised kernels */
+    Q4_ERR_DEVICE = -7     /* not an sm_100 device */
+};
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 1. The reference's five entry points, same names, argument order and meaning.
+ *    Replaces: pythonInterface.cpp:34-46 (c* shims) -> :15-27 -> ops.cu launchers.
+ *    Differences: return int instead of void; launch on the legacy default stream like the reference.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* out[m] = A[1,k] . dequant(B[m,k])^T, fp32 activations/outputs, `absmax` already fp32 per block, `datatype` the
+ * 16-entry code table.  n must be 1.  Replaces pythonInterface.cpp:34 / ops.cu:167-171 / kernels.cu:1062. */
+int cgemm_4bit_inference_naive_fp32(int m, int n, int k, float* A, unsigned char* B, float* absmax, float* datatype,
+                                    float* out, int lda, int ldb, int ldc, int blocksize);
+/* fp16 -> FP4 blockwise quantise.  `code` is ignored (NULL in the reference, core.py:553).
+ * Replaces pythonInterface.cpp:37 / ops.cu:53-95 / kernels.cu:340 <half,BS,*,0,FP4>. */
+int cquantize_blockwise_fp16_fp4(float* code, void* A, float* absmax, unsigned char* out, int blocksize, const int n);
+/* FP4 -> fp16 blockwise dequantise with fp32 absmax.  Replaces pythonInterface.cpp:40 / ops.cu:97-128 / kernels.cu:480. */
+int cdequantize_blockwise_fp16_fp4(float* code, unsigned char* A, float* absmax, void* out, int blocksize, const int n);
+/* fp32 -> 8-bit codebook blockwise quantise (`code` = 256 sorted floats).  Replaces pythonInterface.cpp:43. */
+int cquantize_blockwise_fp32(float* code, float* A, float* absmax, unsigned char* out, int blocksize, const int n);
+/* 8-bit codebook -> fp32 blockwise dequantise.  Replaces pythonInterface.cpp:46. */
+int cdequantize_blockwise_fp32(float* code, unsigned char* A, float* absmax, float* out, int blocksize, const int n);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 2. Generalised entry points (dtype-tagged, explicit stream, fused double-quant).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Double-quant ("nested") statistics of one quantised tensor, as the reference's QuantState holds them
+ * (core.py:23-88, :563-576).  If qabsmax == NULL the tensor is not nested and `absmax` (fp32 per block) is used.
+ * Otherwise absmax[b] = code2[qabsmax[b]] * absmax2[b / blocksize2] + *offset, evaluated as one fp32 multiply then
+ * one fp32 add (kernels.cu:552 + core.py:468), inside the consuming kernel. */
+typedef struct q4_absmax_t {
+    const float* absmax;      /* fp32 [nblocks]              (non-nested) */
+    const uint8_t* qabsmax;   /* uint8 [nblocks]             (nested)     */
+    const float* code2;       /* fp32 [256] dynamic map      (nested)     */
+    const float* absmax2;     /* fp32 [ceil(nblocks/blocksize2)]          */
+    const float* offset;      /* fp32 [1], device memory     (nested)     */
+    int blocksize2;           /* 256 in the reference (core.py:565)       */
+} q4_absmax_t;
+
+/* Blockwise 4-bit quantise: A (in_dtype, n elements, contiguous) -> out uint8[(n+1)/2], absmax fp32[ceil(n/bs)].
+ * Bit-exact with kernels.cu:401-476 for Q4_FP4 (all three input types).  Replaces ops.cu:53-95 <T,0,FP4>. */
+int q4_quantize_blockwise_4bit(const void* A, float* absmax, uint8_t* out, int blocksize, int64_t n, int quant_type,
+                               int in_dtype, void* stream);
+/* Blockwise 8-bit codebook quantise of fp32 data (used for the double-quant of absmax, core.py:565).
+ * Bit-exact with kernels.cu:166-238 + :453-461.  Replaces ops.cu:53-95 <float,0,General8bit>. */
+int q4_quantize_blockwise_8bit(const float* code, const float* A, float* absmax, uint8_t* out, int blocksize,
+                               int64_t n, void* stream);
+/* Blockwise 8-bit dequantise to fp32: out[i] = code[A[i]] * absmax[i / blocksize].  Replaces ops.cu:127. */
+int q4_dequantize_blockwise_8bit(const float* code, const uint8_t* A, const float* absmax, float* out, int blocksize,
+                                 int64_t n, void* stream);
+/* Blockwise 4-bit dequantise, double-quant decode fused: A uint8[(n+1)/2] -> out (out_dtype, n elements).
+ * Bit-exact with kernels.cu:528-567 (+ core.py:613-617 when nested).  Replaces ops.cu:121-125 + 2 torch launches. */
+int q4_dequantize_blockwise_4bit(const uint8_t* A, const q4_absmax_t* stats, void* out, int blocksize, int64_t n,
+                                 int quant_type, int out_dtype, void* stream);
+
+/* Batch-1 decode GEMV with the double-quant decode fused:
+ *     out[r] = sum_k x[k] * code[nib(B[r,k])] * absmax[(r*K + k) / blocksize]   (+ bias[r]),  r in [0, N)
+ * x, out, bias are `dtype`; accumulation is fp32.  `code` = 16 fp32 entries (QuantState.code).
+ * K must be even.  Replaces core.py:467-499 (3 launches) / ops.cu:167-171 / kernels.cu:1062.
+ * flags: Q4_GEMV_EXACT_F32 forces the fp32-multiply path (reference arithmetic for T=float) for any dtype. */
+enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2 };
+int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias,
+                 void* out, int64_t N, int64_t K, int blocksize, int dtype, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3. Introspection
+ * ---------------------------------------------------------------------------------------------------------- */
+int q4_abi_version(void);                 /* == Q4_ABI_VERSION */
+const char* q4_error_string(int code);    /* static string; cudaGetErrorString for positive codes */
+/* counts kernel launches issued through this library since process start (bench.py's gpu_launches) */
+int64_t q4_launch_count(void);
+/* fills sm_count / cc_major / cc_minor of the current device; returns 0 or a cudaError_t */
+int q4_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUANTIZATIONS_B200_H */

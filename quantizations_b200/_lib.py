@@ -1,0 +1,89 @@
+"""ctypes binding of libquantizations_b200.so (the C ABI in include/quantizations_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, this module raises.  The library is built
+in-tree by `python -m quantizations_b200.build` (also run by __graft_entry__.build()).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libquantizations_b200.so")
+
+Q4_F32, Q4_F16, Q4_BF16 = 0, 1, 2
+Q4_GENERAL8BIT, Q4_FP4, Q4_NF4 = 0, 1, 2
+Q4_GEMV_DEFAULT, Q4_GEMV_EXACT_F32, Q4_GEMV_PDL = 0, 1, 2
+
+
+class Q4Error(RuntimeError):
+    pass
+
+
+class AbsmaxStats(ctypes.Structure):
+    """q4_absmax_t"""
+
+    _fields_ = [
+        ("absmax", ctypes.c_void_p),
+        ("qabsmax", ctypes.c_void_p),
+        ("code2", ctypes.c_void_p),
+        ("absmax2", ctypes.c_void_p),
+        ("offset", ctypes.c_void_p),
+        ("blocksize2", ctypes.c_int),
+    ]
+
+
+_vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+_SIGNATURES = {
+    # reference names (pythonInterface.cpp:154-161)
+    "cgemm_4bit_inference_naive_fp32": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],
+    "cquantize_blockwise_fp16_fp4": [_vp, _vp, _vp, _vp, _i, _i],
+    "cdequantize_blockwise_fp16_fp4": [_vp, _vp, _vp, _vp, _i, _i],
+    "cquantize_blockwise_fp32": [_vp, _vp, _vp, _vp, _i, _i],
+    "cdequantize_blockwise_fp32": [_vp, _vp, _vp, _vp, _i, _i],
+    # generalised API
+    "q4_quantize_blockwise_4bit": [_vp, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "q4_quantize_blockwise_8bit": [_vp, _vp, _vp, _vp, _i, _i64, _vp],
+    "q4_dequantize_blockwise_8bit": [_vp, _vp, _vp, _vp, _i, _i64, _vp],
+    "q4_dequantize_blockwise_4bit": [_vp, ctypes.POINTER(AbsmaxStats), _vp, _i, _i64, _i, _i, _vp],
+    "q4_gemv_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp],
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library; raise loudly if it is not built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Q4Error(
+                f"{LIB_PATH} not found: build it with `python -m quantizations_b200.build` "
+                "(quantizations_b200 has no CPU or PyTorch fallback)"
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library is stale: also loud
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        L.q4_abi_version.restype = ctypes.c_int
+        L.q4_error_string.restype = ctypes.c_char_p
+        L.q4_error_string.argtypes = [ctypes.c_int]
+        L.q4_launch_count.restype = ctypes.c_int64
+        L.q4_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3
+        L.q4_device_info.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise Q4Error(f"{what} failed: {lib().q4_error_string(code).decode()} (code {code})")
+
+
+def launch_count() -> int:
+    return int(lib().q4_launch_count())
+
+
+def exported_symbols():
+    return list(_SIGNATURES) + ["q4_abi_version", "q4_error_string", "q4_launch_count", "q4_device_info"]

@@ -1,0 +1,521 @@
+"""Functional layer of the B200 4-bit Linear engine -- host-side mirror of the reference's core.py.
+
+Same public names, signatures, return layouts and error behaviour as /root/reference/core.py (cited per function) so
+that callers -- including HF transformers' bnb-linear replacement -- can switch by changing one import.  What differs:
+
+* every native call goes through the C ABI of libquantizations_b200.so (quantizations_b200/_lib.py), on the current
+  torch CUDA stream, with its return code checked (the reference launches on the legacy stream and checks nothing);
+* `quant_type` accepts "nf4" as well as "fp4" and `compress_statistics=False` is honoured (the reference is
+  FP4-only and always nests, core.py:27,533,563-565);
+* `gemv_4bit` is ONE launch: the 8-bit absmax decode (+ offset) the reference runs as two extra launches on every
+  call (core.py:467-468) is fused into the GEMV kernel; `dequantize_4bit` likewise fuses it (core.py:613-617);
+* fp16 / bf16 / fp32 inputs are dispatched by dtype (the reference reinterprets every input as fp16 for quantize and
+  as fp32 for GEMV regardless of the tensor, pythonInterface.cpp:60-64,82).
+
+There is no CPU path: a non-CUDA tensor raises NotImplementedError exactly where the reference does (core.py:530).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import AbsmaxStats, check
+
+name2qmap = {}
+
+dtype2bytes = {}
+dtype2bytes[torch.uint8] = 1
+
+_VALID_BLOCKSIZES = [4096, 2048, 1024, 512, 256, 128, 64]
+_DTYPE_CODE = {torch.float32: _lib.Q4_F32, torch.float16: _lib.Q4_F16, torch.bfloat16: _lib.Q4_BF16}
+_QUANT_CODE = {"fp4": _lib.Q4_FP4, "nf4": _lib.Q4_NF4}
+
+# NF4 table: the reference's only NF4 artefact, csrc/kernels.cu:851
+_NF4_VALUES = [
+    -1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635,
+    -0.18477343022823334, -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725,
+    0.24611230194568634, 0.33791524171829224, 0.44070982933044434, 0.5626170039176941,
+    0.7229568362236023, 1.0,
+]  # fmt: skip
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class QuantState:
+    """Container for the quantisation statistics of one tensor; layout of reference core.py:23-88.
+
+    absmax  uint8 [nblocks] when nested (8-bit codes of absmax - offset), else float32 [nblocks]
+    shape   torch.Size of the original [N, K] weight          code    float32 [16] 4-bit code table
+    dtype   dtype of the original weight                      blocksize  64 by default
+    offset  0-dim float32 tensor (mean of absmax)             state2  QuantState of the 8-bit level
+                                                                       (absmax float32 [ceil(nblocks/256)],
+                                                                        code float32 [256], blocksize 256)
+    """
+
+    valid_quant_types = ("fp4", "nf4")
+    valid_qs_type_keys = [f"bitsandbytes__{x}" for x in valid_quant_types]
+    valid_qs_keys = [
+        "absmax",
+        "quant_map",
+        "nested_absmax",
+        "nested_quant_map",
+        "quant_state",
+        "quant_type",
+        "blocksize",
+        "dtype",
+        "shape",
+        "nested_blocksize",
+        "nested_dtype",
+        "nested_offset",
+    ]
+
+    def __init__(self, absmax, shape=None, code=None, blocksize=None, quant_type=None, dtype=None, offset=None, state2=None):
+        self.absmax = absmax
+        self.shape = shape
+        self.code = code
+        self.dtype = dtype
+        self.blocksize = blocksize
+        self.quant_type = quant_type
+        self.offset = offset
+        self.state2 = state2
+        self.nested = state2 is not None
+        self._stats = None  # cached C struct of pointers (see native_stats)
+
+    def to(self, device):
+        """Move the statistics to `device` (reference core.py:78-88; also handles a non-nested state)."""
+        self.absmax = self.absmax.to(device)
+        if self.code is not None:
+            self.code = self.code.to(device)
+        if self.nested:
+            self.offset = self.offset.to(device)
+            self.state2.absmax = self.state2.absmax.to(device)
+            self.state2.code = self.state2.code.to(device)
+            self.state2._stats = None
+        self._stats = None
+
+    def native_stats(self) -> AbsmaxStats:
+        """q4_absmax_t view of this state (include/quantizations_b200.h); cached until the tensors move."""
+        key = (self.absmax.data_ptr(), self.state2.absmax.data_ptr() if self.nested else 0)
+        if self._stats is None or self._stats[0] != key:
+            if self.nested:
+                s2 = self.state2
+                if self.absmax.dtype != torch.uint8 or s2.absmax.dtype != torch.float32:
+                    raise ValueError("nested QuantState needs uint8 absmax and float32 state2.absmax")
+                st = AbsmaxStats(None, self.absmax.data_ptr(), s2.code.data_ptr(), s2.absmax.data_ptr(),
+                                 self.offset.data_ptr(), int(s2.blocksize))
+            else:
+                if self.absmax.dtype != torch.float32:
+                    raise ValueError("QuantState.absmax must be float32 when not nested")
+                st = AbsmaxStats(self.absmax.data_ptr(), None, None, None, None, 0)
+            self._stats = (key, st)
+        return self._stats[1]
+
+    # ---- bnb-compatible serialisation (the on-disk format of this path; keys listed but unused in the
+    # reference, core.py:29-42; HF's Bnb4bitDeserialize / save_pretrained need them) -------------------------
+
+    def as_dict(self, packed: bool = False) -> dict:
+        """Tensors + metadata under bitsandbytes' state-dict key names."""
+        qs_dict = {
+            "quant_type": self.quant_type,
+            "absmax": self.absmax,
+            "blocksize": self.blocksize,
+            "quant_map": self.code,
+            "dtype": str(self.dtype).strip("torch."),
+            "shape": tuple(self.shape),
+        }
+        if self.nested:
+            qs_dict.update(
+                {
+                    "nested_absmax": self.state2.absmax,
+                    "nested_blocksize": self.state2.blocksize,
+                    "nested_quant_map": self.state2.code.clone(),
+                    "nested_dtype": str(self.state2.dtype).strip("torch."),
+                    "nested_offset": self.offset.item(),
+                }
+            )
+        if not packed:
+            return qs_dict
+        import json
+
+        tensors = {k: v for k, v in qs_dict.items() if isinstance(v, torch.Tensor)}
+        meta = {k: v for k, v in qs_dict.items() if not isinstance(v, torch.Tensor)}
+        blob = torch.tensor(list(json.dumps(meta).encode("utf-8")), dtype=torch.uint8)
+        tensors["quant_state." + "bitsandbytes__" + self.quant_type] = blob
+        return tensors
+
+    @classmethod
+    def from_dict(cls, qs_dict: dict, device) -> "QuantState":
+        """Inverse of as_dict(packed=True/False); accepts keys with or without a leading module prefix."""
+        import json
+
+        qs_key = [k for k, v in qs_dict.items() if "quant_state" in k and isinstance(v, torch.Tensor)]
+        if not len(qs_key) and "quant_type" not in qs_dict:
+            raise ValueError("Expected packed or unpacked quant_state items, found neither")
+        elif len(qs_key) > 1 or (len(qs_key) == 1 and qs_key[0].split(".")[-1] not in cls.valid_qs_type_keys):
+            raise ValueError(f"There should be exactly one `quant_state` item with ending from {cls.valid_qs_type_keys}.")
+        qs_dict = dict(qs_dict)
+        if len(qs_key) == 1:
+            blob = qs_dict.pop(qs_key[0])
+            qs_dict.update(json.loads(bytes(blob.cpu().tolist()).decode("utf-8")))
+        qs_dict = {k.split(".")[-1]: v for k, v in qs_dict.items()}
+        if not set(qs_dict.keys()).issubset(cls.valid_qs_keys):
+            raise ValueError(f"unexpected quant_state keys: {set(qs_dict) - set(cls.valid_qs_keys)}")
+
+        if "nested_absmax" in qs_dict:
+            offset = torch.tensor(float(qs_dict["nested_offset"]), dtype=torch.float32, device=device)
+            state2 = cls(
+                absmax=qs_dict["nested_absmax"].to(device),
+                blocksize=qs_dict["nested_blocksize"],
+                code=qs_dict["nested_quant_map"].to(device),
+                dtype=getattr(torch, qs_dict["nested_dtype"]),
+            )
+        else:
+            offset, state2 = None, None
+        return cls(
+            quant_type=qs_dict["quant_type"],
+            absmax=qs_dict["absmax"].to(device),
+            blocksize=qs_dict["blocksize"],
+            code=qs_dict["quant_map"].to(device),
+            dtype=getattr(torch, qs_dict["dtype"]),
+            shape=torch.Size(qs_dict["shape"]) if qs_dict["shape"] is not None else None,
+            offset=offset,
+            state2=state2,
+        )
+
+
+class Params4bit(torch.nn.Parameter):
+    """4-bit quantised parameter; same constructor and `.to()` behaviour as reference core.py:91-190.
+
+    HF / accelerate rebuild the parameter as `Params4bit(value, requires_grad=False, **old.__dict__).to(device)`, so
+    `__new__` accepts exactly the attributes it sets (plus `compress_statistics`, which the reference's Linear4bit
+    accepts and ignores, modules.py:80).
+    """
+
+    def __new__(
+        cls,
+        data: Optional[Tensor] = None,
+        requires_grad=False,
+        quant_state: Optional[QuantState] = None,
+        blocksize: int = 64,
+        quant_type: str = "fp4",
+        quant_storage: torch.dtype = torch.uint8,
+        module: Optional["Linear4bit"] = None,  # noqa: F821
+        bnb_quantized: bool = False,
+        compress_statistics: bool = True,
+    ) -> "Params4bit":
+        if data is None:
+            data = torch.empty(0)
+        self = Tensor._make_subclass(cls, data, requires_grad)
+        self.blocksize = blocksize
+        self.compress_statistics = compress_statistics
+        self.quant_type = quant_type
+        self.quant_state = quant_state
+        self.quant_storage = quant_storage
+        self.bnb_quantized = bnb_quantized
+        self.data = data
+        self.module = module
+        return self
+
+    @classmethod
+    def from_prequantized(cls, data: Tensor, quantized_stats: dict, requires_grad: bool = False, device="cuda",
+                          module=None, **kwargs) -> "Params4bit":
+        """Rebuild a parameter from packed bytes + serialised statistics (bnb checkpoint format; absent in the
+        reference, needed by HF's Bnb4bitDeserialize)."""
+        self = Tensor._make_subclass(cls, data.to(device), requires_grad)
+        self.quant_state = QuantState.from_dict(qs_dict=quantized_stats, device=device)
+        self.blocksize = self.quant_state.blocksize
+        self.compress_statistics = self.quant_state.nested
+        self.quant_type = self.quant_state.quant_type
+        self.quant_storage = data.dtype
+        self.bnb_quantized = True
+        self.module = module
+        if module is not None:
+            module.quant_state = self.quant_state
+        return self
+
+    def _quantize(self, device):
+        """reference core.py:139-161"""
+        w = self.data.contiguous().cuda(device)
+        w_4bit, quant_state = quantize_4bit(
+            w,
+            blocksize=self.blocksize,
+            quant_type=self.quant_type,
+            quant_storage=self.quant_storage,
+            compress_statistics=self.compress_statistics,
+        )
+        self.data = w_4bit
+        self.quant_state = quant_state
+        if self.module is not None:
+            self.module.quant_state = quant_state
+        self.bnb_quantized = True
+        return self
+
+    def cuda(self, device=None, non_blocking: bool = False):
+        return self.to(device="cuda" if device is None else device, non_blocking=non_blocking)
+
+    def to(self, *args, **kwargs):
+        """First move to a CUDA device quantises (reference core.py:164-190); later moves carry the state along."""
+        device, dtype, non_blocking, convert_to_format = torch._C._nn._parse_to(*args, **kwargs)
+
+        if device is not None and device.type == "cuda" and not self.bnb_quantized:
+            return self._quantize(device)
+        if self.quant_state is not None and device is not None:
+            self.quant_state.to(device)
+        new_param = Params4bit(
+            super().to(device=device, dtype=dtype, non_blocking=non_blocking),
+            requires_grad=self.requires_grad,
+            quant_state=self.quant_state,
+            blocksize=self.blocksize,
+            quant_type=self.quant_type,
+            quant_storage=self.quant_storage,
+            module=self.module,
+            bnb_quantized=self.bnb_quantized,
+            compress_statistics=self.compress_statistics,
+        )
+        return new_param
+
+
+def get_4bit_type(typename, device=None, blocksize=64):
+    """16-entry code table, float32, normalised to max |v| = 1.  reference core.py:193-229 ("fp4"); "nf4" is the table
+    at reference csrc/kernels.cu:851."""
+    if device is None:
+        device = "cuda"
+    if typename == "fp4":
+        # index = nibble: 0b000 0, 0b001 0.0625, 0b010 8, 0b011 12, 0b100 4, 0b101 6, 0b110 2, 0b111 3 (x1/12);
+        # bit 3 = sign.  Entry 8 is +0.0 as in the reference (its list holds the integer literal -0).
+        magnitudes = [0.0, 0.0625, 8.0, 12.0, 4.0, 6.0, 2.0, 3.0]
+        data = magnitudes + [0.0] + [-m for m in magnitudes[1:]]
+    elif typename == "nf4":
+        data = list(_NF4_VALUES)
+    else:
+        raise NotImplementedError(f"Typename {typename} not supported")
+    data = torch.tensor(data, device=device)
+    data.div_(data.abs().max())
+    assert data.numel() == 16
+    return data
+
+
+def get_ptr(A: Optional[Tensor]) -> int:
+    """reference core.py:232-248"""
+    return 0 if A is None else A.data.data_ptr()
+
+
+def create_dynamic_map(signed=True, max_exponent_bits=7, total_bits=8):
+    """Dynamic 8-bit quantisation map (256 sorted float32 codes).  reference core.py:251-314.
+
+    Built with the same torch CPU ops (torch.linspace in float32, Python-float scaling, sort) so the table is
+    bit-identical to the reference's: tests pin its sha256.
+    """
+    non_sign_bits = total_bits - 1  # the reference subtracts 1 whether or not `signed` (core.py:274)
+    extra = 2 ** (non_sign_bits - max_exponent_bits) - 1
+    signs = (1.0, -1.0) if signed else (1.0,)
+    values = []
+    i = 0
+    for i in range(max_exponent_bits):
+        n_edges = int(2 ** (i + non_sign_bits - max_exponent_bits + (0 if signed else 1)) + 1)
+        edges = torch.linspace(0.1, 1, n_edges)
+        centres = (edges[:-1] + edges[1:]) / 2.0
+        for sgn in signs:
+            values += ((sgn * 10 ** (-(max_exponent_bits - 1) + i)) * centres).tolist()
+    if extra > 0:
+        edges = torch.linspace(0.1, 1, extra + 1)
+        centres = (edges[:-1] + edges[1:]) / 2.0
+        for sgn in signs:
+            values += ((sgn * 10 ** (-(max_exponent_bits - 1) + i)) * centres).tolist()
+    values += [0, 1.0]
+    assert len(values) == 2**total_bits
+    values += [0] * (256 - len(values))
+    values.sort()
+    return Tensor(values)
+
+
+def _dynamic_map(device) -> Tensor:
+    key = ("dynamic", str(device))
+    if key not in name2qmap:
+        if "dynamic" not in name2qmap:
+            name2qmap["dynamic"] = create_dynamic_map()
+        name2qmap[key] = name2qmap["dynamic"].to(device)
+    return name2qmap[key]
+
+
+def quantize_blockwise(A: Tensor, blocksize=4096) -> Tuple[Tensor, QuantState]:
+    """8-bit blockwise quantisation of a float32 tensor with the dynamic map.  reference core.py:317-366."""
+    if A.device.type != "cuda":
+        raise NotImplementedError(f"Device type not supported for blockwise quantization: {A.device.type}")
+    if A.dtype != torch.float32:
+        raise NotImplementedError(f"quantize_blockwise expects float32 input, got {A.dtype}")
+    code = _dynamic_map(A.device)
+    A = A.contiguous()
+    n = A.numel()
+    blocks = -(n // -blocksize)
+    assert blocksize in _VALID_BLOCKSIZES
+    absmax = torch.zeros((blocks,), device=A.device, dtype=torch.float32)
+    out = torch.zeros_like(A, dtype=torch.uint8)
+    with torch.cuda.device(A.device):
+        check(_lib.lib().q4_quantize_blockwise_8bit(code.data_ptr(), A.data_ptr(), absmax.data_ptr(), out.data_ptr(),
+                                                    blocksize, n, _stream(A)), "quantize_blockwise")
+    return out, QuantState(absmax=absmax, code=code, blocksize=blocksize, dtype=A.dtype)
+
+
+def dequantize_blockwise(
+    A: Tensor,
+    quant_state: Optional[QuantState] = None,
+    absmax: Optional[Tensor] = None,
+    code: Optional[Tensor] = None,
+    out: Optional[Tensor] = None,
+    blocksize: int = 4096,
+    nested=False,
+) -> Tensor:
+    """8-bit blockwise dequantisation to float32: out[i] = code[A[i]] * absmax[i // blocksize].  reference core.py:369-423
+    (which requires quant_state despite the assert; here absmax+code+blocksize are honoured when it is None)."""
+    assert quant_state is not None or absmax is not None
+    if quant_state is None:
+        quant_state = QuantState(absmax=absmax, code=_dynamic_map(A.device) if code is None else code,
+                                 blocksize=blocksize, dtype=torch.float32)
+    if quant_state.blocksize not in _VALID_BLOCKSIZES:
+        raise ValueError(
+            f"The blockwise of {quant_state.blocksize} is not supported. Supported values: [2048, 4096, 1024, 512, 256, 128, 64]",
+        )
+    if out is None:
+        out = torch.empty(A.shape, dtype=quant_state.dtype, device=A.device)
+    if out.dtype != torch.float32:
+        raise NotImplementedError(f"dequantize_blockwise writes float32, got out dtype {out.dtype}")
+    qcode = quant_state.code.to(A.device)
+    A = A.contiguous()
+    with torch.cuda.device(A.device):
+        check(_lib.lib().q4_dequantize_blockwise_8bit(qcode.data_ptr(), A.data_ptr(), quant_state.absmax.data_ptr(),
+                                                      out.data_ptr(), quant_state.blocksize, A.numel(), _stream(A)),
+              "dequantize_blockwise")
+    return out
+
+
+def gemv_4bit(
+    A: Tensor,
+    B: Tensor,
+    out: Optional[Tensor] = None,
+    transposed_A=False,
+    transposed_B=False,
+    state=None,
+    bias: Optional[Tensor] = None,
+    flags: int = _lib.Q4_GEMV_DEFAULT,
+):
+    """out[..., n] = sum_k A[..., k] * dequant(B)[n, k]  for a single activation vector.  reference core.py:426-504.
+
+    One kernel launch (fused double-quant decode, optional fused bias) instead of the reference's three.
+    """
+    if state is None:
+        raise ValueError("state cannot None. gem_4bit( ) requires the state from quantize_4bit( )")
+    if A.numel() != A.shape[-1]:
+        raise ValueError(
+            'Dimensions of A are invalid. Must be a vector with the leading dimensions of "1", e.g. [1, 1, 2048]',
+        )
+    if A.dtype not in _DTYPE_CODE:
+        raise NotImplementedError(f"Matmul not implemented for data type {A.dtype}")
+    if B.dtype not in [torch.uint8, torch.bfloat16, torch.float16, torch.float32]:
+        raise NotImplementedError(f"Matmul not implemented for data type {B.dtype}")
+    Bshape = state.shape
+    bout, k = Bshape[0], Bshape[1]
+    if A.shape[-1] != k:
+        raise ValueError(f"A has {A.shape[-1]} features but the quantised weight expects {k}")
+    if out is None:
+        out = torch.empty(A.shape[:-1] + (bout,), dtype=A.dtype, device=A.device)
+    if not A.is_contiguous():
+        A = A.contiguous()
+    lib = _lib.lib()
+    code = lib.q4_gemv_4bit(
+        A.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
+        None if bias is None else bias.data_ptr(), out.data_ptr(), bout, k, state.blocksize,
+        _DTYPE_CODE[A.dtype], flags, torch.cuda.current_stream(A.device).cuda_stream,
+    )
+    if code != 0:
+        check(code, "gemv_4bit")
+    return out
+
+
+def quantize_4bit(
+    A: Tensor,
+    blocksize=64,
+    quant_type="fp4",
+    quant_storage=torch.uint8,
+    compress_statistics=True,
+) -> Tuple[Tensor, QuantState]:
+    """Blockwise 4-bit quantisation.  reference core.py:507-578.
+
+    Returns (packed uint8 [(n+1)//2, 1], QuantState).  With compress_statistics (the reference's only mode) absmax is
+    itself quantised: offset = absmax.mean(); 8-bit blockwise (blocksize 256) of absmax - offset.  mean() and the
+    subtraction are the same torch ops the reference calls, so `offset` is bit-identical on the same device.
+    """
+    if A.device.type != "cuda":
+        raise NotImplementedError(f"Device type not supported for FP4 quantization: {A.device.type}")
+    if quant_type not in _QUANT_CODE:
+        raise NotImplementedError(f"4-bit quantization data type {quant_type} is not implemented.")
+    if A.dtype not in _DTYPE_CODE:
+        raise NotImplementedError(f"4-bit quantization is not implemented for input dtype {A.dtype}")
+
+    n = A.numel()
+    input_shape = A.shape
+    blocks = -(n // -blocksize)
+    absmax = torch.zeros((blocks,), device=A.device, dtype=torch.float32)
+    mod = dtype2bytes[quant_storage] * 2  # KeyError for anything but uint8, like the reference (core.py:545)
+    out = torch.zeros(((n + 1) // mod, 1), dtype=quant_storage, device=A.device)
+    assert blocksize in _VALID_BLOCKSIZES
+    A = A.contiguous()
+    with torch.cuda.device(A.device):
+        check(_lib.lib().q4_quantize_blockwise_4bit(A.data_ptr(), absmax.data_ptr(), out.data_ptr(), blocksize, n,
+                                                    _QUANT_CODE[quant_type], _DTYPE_CODE[A.dtype], _stream(A)),
+              "quantize_4bit")
+    code = get_4bit_type(quant_type, device=A.device)
+
+    if compress_statistics:
+        offset = absmax.mean()
+        absmax -= offset
+        qabsmax, state2 = quantize_blockwise(absmax, blocksize=256)
+        del absmax
+        state = QuantState(absmax=qabsmax, shape=input_shape, dtype=A.dtype, blocksize=blocksize, code=code,
+                           quant_type=quant_type, offset=offset, state2=state2)
+    else:
+        state = QuantState(absmax=absmax, shape=input_shape, dtype=A.dtype, blocksize=blocksize, code=code,
+                           quant_type=quant_type)
+    return out, state
+
+
+def _dequantize_4bit_into(A: Tensor, quant_state: QuantState, out: Tensor) -> Tensor:
+    """Dequantise packed `A` into preallocated contiguous `out` (any of fp16/bf16/fp32), one launch."""
+    with torch.cuda.device(A.device):
+        check(_lib.lib().q4_dequantize_blockwise_4bit(A.data_ptr(), quant_state.native_stats(), out.data_ptr(),
+                                                      quant_state.blocksize, out.numel(),
+                                                      _QUANT_CODE[quant_state.quant_type], _DTYPE_CODE[out.dtype],
+                                                      _stream(A)), "dequantize_4bit")
+    return out
+
+
+def dequantize_4bit(
+    A: Tensor,
+    quant_state: Optional[QuantState] = None,
+    blocksize: int = 64,
+    quant_type="fp4",
+) -> Tensor:
+    """Blockwise 4-bit dequantisation.  reference core.py:581-634.
+
+    Returns the TRANSPOSE (a [K, N] view) of the dequantised [N, K] weight in quant_state.dtype, exactly like the
+    reference (`return out.t()`, core.py:634).  The quantisation type is taken from the state.
+    """
+    if blocksize not in _VALID_BLOCKSIZES:
+        raise ValueError(
+            f"The blockwise of {blocksize} is not supported. Supported values: [2048, 4096, 1024, 512, 256, 128, 64]",
+        )
+    if quant_state is None:
+        raise ValueError("quant_state is required")
+    qt = quant_state.quant_type if quant_state.quant_type is not None else quant_type
+    if qt not in _QUANT_CODE:
+        raise NotImplementedError(f"4-bit quantization data type {qt} is not implemented.")
+    if quant_state.dtype not in _DTYPE_CODE:
+        raise NotImplementedError(f"dequantize_4bit cannot produce dtype {quant_state.dtype}")
+    out = torch.empty(quant_state.shape, dtype=quant_state.dtype, device=A.device)
+    _dequantize_4bit_into(A, quant_state, out)
+    return out.t()

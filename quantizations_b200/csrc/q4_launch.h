@@ -1,0 +1,36 @@
+// q4_launch.h -- host-side declarations shared by the kernel translation units and the extern "C" layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/quantizations_b200.h"
+
+namespace q4 {
+
+// Called once after every kernel launch: bumps the launch counter (q4_launch_count) and returns the launch status
+// (the reference never checks: ops.cu:28,50,82-94,125-127,170).  cudaPeekAtLastError keeps sticky errors visible to
+// the caller's own checks.
+int finish_launch();
+
+int quantize_4bit(const void* A, float* absmax, uint8_t* out, int blocksize, int64_t n, int quant_type, int in_dtype,
+                  cudaStream_t stream);
+int quantize_8bit(const float* code, const float* A, float* absmax, uint8_t* out, int blocksize, int64_t n,
+                  cudaStream_t stream);
+int dequantize_8bit(const float* code, const uint8_t* A, const float* absmax, float* out, int blocksize, int64_t n,
+                    cudaStream_t stream);
+int dequantize_4bit(const uint8_t* A, const q4_absmax_t* stats, void* out, int blocksize, int64_t n, int quant_type,
+                    int out_dtype, cudaStream_t stream);
+int gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
+              int64_t N, int64_t K, int blocksize, int dtype, int flags, cudaStream_t stream);
+
+int sm_count();  // cached multiprocessor count of the current device
+
+inline int ilog2(int v)
+{
+    int s = 0;
+    while ((1 << s) < v) s++;
+    return s;
+}
+
+}  // namespace q4

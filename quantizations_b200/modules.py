@@ -1,0 +1,84 @@
+"""nn.Module layer -- host-side mirror of the reference's modules.py (Linear4bit, matmul_4bit).
+
+reference: /root/reference/modules.py:28-64 (matmul_4bit), :67-151 (Linear4bit).  Inference only, like the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .core import Params4bit, QuantState, _dequantize_4bit_into, gemv_4bit
+
+
+def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: torch.Tensor = None, bias=None):
+    """A @ dequant(B)^T (+ bias).  reference modules.py:28-64.
+
+    Decode (A is a single vector): one fused GEMV launch, bias included.
+    Prefill: the weight is dequantised straight into A's dtype (one launch, no fp16 detour and no cast, unlike
+    modules.py:64) and contracted on the tensor cores.
+    """
+    assert quant_state is not None
+    if A.numel() == A.shape[-1]:
+        return gemv_4bit(A, B, out, state=quant_state, bias=bias)
+    W = torch.empty(quant_state.shape, dtype=A.dtype, device=A.device)
+    _dequantize_4bit_into(B, quant_state, W)
+    return torch.nn.functional.linear(A, W, bias)
+
+
+class Linear4bit(nn.Linear):
+    """Linear layer over a 4-bit blockwise-quantised weight; drop-in for the reference's Linear4bit
+    (modules.py:67-151) and, through it, for bitsandbytes.nn.Linear4bit as HF transformers constructs it:
+    Linear4bit(in, out, bias, compute_dtype, compress_statistics=..., quant_type=..., quant_storage=...).
+
+    quant_type: "fp4" (reference) or "nf4".  compress_statistics=False keeps fp32 absmax (the reference accepts the
+    flag and ignores it, modules.py:80).
+    """
+
+    def __init__(
+        self,
+        input_features,
+        output_features,
+        bias=False,
+        compute_dtype=None,
+        compress_statistics=True,
+        quant_type="fp4",
+        quant_storage=torch.uint8,
+        device=None,
+    ):
+        super().__init__(input_features, output_features, bias, device)
+        self.weight = Params4bit(
+            self.weight.data,
+            requires_grad=False,
+            quant_type=quant_type,
+            quant_storage=quant_storage,
+            module=self,
+            compress_statistics=compress_statistics,
+        )
+        self.compute_dtype = compute_dtype
+        self.compute_type_is_set = False
+        self.quant_state = None
+        self.quant_storage = quant_storage
+
+    def set_compute_type(self, x):
+        """reference modules.py:112-122: fp32 / bf16 inputs set the compute dtype; fp16 keeps the configured one."""
+        if x.dtype in [torch.float32, torch.bfloat16]:
+            self.compute_dtype = x.dtype
+
+    def forward(self, x: torch.Tensor):
+        """reference modules.py:124-151"""
+        if not self.compute_type_is_set:
+            self.set_compute_type(x)
+            self.compute_type_is_set = True
+
+        inp_dtype = x.dtype
+        if self.compute_dtype is not None and x.dtype != self.compute_dtype:
+            x = x.to(self.compute_dtype)
+        bias = self.bias
+        if bias is not None and bias.dtype != x.dtype:
+            bias = bias.to(x.dtype)
+        weight = self.weight
+        if weight.quant_state is None:
+            raise RuntimeError("Linear4bit weight is not quantized yet: move the module to a CUDA device first")
+        out = matmul_4bit(x, weight.data, bias=bias, quant_state=weight.quant_state)
+        return out if out.dtype == inp_dtype else out.to(inp_dtype)

@@ -1,0 +1,310 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the reference-shaped Python API) against the CPU oracle on the
+same seeded inputs, against the golden outputs of the reference's own kernels, and -- at BASELINE.json's full sizes --
+through size-independent properties.
+
+Bars (BASELINE.json north_star): quantize (packed bytes, absmax, nested codes) and dequantize outputs BIT-EXACT;
+GEMV within max|err| <= 1e-2 * max|truth| of an fp64 truth (stated per test).
+"""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import iter_cases
+
+pytestmark = pytest.mark.gpu
+
+TDT = {"float16": torch.float16, "bfloat16": torch.bfloat16, "float32": torch.float32}
+DEV = "cuda:0"
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def f32(t):
+    return t.detach().float().cpu().numpy()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bits_equal(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
+    if got.dtype.kind == "f":
+        neq = bits(got) != bits(want)
+        both_nan = np.isnan(got) & np.isnan(want)
+        neq &= ~both_nan
+    else:
+        neq = got != want
+    assert not neq.any(), f"{what}: {int(neq.sum())} of {neq.size} differ, first at {np.argwhere(neq)[:4].ravel()}"
+
+
+@pytest.fixture(scope="module")
+def q():
+    import quantizations_b200 as q
+
+    q._lib.lib()  # fail loudly if the CUDA library is missing
+    return q
+
+
+def make_state(q, st, device=DEV):
+    """oracle state dict -> product QuantState on the GPU"""
+    code = dev(st["code"])
+    if "qabsmax" in st:
+        s2 = q.QuantState(absmax=dev(st["absmax2"]), code=dev(st["code2"]), blocksize=256, dtype=torch.float32)
+        return q.QuantState(absmax=dev(st["qabsmax"]), shape=torch.Size(st["shape"]), code=code, blocksize=st["blocksize"],
+                            quant_type=st["quant_type"], dtype=torch.float16,
+                            offset=torch.tensor(float(st["offset"]), dtype=torch.float32, device=device), state2=s2)
+    return q.QuantState(absmax=dev(st["absmax_f32"]), shape=torch.Size(st["shape"]), code=code, blocksize=st["blocksize"],
+                        quant_type=st["quant_type"], dtype=torch.float16)
+
+
+# ------------------------------------------------------------------------------------------------ quantize
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16", "float32"])
+@pytest.mark.parametrize("quant_type", ["fp4", "nf4"])
+@pytest.mark.parametrize("blocksize,n", [(64, 64 * 1024), (64, 1001), (64, 63), (64, 1), (128, 5000), (256, 4096),
+                                         (512, 5003), (1024, 8192), (2048, 9000), (4096, 16384 + 7)])
+def test_quantize_4bit_bit_exact_vs_oracle(q, oracle, dtype, quant_type, blocksize, n):
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, quant_type, blocksize, n)).encode()))
+    a = (rng.standard_normal(n) * 0.02).astype(np.float32)
+    a[rng.integers(0, n, max(1, n // 50))] = 0.0
+    A = dev(a, TDT[dtype])
+    a = f32(A)
+    packed, state = q.quantize_4bit(A, blocksize=blocksize, quant_type=quant_type, compress_statistics=False)
+    o_packed, o_absmax = oracle.quantize_blockwise_4bit(a, blocksize, quant_type)
+    assert packed.shape == ((n + 1) // 2, 1) and packed.dtype == torch.uint8
+    assert_bits_equal(state.absmax.cpu().numpy(), o_absmax, "absmax")
+    assert_bits_equal(packed.cpu().numpy().ravel(), o_packed, "packed")
+
+
+@pytest.mark.parametrize("quant_type", ["fp4", "nf4"])
+def test_quantize_4bit_nested_bit_exact_vs_oracle(q, oracle, quant_type):
+    """Whole quantize_4bit recipe (core.py:536-576): the offset is torch's CUDA mean, handed to the oracle."""
+    rng = np.random.default_rng(7)
+    N, K = 512, 1024
+    A = dev((rng.standard_normal((N, K)) * 0.02).astype(np.float32), torch.bfloat16)
+    packed, state = q.quantize_4bit(A, quant_type=quant_type)
+    assert state.nested and state.absmax.dtype == torch.uint8 and state.state2.blocksize == 256
+    st = oracle.quantize_4bit(f32(A), 64, quant_type, offset=float(state.offset.item()))
+    assert_bits_equal(packed.cpu().numpy().ravel(), st["packed"], "packed")
+    assert_bits_equal(state.absmax.cpu().numpy(), st["qabsmax"], "qabsmax")
+    assert_bits_equal(state.state2.absmax.cpu().numpy(), st["absmax2"], "absmax2")
+    assert_bits_equal(state.state2.code.cpu().numpy(), st["code2"], "code2")
+    assert_bits_equal(state.code.cpu().numpy(), st["code"], "code")
+    assert tuple(state.shape) == (N, K) and state.dtype == torch.bfloat16
+
+
+def test_quantize_fp4_matches_reference_golden(q, golden):
+    g = golden("quantize_fp4")
+    for k, (dtype, blocksize, n, kind) in iter_cases(g):
+        A = dev(g[k + "_in"], TDT[dtype])
+        packed, state = q.quantize_4bit(A, blocksize=int(blocksize), quant_type="fp4", compress_statistics=False)
+        assert_bits_equal(state.absmax.cpu().numpy(), g[k + "_absmax"], f"{k} {dtype} bs={blocksize} n={n} {kind}: absmax")
+        assert_bits_equal(packed.cpu().numpy().ravel(), g[k + "_packed"], f"{k} {dtype} bs={blocksize} n={n} {kind}: packed")
+
+
+def test_blockwise_8bit_matches_reference_golden(q, golden):
+    g = golden("blockwise_8bit")
+    for k, (name, blocksize) in iter_cases(g):
+        A = dev(g[k + "_in"])
+        out, st = q.quantize_blockwise(A, blocksize=int(blocksize))
+        assert_bits_equal(st.absmax.cpu().numpy(), g[k + "_absmax"], f"{k} {name} bs={blocksize}: absmax")
+        assert_bits_equal(out.cpu().numpy(), g[k + "_q"], f"{k} {name} bs={blocksize}: codes")
+        deq = q.dequantize_blockwise(out, st)
+        assert_bits_equal(deq.cpu().numpy(), g[k + "_deq"], f"{k} {name} bs={blocksize}: dequantized")
+
+
+@pytest.mark.parametrize("blocksize,n", [(256, 256 * 100 + 3), (4096, 4096 * 3 + 1), (64, 1000), (1024, 1024)])
+def test_blockwise_8bit_bit_exact_vs_oracle(q, oracle, blocksize, n):
+    rng = np.random.default_rng(blocksize + n)
+    a = rng.uniform(-1, 1, n).astype(np.float32) * 0.3
+    out, st = q.quantize_blockwise(dev(a), blocksize=blocksize)
+    o_q, o_am = oracle.quantize_blockwise_8bit(a, blocksize)
+    assert_bits_equal(st.absmax.cpu().numpy(), o_am, "absmax")
+    assert_bits_equal(out.cpu().numpy(), o_q, "codes")
+    deq = q.dequantize_blockwise(out, st)
+    assert_bits_equal(deq.cpu().numpy(), oracle.dequantize_blockwise_8bit(o_q, o_am, blocksize), "dequantized")
+
+
+# ------------------------------------------------------------------------------------------------ dequantize
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16", "float32"])
+@pytest.mark.parametrize("quant_type", ["fp4", "nf4"])
+@pytest.mark.parametrize("nested", [False, True])
+@pytest.mark.parametrize("shape", [(256, 512), (3, 100), (1, 7), (64, 64)])
+def test_dequantize_4bit_bit_exact_vs_oracle(q, oracle, dtype, quant_type, nested, shape):
+    rng = np.random.default_rng(11)
+    w = (rng.standard_normal(shape) * 0.02).astype(np.float32)
+    A = dev(w, TDT[dtype])
+    packed, state = q.quantize_4bit(A, quant_type=quant_type, compress_statistics=nested)
+    out = q.dequantize_4bit(packed, state)
+    assert out.shape == (shape[1], shape[0]) and out.dtype == TDT[dtype]  # the reference returns out.t() (core.py:634)
+    st = oracle.quantize_4bit(f32(A), 64, quant_type, offset=float(state.offset.item()) if nested else None,
+                              compress_statistics=nested)
+    want = oracle.dequantize_4bit(st, dtype)
+    assert_bits_equal(f32(out.t()), want, "dequantized weight")
+
+
+def test_dequantize_fp4_matches_reference_golden(q, golden):
+    g = golden("dequantize_fp4")
+    for k, (dtype, blocksize, n) in iter_cases(g):
+        n, blocksize = int(n), int(blocksize)
+        state = q.QuantState(absmax=dev(g[k + "_absmax"]), shape=torch.Size((1, n)), code=q.get_4bit_type("fp4", DEV),
+                             blocksize=blocksize, quant_type="fp4", dtype=TDT[dtype])
+        out = q.dequantize_4bit(dev(g[k + "_packed"]), state, blocksize=blocksize)
+        assert_bits_equal(f32(out).ravel(), g[k + "_out"], f"{k} {dtype} bs={blocksize} n={n}")
+
+
+def test_reference_recipe_golden(q, golden):
+    """The reference's full quantize_4bit -> dequantize_4bit / gemv_4bit recipe on one weight, step by step."""
+    g = golden("linear_fp4_recipe")
+    N, K = (int(v) for v in g["shape"])
+    W = dev(g["w"], torch.float16).reshape(N, K)
+    packed, state = q.quantize_4bit(W, quant_type="fp4")
+    assert_bits_equal(packed.cpu().numpy().ravel(), g["packed"], "packed")
+    assert_bits_equal(np.float32(state.offset.item()), g["offset"], "offset (torch CUDA mean)")
+    assert_bits_equal(state.absmax.cpu().numpy(), g["qabsmax"], "qabsmax")
+    assert_bits_equal(state.state2.absmax.cpu().numpy(), g["absmax2"], "absmax2")
+    wdeq = q.dequantize_4bit(packed, state).t()
+    assert_bits_equal(f32(wdeq).ravel(), g["wdeq"], "dequantized weight (fused double-quant decode)")
+    x = dev(g["x"]).reshape(1, 1, K)
+    y = q.gemv_4bit(x, packed, state=state)
+    assert y.shape == (1, 1, N)
+    np.testing.assert_allclose(f32(y).ravel(), g["y"], rtol=0, atol=2e-6 * np.abs(g["y"]).max() + 1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ GEMV
+
+
+def gemv_truth(oracle, x, st, N, K):
+    return oracle.gemv_4bit_f64(x, st["packed"], oracle.state_absmax(st), st["code"], N, K, st["blocksize"])
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float32"])
+@pytest.mark.parametrize("quant_type", ["nf4", "fp4"])
+@pytest.mark.parametrize("nested", [True, False])
+@pytest.mark.parametrize("N,K", [(64, 256), (33, 1088), (1024, 4096), (7, 14336), (300, 2048), (5, 64), (129, 6144)])
+def test_gemv_vs_fp64_truth(q, oracle, dtype, quant_type, nested, N, K):
+    """tolerance: max|y - truth| <= 1e-2 * max|truth| (BASELINE north_star), plus the output type's own rounding."""
+    rng = np.random.default_rng(N * 131 + K)
+    W = dev((rng.standard_normal((N, K)) * 0.02).astype(np.float32), TDT[dtype] if dtype != "float32" else torch.float16)
+    packed, state = q.quantize_4bit(W, quant_type=quant_type, compress_statistics=nested)
+    x = dev(rng.standard_normal(K).astype(np.float32), TDT[dtype]).reshape(1, 1, K)
+    bias = dev(rng.standard_normal(N).astype(np.float32), TDT[dtype])
+    y = q.gemv_4bit(x, packed, state=state)
+    yb = q.gemv_4bit(x, packed, state=state, bias=bias)
+    assert y.shape == (1, 1, N) and y.dtype == TDT[dtype]
+    st = oracle.quantize_4bit(f32(W), 64, quant_type, offset=float(state.offset.item()) if nested else None,
+                              compress_statistics=nested)
+    truth = gemv_truth(oracle, f32(x).ravel(), st, N, K)
+    scale = np.abs(truth).max()
+    err = np.abs(f32(y).ravel() - truth).max()
+    assert err <= 1e-2 * scale, f"max err {err:.3e} vs scale {scale:.3e}"
+    tight = {"float32": 1e-5, "float16": 2e-3, "bfloat16": 8e-3}[dtype]
+    assert err <= tight * scale, f"max err {err:.3e} exceeds the expected {tight} * {scale:.3e}"
+    errb = np.abs(f32(yb).ravel() - (truth + f32(bias))).max()
+    assert errb <= 1e-2 * np.abs(truth + f32(bias)).max()
+
+
+def test_gemv_matches_reference_golden(q, golden):
+    """Against the reference kernel's own outputs (fp32 exported instance; fp16/bf16 instances via the test shim).
+    The reference's 16-bit instances round code, absmax, code*absmax and every product to T (kernels.cu:1120,1131,
+    1169,1206); ours keeps fp32 where it can, so grade ours against the reference with the reference's own distance
+    from truth as the yard-stick."""
+    g = golden("gemv")
+    for k, (dtype, N, K, code_name) in iter_cases(g):
+        N, K = int(N), int(K)
+        state = q.QuantState(absmax=dev(g[k + "_absmax"]), shape=torch.Size((N, K)), code=dev(g[k + "_code"]), blocksize=64,
+                             quant_type=code_name, dtype=torch.float16)
+        x = dev(g[k + "_x"], TDT[dtype]).reshape(1, 1, K)
+        y = f32(q.gemv_4bit(x, dev(g[k + "_packed"]), state=state)).ravel()
+        ref = g[k + "_out"]
+        scale = np.abs(ref).max()
+        tol = {"float32": 2e-6, "float16": 4e-3, "bfloat16": 3e-2}[dtype]
+        assert np.abs(y - ref).max() <= tol * scale, f"{k} {dtype} {N}x{K} {code_name}: {np.abs(y - ref).max():.3e} vs {scale:.3e}"
+
+
+def test_gemv_error_behaviour(q):
+    """reference core.py:453-460"""
+    W = torch.randn(64, 128, device=DEV, dtype=torch.float16)
+    packed, state = q.quantize_4bit(W)
+    with pytest.raises(ValueError):
+        q.gemv_4bit(torch.randn(1, 1, 128, device=DEV), packed, state=None)
+    with pytest.raises(ValueError):
+        q.gemv_4bit(torch.randn(2, 128, device=DEV), packed, state=state)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+
+
+LLAMA3_8B_SHAPES = [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336)]
+
+
+@pytest.mark.parametrize("N,K", LLAMA3_8B_SHAPES)
+@pytest.mark.parametrize("quant_type", ["nf4", "fp4"])
+def test_full_size_roundtrip_and_linearity(q, N, K, quant_type):
+    """BASELINE.json config 2 sizes.  Properties that need no CPU oracle:
+    (1) quantize is idempotent on its own output: quantize(dequantize(q(W))) reproduces the same packed bytes;
+    (2) every dequantized block's max |value| equals its decoded absmax times a code of magnitude 1 (the absmax
+        element always maps to +-1);
+    (3) GEMV is linear: gemv(a*x1 + x2) == a*gemv(x1) + gemv(x2) within fp rounding, and
+    (4) GEMV agrees with a torch fp32 matmul of the dequantized weight (max err <= 1e-2 * max|y|)."""
+    torch.manual_seed(0)
+    W = (torch.randn(N, K, device=DEV, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+    packed, state = q.quantize_4bit(W, quant_type=quant_type)
+    assert packed.numel() == N * K // 2 and state.absmax.numel() == N * K // 64
+    Wd = q.dequantize_4bit(packed, state).t().contiguous()
+    assert Wd.shape == (N, K) and Wd.dtype == torch.bfloat16
+    # (2)
+    blockmax = Wd.float().reshape(-1, 64).abs().amax(dim=1)
+    absmax = q.dequantize_blockwise(state.absmax, state.state2) + state.offset
+    assert torch.equal(blockmax.to(torch.bfloat16), absmax.abs().to(torch.bfloat16))
+    # (1) re-quantising the dequantised weight with UNCOMPRESSED statistics must give back the same codes wherever the
+    # bf16 rounding of absmax did not move the block maximum (it is the same value by (2)), i.e. everywhere.
+    packed2, state2 = q.quantize_4bit(Wd, quant_type=quant_type, compress_statistics=False)
+    same = (packed2 == packed).float().mean().item()
+    assert same > 0.999, f"only {same:.5f} of the packed bytes survive a dequantize->quantize round trip"
+    # (3) + (4)
+    torch.manual_seed(1)
+    x1 = torch.randn(1, 1, K, device=DEV, dtype=torch.bfloat16)
+    x2 = torch.randn(1, 1, K, device=DEV, dtype=torch.bfloat16)
+    y1, y2 = q.gemv_4bit(x1, packed, state=state).float(), q.gemv_4bit(x2, packed, state=state).float()
+    y12 = q.gemv_4bit((2 * x1 + x2), packed, state=state).float()
+    ref = (2 * x1 + x2).float().reshape(1, K) @ Wd.float().t()
+    scale = ref.abs().max().item()
+    assert (y12 - ref).abs().max().item() <= 1e-2 * scale
+    assert (y12 - (2 * y1 + y2)).abs().max().item() <= 2e-2 * scale
+
+
+def test_linear4bit_module_decode_and_prefill(q):
+    """Linear4bit as HF constructs it (modules.py:86-110): quantises on .to('cuda'), decode -> GEMV, prefill -> GEMM."""
+    torch.manual_seed(0)
+    lin = q.Linear4bit(512, 256, bias=True, compute_dtype=torch.bfloat16, compress_statistics=True, quant_type="nf4")
+    w_ref = lin.weight.data.clone()
+    lin = lin.to(DEV)
+    assert type(lin.weight).__name__ == "Params4bit" and lin.weight.dtype == torch.uint8
+    assert lin.weight.shape == (512 * 256 // 2, 1) and lin.quant_state is lin.weight.quant_state
+    Wd = q.dequantize_4bit(lin.weight.data, lin.weight.quant_state).t().float()
+    assert (Wd.cpu() - w_ref).abs().max() < 0.2 * w_ref.abs().max()
+    x = torch.randn(1, 1, 512, device=DEV, dtype=torch.bfloat16)
+    y = lin(x)
+    ref = x.float() @ Wd.t() + lin.bias.float()
+    assert y.shape == (1, 1, 256) and y.dtype == torch.bfloat16
+    assert (y.float() - ref).abs().max() <= 1e-2 * ref.abs().max()
+    xp = torch.randn(2, 17, 512, device=DEV, dtype=torch.bfloat16)
+    yp = lin(xp)
+    refp = xp.float() @ Wd.t() + lin.bias.float()
+    assert yp.shape == (2, 17, 256)
+    assert (yp.float() - refp).abs().max() <= 2e-2 * refp.abs().max()
+    # the accelerate/HF rebuild pattern: Params4bit(value, requires_grad=False, **old.__dict__).to(device)
+    old = lin.weight
+    rebuilt = q.Params4bit(old.data, requires_grad=False, **old.__dict__).to(DEV)
+    assert rebuilt.quant_state is old.quant_state and rebuilt.bnb_quantized
