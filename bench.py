@@ -1,0 +1,485 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): the NF4 + double-quant Linear4bit stack of Llama-3-8B at batch 1 -- per layer
+q_proj 4096x4096, k_proj/v_proj 1024x4096, o_proj 4096x4096, gate_proj/up_proj 14336x4096, down_proj 4096x14336,
+x 32 layers = 224 GEMVs per step over 3.5 GB of DISTINCT packed weights (random-init, synthetic), far larger than the
+126 MB L2, so every step streams every byte from HBM.  A step = one decode token's worth of Linear4bit forwards.
+
+metric / unit   BASELINE.json's: 4-bit GEMV HBM GB/s = algorithmic bytes of the step / step time
+value           device-timed (CUDA events around K graph replays), inputs resident in HBM, launches through the C ABI
+e2e             the same step through the public Python API (Linear4bit.forward under quantizations_b200.graphs), with
+                the activations copied from pinned host memory and the outputs copied back inside the timed region
+roofline        the GEMV kernel: algorithmic bytes per launch / average launch duration vs MEASURED_PEAKS.json hbm_gbs
+cpu_baseline    oracle/q4_torch_cpu.py (torch-CPU dequantize -> matmul port) on the box's host cores, bounded sample
+--impl reference   the reference's own kernels (oracle/_ref, built from /root/reference for sm_100a) driven with the
+                reference's gemv_4bit call sequence (core.py:467-499) on the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "4-bit GEMV HBM GB/s (% of ~8 TB/s); Llama-3-8B bs=1 decode tok/s"
+LLAMA3_8B = dict(hidden=4096, inter=14336, kv=1024, layers=32)
+LLAMA3_70B = dict(hidden=8192, inter=28672, kv=1024, layers=80)
+
+
+def layer_shapes(cfg, tp: int = 1):
+    """(name, N, K, parallel) of one decoder layer's Linear4bit modules, Megatron-style TP split."""
+    h, i, kv = cfg["hidden"], cfg["inter"], cfg["kv"]
+    return [
+        ("q_proj", h // tp, h, "col"), ("k_proj", kv // tp, h, "col"), ("v_proj", kv // tp, h, "col"),
+        ("o_proj", h, h // tp, "row"), ("gate_proj", i // tp, h, "col"), ("up_proj", i // tp, h, "col"),
+        ("down_proj", h, i // tp, "row"),
+    ]  # fmt: skip
+
+
+def algo_bytes(N: int, K: int, xbytes: int = 2, nested: bool = True) -> int:
+    """packed + absmax (+ nested tables) + code + x + y."""
+    n = N * K
+    b = n // 2 + 64 + xbytes * K + xbytes * N
+    b += (n // 64 + 4 * -(-n // 16384) + 1024 + 4) if nested else 4 * (n // 64)
+    return b
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_stack(cfg, tp, rank, device, dtype, quant_type, layers, q):
+    """Random-init, quantised Linear4bit stack.  Every rank draws the full weight from a shared seed and quantises its own
+    slice (row-parallel shards are quantised as their own [N, K/p] tensors)."""
+    mods = []
+    g = torch.Generator(device=device)
+    for layer in range(layers):
+        for j, (name, N, K, par) in enumerate(layer_shapes(cfg, tp)):
+            g.manual_seed(1000 * layer + j)
+            fullN, fullK = (N * tp, K) if par == "col" else (N, K * tp)
+            if tp == 1:
+                W = torch.randn(N, K, device=device, dtype=torch.float32, generator=g).mul_(0.02).to(dtype)
+            else:
+                Wf = torch.randn(fullN, fullK, device=device, dtype=torch.float32, generator=g).mul_(0.02).to(dtype)
+                W = (Wf[rank * N:(rank + 1) * N] if par == "col" else Wf[:, rank * K:(rank + 1) * K]).contiguous()
+                del Wf
+            lin = q.Linear4bit(K, N, bias=False, compute_dtype=dtype, compress_statistics=True, quant_type=quant_type,
+                               device="meta")
+            lin.weight = q.Params4bit(W, requires_grad=False, quant_type=quant_type, module=lin).to(device)
+            lin.parallel, lin.name_ = par, name
+            mods.append(lin)
+            del W
+    return mods
+
+
+def run_ours(args, rank, world, device):
+    import quantizations_b200 as q
+    from quantizations_b200 import _lib, graphs
+
+    L = _lib.lib()
+    dtype = torch.bfloat16
+    cfg = LLAMA3_8B if args.model == "llama3-8b" else LLAMA3_70B
+    layers = args.layers or cfg["layers"]
+    tp = world
+    mods = build_stack(cfg, tp, rank, device, dtype, "nf4", layers, q)
+    step_bytes_local = sum(algo_bytes(m.out_features, m.in_features) for m in mods)
+    step_bytes = step_bytes_local * world  # every rank streams its own shard
+    packed_bytes = sum(m.weight.numel() for m in mods)
+
+    h, inter = cfg["hidden"], cfg["inter"]
+    torch.manual_seed(1)
+    x_in = {K: torch.randn(1, 1, K, device=device, dtype=dtype) for K in {m.in_features for m in mods}}
+    outs = {}
+    for m in mods:
+        outs.setdefault((m.name_, m.out_features), torch.empty(1, 1, m.out_features, device=device, dtype=dtype))
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+
+        comm = dist
+
+    flags = _lib.Q4_GEMV_PDL if args.pdl else 0
+
+    def step_cabi():
+        """one decode token's worth of Linear4bit GEMVs straight through the C ABI"""
+        stream = torch.cuda.current_stream().cuda_stream
+        for m in mods:
+            st = m.weight.quant_state
+            out = outs[(m.name_, m.out_features)]
+            rc = L.q4_gemv_4bit(x_in[m.in_features].data_ptr(), m.weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None,
+                                out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags, stream)
+            if rc:
+                _lib.check(rc, "q4_gemv_4bit")
+            if comm is not None and m.parallel == "row":
+                comm.all_reduce(out)
+
+    # ---- value: CUDA-graph replay of the step, device-timed
+    n0 = _lib.launch_count()
+    step_cabi()
+    launches_per_step = _lib.launch_count() - n0
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        graph = graphs.capture(step_cabi)
+    run = graph.replay if graph is not None else step_cabi
+
+    def barrier():
+        if comm is not None:
+            comm.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        run()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(device.index) as clk:
+        pad_until = time.time() + 0.35  # let the sampler see the load: repeat the timed block until 0.35 s have passed
+        times = []
+        while True:
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                run()
+            e1.record()
+            barrier()
+            times.append(e0.elapsed_time(e1))
+            if time.time() > pad_until:
+                break
+    ms_total = times[0]  # the contract's number: the FIRST timed block of exactly K steps
+    if comm is not None:
+        t = torch.tensor([ms_total], device=device)
+        comm.all_reduce(t, op=comm.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_per_step = ms_total / args.steps
+    value = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: public Python API (Linear4bit.forward captured by quantizations_b200.graphs), host buffers in and out
+    xin_host = {K: v.cpu().pin_memory() for K, v in x_in.items()}
+    x_static = {K: torch.empty_like(v) for K, v in x_in.items()}
+    out_keys = list(outs)
+    y_host = {k: torch.empty(outs[k].shape, dtype=dtype).pin_memory() for k in out_keys}
+    y_static = {}
+
+    def step_api():
+        for m in mods:
+            y = m(x_static[m.in_features])
+            if comm is not None and m.parallel == "row":
+                comm.all_reduce(y)
+            y_static[(m.name_, m.out_features)] = y
+
+    step_api()
+    torch.cuda.synchronize()
+    g2 = graphs.capture(step_api) if not args.no_graph else None
+
+    def e2e_step():
+        for K, v in xin_host.items():
+            x_static[K].copy_(v, non_blocking=True)
+        (g2.replay if g2 is not None else step_api)()
+        for k in out_keys:
+            y_host[k].copy_(y_static[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if comm is not None:
+        t = torch.tensor([e2e_ms], device=device)
+        comm.all_reduce(t, op=comm.ReduceOp.MAX)
+        e2e_ms = t.item()
+    h2d = sum(v.numel() * v.element_size() for v in xin_host.values())
+    d2h = sum(v.numel() * v.element_size() for v in y_host.values())
+
+    # sanity: the e2e outputs equal the C-ABI outputs (same kernels)
+    for k in out_keys:
+        if not torch.equal(y_host[k].to(device), outs[k]) and world == 1:
+            raise RuntimeError(f"e2e output {k} differs from the C-ABI output")
+
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    per_launch_us = ms_per_step * 1e3 / launches_per_step
+    res = {
+        "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"{args.model} Linear4bit stack, NF4 + double-quant, blocksize 64, bs=1 decode: {layers} layers x "
+                        f"(q,k,v,o,gate,up,down) = {len(mods)} GEMVs/step per GPU" + (f", tensor-parallel tp{world} (NCCL all-reduce after o_proj/down_proj)" if world > 1 else ""),
+            "shapes": sorted({f"{m.out_features}x{m.in_features}" for m in mods}),
+            "packed_weight_bytes_per_gpu": packed_bytes, "algorithmic_bytes_per_step": step_bytes,
+            "l2_policy": "inputs larger than L2: every layer has its own weights (3.5 GB/step >> 126 MB L2), no flush needed",
+            "launch": ("CUDA graph replay" if graph is not None else "eager") + (" + programmatic dependent launch" if args.pdl else ""),
+            "parallelism": f"tp{world}" if world > 1 else "single GPU",
+        },
+        "pct_of_8TBs": round(value / world / 8000 * 100, 2),
+        "decode_linear_tok_s": round(1e3 / ms_per_step, 1),
+        "e2e": {"value": round(step_bytes / (e2e_ms * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(e2e_ms, 4),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "quantizations_b200.Linear4bit.forward x%d under quantizations_b200.graphs.capture, pinned-host x in / y out" % len(mods)},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "kernel": "q4::gemv_lut256_kernel<bf16, nested>", "achieved": round(value / world, 1), "peak": peak,
+                     "unit": "GB/s", "frac": round(value / world / peak, 4), "peak_source": peak_src,
+                     "avg_launch_us": round(per_launch_us, 3), "algorithmic_bytes_per_launch": step_bytes_local // launches_per_step,
+                     "traffic": None, "timed_blocks_ms": [round(t, 3) for t in times[:5]]},
+    }
+    if world == 1 and not args.no_cpu:
+        res["cpu_baseline"] = cpu_baseline(mods[:7], x_in, budget_s=args.cpu_seconds)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle/ port)
+
+
+def cpu_baseline(mods, x_in, budget_s=12.0):
+    """torch-CPU dequantize -> matmul of the same packed format on the host cores, on ONE decoder layer (7 matrices)."""
+    from oracle import q4_torch_cpu as cpu
+
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    host = []
+    for m in mods:
+        st = m.weight.quant_state
+        host.append(dict(packed=m.weight.data.cpu(), qabs=st.absmax.cpu(), code2=st.state2.code.cpu(), absmax2=st.state2.absmax.cpu(),
+                         offset=st.offset.cpu(), code=st.code.cpu(), shape=tuple(st.shape), x=x_in[m.in_features].cpu()))
+    nbytes = sum(algo_bytes(h["shape"][0], h["shape"][1]) for h in host)
+
+    def one_pass():
+        for h in host:
+            am = cpu.decode_absmax(h["qabs"], h["code2"], h["absmax2"], h["offset"])
+            cpu.linear(h["x"], h["packed"], am, h["code"], h["shape"])
+
+    one_pass()
+    t0, n = time.perf_counter(), 0
+    while True:
+        one_pass()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 20:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": round(nbytes / dt / 1e9, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one Llama-3-8B decoder layer (7 Linear4bit matrices, {nbytes} algorithmic bytes) x {n} passes, "
+                      f"oracle/q4_torch_cpu.py: unpack -> code lookup -> x decoded absmax -> F.linear fp32",
+            "ms_per_layer": round(dt * 1e3, 2)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+
+
+def run_reference(args, rank, world, device):
+    """The reference's own CUDA kernels (oracle/_ref/kbkim_lib.so + ref_shim.so, compiled from /root/reference for sm_100a)
+    on the same workload, driven with the reference's gemv_4bit call sequence (core.py:467-499): dequantize_blockwise of the
+    8-bit absmax, torch `+= offset`, then the GEMV kernel -- three launches per Linear.  bf16 uses the kernel instance the
+    reference instantiates but does not export (ops.cu:177), NF4 its code-table argument."""
+    if rank != 0:
+        return None
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    base = {"impl": "reference", "metric": METRIC, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic"}
+    have_gpu = torch.cuda.is_available()
+    if have_gpu and os.path.exists(os.path.join(ref_dir, "ref_shim.so")) and os.path.exists(os.path.join(ref_dir, "kbkim_lib.so")):
+        import quantizations_b200 as q
+
+        sys.path.insert(0, ref_dir)
+        import kbkim_lib
+
+        shim = ctypes.CDLL(os.path.join(ref_dir, "ref_shim.so"))
+        vp, i32 = ctypes.c_void_p, ctypes.c_int
+        shim.ref_gemv_bf16_async.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32]
+        shim.ref_gemv_bf16_async.restype = None
+        dtype = torch.bfloat16
+        cfg = LLAMA3_8B
+        layers = args.layers or cfg["layers"]
+        mods = build_stack(cfg, 1, 0, device, dtype, "nf4", layers, q)
+        step_bytes = sum(algo_bytes(m.out_features, m.in_features) for m in mods)
+        x_in = {K: torch.randn(1, 1, K, device=device, dtype=dtype) for K in {m.in_features for m in mods}}
+        outs = {(m.name_, m.out_features): torch.empty(1, 1, m.out_features, device=device, dtype=dtype) for m in mods}
+        absmax_buf = {m.weight.quant_state.absmax.numel(): torch.empty(m.weight.quant_state.absmax.numel(), device=device)
+                      for m in mods}
+
+        def step():
+            for m in mods:
+                st = m.weight.quant_state
+                am = absmax_buf[st.absmax.numel()]
+                kbkim_lib.cdequantize_blockwise_fp32(st.state2.code.data_ptr(), st.absmax.data_ptr(), st.state2.absmax.data_ptr(),
+                                                     am.data_ptr(), 256, st.absmax.numel())        # core.py:467
+                am += st.offset                                                                   # core.py:468
+                N, K = m.out_features, m.in_features
+                shim.ref_gemv_bf16_async(N, 1, K, x_in[K].data_ptr(), m.weight.data_ptr(), am.data_ptr(), st.code.data_ptr(),
+                                   outs[(m.name_, N)].data_ptr(), N, (K + 1) // 2, N, 64)          # core.py:486-499
+
+        # the reference launches on the legacy default stream (ops.cu:170): run everything there
+        with torch.cuda.stream(torch.cuda.default_stream(device)):
+            for _ in range(max(3, args.warmup)):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with ClockSampler(device.index) as clk:
+                e0.record()
+                for _ in range(args.steps):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step()
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        v = step_bytes / (ms * 1e-3) / 1e9
+        return {**base, "value": round(v, 1), "ms_per_step": round(ms, 4),
+                "config": {"workload": f"llama3-8b Linear4bit stack, NF4 + double-quant, bs=1 decode: {layers} layers x 7 = {len(mods)} "
+                                       "reference gemv_4bit calls/step (3 launches each), reference CUDA kernels rebuilt for sm_100a",
+                           "algorithmic_bytes_per_step": step_bytes},
+                "cpu_baseline": {"value": round(v, 1), "unit": "GB/s", "cores": 0, "kind": "reference",
+                                 "sample": "whole step; the reference's implementation of this path is CUDA (it has no CPU path), "
+                                           "so it is timed on the same B200 rather than on host cores"},
+                "e2e": {"value": round(step_bytes / (wall_ms * 1e-3) / 1e9, 1), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "clocks": clk.summary(), "gpu_launches": 3 * len(mods) * args.steps}
+    # no GPU / no compiled reference: the oracle port on host cores
+    from oracle import q4_oracle as orc  # noqa: F401
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    N, K = 4096, 4096
+    st = orc.quantize_4bit((rng.standard_normal((N, K)) * 0.02).astype(np.float32), 64, "nf4")
+    x = rng.standard_normal(K).astype(np.float32)
+    am = orc.state_absmax(st)
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 5 or n < 1:
+        orc.gemv_4bit(x, st["packed"], am, st["code"], N, K, 64, "bfloat16")
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    v = algo_bytes(N, K) / dt / 1e9
+    return {**base, "value": round(v, 3), "ms_per_step": round(dt * 1e3, 3), "config": {"workload": "4096x4096 NF4 GEMV, oracle port on host cores"},
+            "cpu_baseline": {"value": round(v, 3), "unit": "GB/s", "cores": orc.num_threads(), "kind": "port",
+                             "sample": f"{n} x 4096x4096 GEMV (oracle/q4_oracle.c, reference summation order)"},
+            "e2e": {"value": round(v, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama3-70b"])
+    ap.add_argument("--layers", type=int, default=0, help="decoder layers in the stack (0 = the model's own count)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", dest="pdl", action="store_false")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        if device.type == "cuda":
+            torch.cuda.set_device(device)
+        res = run_reference(args, 0, world, device)
+        print(json.dumps(res), flush=True)
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: quantizations_b200 has no CPU path (use --impl reference for the CPU oracle timing)")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    try:
+        res = run_ours(args, rank, world, device)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,4 +48,16 @@ int ref_dequant_fp4_fp32(unsigned char* A, float* absmax, float* out, int blocks
 int ref_dequant_8bit_fp32(float* code, unsigned char* A, float* absmax, float* out, int blocksize, int n)
 { dequantizeBlockwise<float, General8bit>(code, A, absmax, out, blocksize, n); return fin(); }
 
+// ---- asynchronous variants for bench.py --impl reference: no synchronisation, the reference's stock behaviour
+//      (launch on the legacy default stream and return, ops.cu:170).
+void ref_gemv_bf16_async(int m, int n, int k, void* A, unsigned char* B, float* absmax, float* code, void* out,
+                         int lda, int ldb, int ldc, int blocksize)
+{ gemm_4bit_inference_naive<__nv_bfloat16, 16>(m, n, k, (__nv_bfloat16*)A, B, absmax, code, (__nv_bfloat16*)out, lda, ldb, ldc, blocksize); }
+void ref_gemv_fp16_async(int m, int n, int k, void* A, unsigned char* B, float* absmax, float* code, void* out,
+                         int lda, int ldb, int ldc, int blocksize)
+{ gemm_4bit_inference_naive<half, 16>(m, n, k, (half*)A, B, absmax, code, (half*)out, lda, ldb, ldc, blocksize); }
+void ref_gemv_fp32_async(int m, int n, int k, float* A, unsigned char* B, float* absmax, float* code, float* out,
+                         int lda, int ldb, int ldc, int blocksize)
+{ gemm_4bit_inference_naive<float, 32>(m, n, k, A, B, absmax, code, out, lda, ldb, ldc, blocksize); }
+
 }  // extern "C"

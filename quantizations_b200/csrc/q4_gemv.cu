@@ -87,7 +87,7 @@ gemv_lut256_kernel(const T* __restrict__ x, const uint8_t* __restrict__ Bq, Absm
 {
     constexpr int U = kRowsInFlight;
     extern __shared__ __align__(16) uint8_t smem[];
-    // [0, 64K): lookup table.  [64K, ...): cross-warp partials, float[2][groups][kw][U].
+    // [0, 64K): lookup table.  [64K, ...): cross-warp partials, float[2][groups][kw][U]; then the staged source tables.
     float* s_part = reinterpret_cast<float*>(smem + kLutBytes);
 
     const int tid = threadIdx.x;
@@ -133,14 +133,19 @@ gemv_lut256_kernel(const T* __restrict__ x, const uint8_t* __restrict__ Bq, Absm
     issue(0);
 
     // ---- 2. build the per-lane-replicated table: 128-B segment 2b = half2{code[b>>4], code[b&15]} x32,
-    //         segment 2b+1 = code2[b] x32.  Threads write consecutive 16-B chunks (conflict-free).
+    //         segment 2b+1 = code2[b] x32.  The two source tables are staged in shared memory with ONE global round
+    //         trip; threads then write consecutive 16-B chunks (conflict-free).
+    float* s_src = s_part + 2 * groups * kw * U;  // [0,256): code2, [256,272): code
+    if (NESTED && tid < 256) s_src[tid] = __ldg(s.code2 + tid);
+    if (tid >= blockDim.x - 16) s_src[256 + (tid - (blockDim.x - 16))] = __ldg(code + (tid - (blockDim.x - 16)));
+    __syncthreads();
     for (int c = tid; c < kLutBytes / 16; c += blockDim.x) {
         const int seg = c >> 3, b = seg >> 1;
         uint32_t word;
         if (seg & 1) {
-            word = NESTED ? __float_as_uint(__ldg(s.code2 + b)) : 0u;
+            word = NESTED ? __float_as_uint(s_src[b]) : 0u;
         } else {
-            __half2 h = __halves2half2(__float2half_rn(__ldg(code + (b >> 4))), __float2half_rn(__ldg(code + (b & 15))));
+            __half2 h = __halves2half2(__float2half_rn(s_src[256 + (b >> 4)]), __float2half_rn(s_src[256 + (b & 15)]));
             word = *reinterpret_cast<uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(smem + c * 16) = make_uint4(word, word, word, word);
@@ -218,9 +223,8 @@ gemv_lut256_kernel(const T* __restrict__ x, const uint8_t* __restrict__ Bq, Absm
             keep += __shfl_xor_sync(0xffffffffu, keep, 4);
             keep += __shfl_xor_sync(0xffffffffu, keep, 2);
             keep += __shfl_xor_sync(0xffffffffu, keep, 1);
-            // lanes 8q..8q+7 now hold the warp's sum for row (q>>1) + 2*(q&1)  [q = lane>>3]
-            const int q = lane >> 3;
-            const int i = (q >> 1) + 2 * (q & 1);
+            // lanes 8i..8i+7 now hold the warp's sum for row i of the batch
+            const int i = lane >> 3;
             float total = keep;
             if (kw > 1) {
                 float* part = s_part + ((buf * groups + lgroup) * kw) * U;
@@ -338,7 +342,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
     if (fast) {
         const int groups = 16 / kw;
         const int threads = groups * kw * 32;
-        const size_t smem = kLutBytes + sizeof(float) * 2 * groups * kw * kRowsInFlight;
+        const size_t smem = kLutBytes + sizeof(float) * (2 * groups * kw * kRowsInFlight + 272);
         auto kern = nested ? gemv_lut256_kernel<T, true> : gemv_lut256_kernel<T, false>;
         static bool attr_set[2] = {false, false};
         if (!attr_set[nested]) {

@@ -270,7 +270,15 @@ def test_full_size_roundtrip_and_linearity(q, N, K, quant_type):
     # (1) re-quantising the dequantised weight with UNCOMPRESSED statistics must give back the same codes wherever the
     # bf16 rounding of absmax did not move the block maximum (it is the same value by (2)), i.e. everywhere.
     packed2, state2 = q.quantize_4bit(Wd, quant_type=quant_type, compress_statistics=False)
-    same = (packed2 == packed).float().mean().item()
+    p1, p2 = packed, packed2
+    if quant_type == "fp4":
+        # FP4 code 0b1000 decodes to -0.0, whose sign the quantiser does not see (x < 0 is false): it re-encodes as 0b0000
+        def fold(p):
+            hi, lo = p >> 4, p & 0xF
+            return (torch.where(hi == 8, torch.zeros_like(hi), hi) << 4) | torch.where(lo == 8, torch.zeros_like(lo), lo)
+
+        p1, p2 = fold(packed), fold(packed2)
+    same = (p2 == p1).float().mean().item()
     assert same > 0.999, f"only {same:.5f} of the packed bytes survive a dequantize->quantize round trip"
     # (3) + (4)
     torch.manual_seed(1)

@@ -1,0 +1,98 @@
+"""Host-side logic of the reference-shaped API (quantizations_b200/core.py, modules.py) that needs no GPU."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import quantizations_b200 as q
+
+
+def test_dynamic_map_is_the_reference_table():
+    m = q.create_dynamic_map()
+    assert m.dtype == torch.float32 and m.shape == (256,)
+    assert hashlib.sha256(m.numpy().astype("<f4").tobytes()).hexdigest() == \
+        "e732639a65f497b4ad684bb166a4467708255edd5207757de8b8f0c7e1fda89c"
+
+
+def test_get_4bit_type(oracle):
+    fp4 = q.get_4bit_type("fp4", device="cpu")
+    nf4 = q.get_4bit_type("nf4", device="cpu")
+    assert np.array_equal(fp4.numpy().view(np.uint32), oracle.fp4_table().view(np.uint32))
+    assert np.array_equal(nf4.numpy().view(np.uint32), oracle.nf4_table().view(np.uint32))
+    with pytest.raises(NotImplementedError):
+        q.get_4bit_type("int4", device="cpu")
+
+
+def test_cpu_tensors_raise_like_the_reference():
+    with pytest.raises(NotImplementedError):  # core.py:530-531
+        q.quantize_4bit(torch.randn(64, 64, dtype=torch.float16))
+    with pytest.raises(NotImplementedError):  # core.py:533-534 (checked after the device in the reference too)
+        q.quantize_4bit(torch.randn(64, 64, dtype=torch.float16), quant_type="int4")
+    with pytest.raises(ValueError):  # core.py:603-606
+        q.dequantize_4bit(torch.zeros(32, 1, dtype=torch.uint8), q.QuantState(absmax=torch.zeros(1)), blocksize=100)
+    with pytest.raises(ValueError):  # core.py:453-454
+        q.gemv_4bit(torch.randn(1, 1, 64), torch.zeros(32, 1, dtype=torch.uint8), state=None)
+    st = q.QuantState(absmax=torch.zeros(1), shape=torch.Size((1, 64)), code=torch.zeros(16), blocksize=64, quant_type="fp4")
+    with pytest.raises(ValueError):  # core.py:457-460: A must be a single vector
+        q.gemv_4bit(torch.randn(2, 64), torch.zeros(32, 1, dtype=torch.uint8), state=st)
+
+
+def test_params4bit_constructor_contract():
+    """HF/accelerate rebuild the parameter as Params4bit(value, requires_grad=False, **old.__dict__)."""
+    w = torch.randn(8, 16)
+    p = q.Params4bit(w, requires_grad=False, quant_type="nf4")
+    assert type(p).__name__ == "Params4bit" and isinstance(p, torch.nn.Parameter)
+    assert p.blocksize == 64 and p.quant_type == "nf4" and p.quant_storage == torch.uint8 and not p.bnb_quantized
+    assert p.quant_state is None and p.module is None and p.compress_statistics is True
+    p2 = q.Params4bit(p.data, requires_grad=False, **p.__dict__)
+    assert p2.quant_type == "nf4" and torch.equal(p2.data, w)
+    p3 = p.to("cpu")  # a CPU move does not quantise (core.py:176-190)
+    assert not p3.bnb_quantized and torch.equal(p3.data, w)
+    assert q.Params4bit().numel() == 0  # data=None -> empty (core.py:125-126)
+
+
+def test_linear4bit_constructor_contract():
+    lin = q.Linear4bit(32, 16, bias=False, compute_dtype=torch.bfloat16, compress_statistics=True, quant_type="nf4",
+                       quant_storage=torch.uint8)
+    assert isinstance(lin, torch.nn.Linear) and type(lin.weight).__name__ == "Params4bit"
+    assert lin.weight.module is lin and lin.compute_dtype == torch.bfloat16 and lin.quant_state is None
+    assert lin.in_features == 32 and lin.out_features == 16 and lin.bias is None and not lin.compute_type_is_set
+    lin.set_compute_type(torch.zeros(1, dtype=torch.float32))
+    assert lin.compute_dtype == torch.float32
+    lin.set_compute_type(torch.zeros(1, dtype=torch.float16))  # fp16 input leaves it alone (modules.py:120-122)
+    assert lin.compute_dtype == torch.float32
+    with pytest.raises(RuntimeError):
+        lin(torch.zeros(1, 1, 32))
+
+
+def test_quant_state_serialisation_roundtrip():
+    s2 = q.QuantState(absmax=torch.rand(3), code=q.create_dynamic_map(), blocksize=256, dtype=torch.float32)
+    st = q.QuantState(absmax=torch.randint(0, 255, (600,), dtype=torch.uint8), shape=torch.Size((20, 1920)),
+                      code=q.get_4bit_type("nf4", "cpu"), blocksize=64, quant_type="nf4", dtype=torch.bfloat16,
+                      offset=torch.tensor(0.031), state2=s2)
+    for packed in (False, True):
+        d = st.as_dict(packed=packed)
+        if packed:
+            assert set(d) == {"absmax", "quant_map", "nested_absmax", "nested_quant_map", "quant_state.bitsandbytes__nf4"}
+            d = {"weight." + k: v for k, v in d.items()}
+        r = q.QuantState.from_dict(d, device="cpu")
+        assert r.nested and r.quant_type == "nf4" and r.blocksize == 64 and r.dtype == torch.bfloat16
+        assert tuple(r.shape) == (20, 1920) and r.state2.blocksize == 256 and r.state2.dtype == torch.float32
+        assert torch.equal(r.absmax, st.absmax) and torch.equal(r.state2.absmax, s2.absmax)
+        assert torch.equal(r.code, st.code) and torch.equal(r.state2.code, s2.code)
+        assert abs(r.offset.item() - 0.031) < 1e-7
+    with pytest.raises(ValueError):
+        q.QuantState.from_dict({"foo": torch.zeros(1)}, device="cpu")
+
+
+def test_native_stats_validation():
+    st = q.QuantState(absmax=torch.zeros(4, dtype=torch.float16), blocksize=64)
+    with pytest.raises(ValueError):
+        st.native_stats()
+    st = q.QuantState(absmax=torch.zeros(4, dtype=torch.float32), blocksize=64)
+    s = st.native_stats()
+    assert s.absmax == st.absmax.data_ptr() and not s.qabsmax and s.blocksize2 == 0
+    assert st.native_stats() is s  # cached until the tensors move
+    st.to("cpu")
+    assert st._stats is None
