@@ -174,11 +174,13 @@ def run_ours(args, rank, world, device):
     def step_cabi():
         """one decode token's worth of Linear4bit GEMVs straight through the C ABI"""
         stream = torch.cuda.current_stream().cuda_stream
-        for m in mods:
+        for i, m in enumerate(mods):
             st = m.weight.quant_state
             out = outs[(m.name_, m.out_features)]
+            nxt = mods[(i + 1) % len(mods)].weight if args.prefetch else None  # the following Linear's packed weight
             rc = L.q4_gemv_4bit(x_in[m.in_features].data_ptr(), m.weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None,
-                                out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags, stream)
+                                out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags,
+                                None if nxt is None else nxt.data_ptr(), 0 if nxt is None else nxt.numel(), stream)
             if rc:
                 _lib.check(rc, "q4_gemv_4bit")
             if comm is not None and m.parallel == "row":
@@ -443,6 +445,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="decoder layers in the stack (0 = the model's own count)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false")
+    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false", help="do not hint the next layer's weight for L2 prefetch")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

@@ -60,6 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        import ctypes
+
+        ctypes.CDLL(LIB)  # unresolved symbols show up here, not on the GPU box
     if verbose:
         print(LIB)
     return LIB

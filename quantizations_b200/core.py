@@ -403,10 +403,13 @@ def gemv_4bit(
     state=None,
     bias: Optional[Tensor] = None,
     flags: int = _lib.Q4_GEMV_DEFAULT,
+    prefetch: Optional[Tensor] = None,
 ):
     """out[..., n] = sum_k A[..., k] * dequant(B)[n, k]  for a single activation vector.  reference core.py:426-504.
 
     One kernel launch (fused double-quant decode, optional fused bias) instead of the reference's three.
+    `prefetch` (optional) is a tensor the next call will stream -- usually the packed weight of the following layer; it is
+    pulled into L2 while this call computes (a hint only, see include/quantizations_b200.h).
     """
     if state is None:
         raise ValueError("state cannot None. gem_4bit( ) requires the state from quantize_4bit( )")
@@ -430,7 +433,9 @@ def gemv_4bit(
     code = lib.q4_gemv_4bit(
         A.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
         None if bias is None else bias.data_ptr(), out.data_ptr(), bout, k, state.blocksize,
-        _DTYPE_CODE[A.dtype], flags, torch.cuda.current_stream(A.device).cuda_stream,
+        _DTYPE_CODE[A.dtype], flags,
+        None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
+        torch.cuda.current_stream(A.device).cuda_stream,
     )
     if code != 0:
         check(code, "gemv_4bit")

@@ -34,6 +34,8 @@ int sm_count()
     return cached[dev];
 }
 
+extern unsigned long long* g_gemv_trace;  // q4_gemv.cu
+
 }  // namespace q4
 
 extern "C" {
@@ -47,7 +49,7 @@ int cgemm_4bit_inference_naive_fp32(int m, int n, int k, float* A, unsigned char
     if (n != 1) return Q4_ERR_SHAPE;
     if (ldb != (k + 1) / 2) return Q4_ERR_SHAPE;  // packed rows are contiguous (core.py:482)
     q4_absmax_t st = {absmax, nullptr, nullptr, nullptr, nullptr, 0};
-    return q4::gemv_4bit(A, B, &st, datatype, nullptr, out, m, k, blocksize, Q4_F32, Q4_GEMV_EXACT_F32, nullptr);
+    return q4::gemv_4bit(A, B, &st, datatype, nullptr, out, m, k, blocksize, Q4_F32, Q4_GEMV_EXACT_F32, nullptr, 0, nullptr);
 }
 
 int cquantize_blockwise_fp16_fp4(float* code, void* A, float* absmax, unsigned char* out, int blocksize, const int n)
@@ -100,10 +102,15 @@ int q4_dequantize_blockwise_4bit(const uint8_t* A, const q4_absmax_t* stats, voi
 }
 
 int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
-                 int64_t N, int64_t K, int blocksize, int dtype, int flags, void* stream)
+                 int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* prefetch, int64_t prefetch_bytes,
+                 void* stream)
 {
-    return q4::gemv_4bit(x, B, stats, code, bias, out, N, K, blocksize, dtype, flags, (cudaStream_t)stream);
+    return q4::gemv_4bit(x, B, stats, code, bias, out, N, K, blocksize, dtype, flags, prefetch, prefetch_bytes,
+                         (cudaStream_t)stream);
 }
+
+// developer hook (not declared in the public header): per-CTA phase timestamps of the GEMV kernel, see tools/
+void q4_debug_set_gemv_trace(unsigned long long* p) { q4::g_gemv_trace = p; }
 
 // ------------------------------------------------------------------------------------------------ 3. introspection
 

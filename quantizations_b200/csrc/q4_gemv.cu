@@ -29,6 +29,9 @@
 //
 //  gemv_generic_kernel (any even K, any valid blocksize, "exact" fp32 arithmetic: w = code*absmax, acc = fma(x,w,acc)
 //    as the reference's T=float instance does) -- warp per row, x staged in shared memory as fp32.
+#include <cstdlib>
+#include <type_traits>
+
 #include "q4_common.cuh"
 #include "q4_launch.h"
 
@@ -80,136 +83,312 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <typename T, bool NESTED>
+// A launch may cover up to kMaxMats weight matrices that share x and are stored back to back (packed bytes, 8-bit
+// absmax, outputs): q/k/v or gate/up of a decoder layer.  To the kernel they are one [rows, K] matrix; only the
+// double-quant offset (one scalar per quantize_4bit call) differs by row range.
+constexpr int kMaxMats = 4;
+struct GemvArgs {
+    const void* x;
+    const float* code;         // 16-entry 4-bit code table
+    const uint8_t* Bq;         // packed weight [rows, K/2]
+    AbsmaxView s;              // statistics (offset unused: see offsets[])
+    const float* offsets[kMaxMats];  // nested: per-matrix offset scalars (device pointers)
+    int row_end[kMaxMats];     // exclusive end row of each matrix (INT_MAX for unused slots)
+    void* out;                 // [rows]
+    const void* bias;          // [rows] or nullptr
+    const uint8_t* next;       // optional: bytes the NEXT launch will stream (pulled into L2 while this one computes)
+    int64_t next_bytes;
+    int rows, K;
+    int kw;      // warps that together cover one row: ceil(K / 2048)
+    int groups;  // row groups per CTA: blockDim / (32 * kw)
+    int rows_per_cta;
+    int debug_mode;             // developer experiments (env Q4_GEMV_DEBUG): 1 = skip the table lookups
+    unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA; nullptr = off
+};
+
+__device__ __forceinline__ void trace_mark(const GemvArgs& a, int slot)
+{
+    if (a.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[blockIdx.x * 8 + slot] = t;
+    }
+}
+
+// Shared-memory plan.  ONE PRMT splices {window high half, weight byte, lane*4} into an LDS address, which requires the
+// table to start at a constant offset from a 64-KB boundary of the CTA's shared window; the constant goes into the
+// LDS immediate.  Two layouts:
+//   COMPACT  the table sits at the very start of dynamic shared memory, which on sm_100 begins kDynBase = 1 KB into the
+//            window (probed once on the host, see dyn_smem_base()); [table 64K | x K*2 | partials | words | scratch].
+//            ~75-95 KB per CTA, so a 256-thread CTA leaves room for the NEXT kernel's CTA on the same SM: with
+//            programmatic dependent launch its prologue (table build, L2 prefetch) overlaps this kernel's main loop.
+//   ALIGNED  fallback if the probe disagrees: 128 KB requested, table at the 64-KB boundary inside it.
+constexpr int kSmemAligned = 128 * 1024;
+constexpr int kDynBase = 1024;
+
+template <int IMM> __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(IMM));
+    return v;
+}
+template <int IMM> __device__ __forceinline__ float lds_f32(uint32_t saddr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(saddr), "n"(IMM));
+    return v;
+}
+// TMA bulk prefetch of a byte range into L2 (UBLKPF.L2): fire-and-forget, no registers, no completion to wait for.
+// `bytes` is rounded down to a multiple of 16; `p` must be 16-byte aligned.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
+{
+    bytes &= ~15u;
+    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// spread a range over the lanes of one warp in 8-KB pieces
+__device__ __forceinline__ void prefetch_l2_range(const uint8_t* p, int64_t bytes, int lane)
+{
+    constexpr int64_t kPiece = 8192;
+    const int64_t skew = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;  // start at the next 16-byte boundary
+    p += skew;
+    bytes -= skew;
+    for (int64_t o = (int64_t)lane * kPiece; o < bytes; o += 32 * kPiece)
+        prefetch_l2_bulk(p + o, (uint32_t)(bytes - o < kPiece ? bytes - o : kPiece));
+}
+
+__global__ void probe_dyn_smem_base(uint32_t* out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    out[0] = (uint32_t)__cvta_generic_to_shared(smem);
+}
+
+template <typename T, bool NESTED, bool MULTI, bool COMPACT>
 __global__ void __launch_bounds__(512, 1)
-gemv_lut256_kernel(const T* __restrict__ x, const uint8_t* __restrict__ Bq, AbsmaxView s, const float* __restrict__ code,
-                   const T* __restrict__ bias, T* __restrict__ out, int N, int K, int kw, int groups)
+gemv_lut256_kernel(const GemvArgs a)
 {
     constexpr int U = kRowsInFlight;
-    extern __shared__ __align__(16) uint8_t smem[];
-    // [0, 64K): lookup table.  [64K, ...): cross-warp partials, float[2][groups][kw][U]; then the staged source tables.
-    float* s_part = reinterpret_cast<float*>(smem + kLutBytes);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int K = a.K, kw = a.kw, groups = a.groups, R = a.rows;
+    const uint32_t smem_saddr = (uint32_t)__cvta_generic_to_shared(smem);
+    // table address = lut_saddr + kImm + byte*256 + lane*4, with lut_saddr 64-KB aligned and kImm an LDS immediate
+    constexpr int kImm = COMPACT ? kDynBase : 0;
+    const uint32_t lut_saddr = COMPACT ? (smem_saddr & 0xFFFF0000u) : ((smem_saddr + 0xFFFFu) & 0xFFFF0000u);
+    uint8_t* lut = COMPACT ? smem : smem + (lut_saddr - smem_saddr);
+    uint8_t* rest = COMPACT ? smem + kLutBytes : smem;
+    uint4* s_x = reinterpret_cast<uint4*>(rest);
+    float* s_part = reinterpret_cast<float*>(rest + 2 * K);
+    uint32_t* s_words = reinterpret_cast<uint32_t*>(s_part + 2 * groups * kw * U);
+    float* s_red = reinterpret_cast<float*>(s_words + 512);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int lgroup = warp / kw;        // row group inside the CTA
     const int kpos = warp - lgroup * kw; // which 2048-wide K slice this warp covers
-    const int G = gridDim.x * groups;    // row groups in the grid
-    const int gid = blockIdx.x + gridDim.x * lgroup;  // consecutive rows land on different SMs
-    const int kblk = kpos * 32 + lane;   // this thread's 64-wide block inside a row
-    const int bpr = K >> 6;              // blocks per row
+    const int bpr = K >> 6;              // 64-wide blocks per row
+    const int kblk = kpos * 32 + lane;   // this thread's block inside a row
     const bool active = kblk < bpr;
+    const int kblk_c = active ? kblk : bpr - 1;  // inactive lanes load a valid address and multiply by x = 0
+
+    // This CTA owns the contiguous rows [row_lo, row_hi): one contiguous byte range of the packed weight.
+    const int row_lo = blockIdx.x * a.rows_per_cta;
+    const int row_hi = row_lo + a.rows_per_cta < R ? row_lo + a.rows_per_cta : R;
 
     // Let the next kernel in the stream start its own prologue (its griddepcontrol.wait still orders it after us).
     pdl_launch_dependents();
+    trace_mark(a, 0);
 
-    // ---- 1. put the first U rows' loads in flight (weights and statistics do not depend on the previous kernel)
+    // ---- 0b. the small latency-critical loads go out FIRST (requests are served in order: behind 64 KB of weight
+    //          loads they would wait microseconds): code table, code2 table, offsets.  Thread t < 256 builds pair word t;
+    //          thread 256 + t (or the same thread when the CTA has fewer than 512 threads) carries code2[t].
+    float tab_a = 0.0f, tab_b = 0.0f, tab_c = 0.0f;
+    if (tid < 256) {
+        tab_a = __ldg(a.code + (tid >> 4));
+        tab_b = __ldg(a.code + (tid & 15));
+    }
+    if (NESTED) {
+        if (nthr < 512) { if (tid < 256) tab_c = __ldg(a.s.code2 + tid); }
+        else if (tid < 512) { if (tid >= 256) tab_c = __ldg(a.s.code2 + (tid - 256)); }
+    }
+    float off[kMaxMats];
+#pragma unroll
+    for (int m = 0; m < kMaxMats; m++) off[m] = (NESTED && (MULTI || m == 0) && a.offsets[m]) ? __ldg(a.offsets[m]) : 0.0f;
+
+    // ---- 0. stream the whole slice HBM -> L2 now, decoupled from the SM's own progress: the demand loads below then
+    //         see L2 latency, and HBM has the entire matrix queued from the first microsecond.  Optionally also this
+    //         CTA's share of the bytes the NEXT launch will read (weights of the following Linear).
+    const bool do_prefetch = a.debug_mode != 2;
+    if (do_prefetch && warp == (nthr >> 5) - 1 && row_lo < row_hi) {
+        prefetch_l2_range(a.Bq + (int64_t)row_lo * (K >> 1), (int64_t)(row_hi - row_lo) * (K >> 1), lane);
+        if (NESTED) prefetch_l2_range(a.s.qabsmax + (int64_t)row_lo * bpr, (int64_t)(row_hi - row_lo) * bpr, lane);
+    }
+    if (do_prefetch && warp == (nthr >> 5) - 2 && a.next_bytes > 0) {
+        const int64_t share = ((a.next_bytes / gridDim.x) + 15) & ~(int64_t)15;
+        const int64_t lo = share * blockIdx.x;
+        const int64_t n = lo + share <= a.next_bytes ? share : a.next_bytes - lo;
+        if (n > 0) prefetch_l2_range(a.next + lo, n, lane);
+    }
+
+    // ---- 1. row bookkeeping.  Group g of the CTA takes rows row_lo + g, + groups, + 2*groups ...: every address advances
+    //         by a constant stride.  The first U rows are only requested AFTER the prologue's shared-memory work (step 4):
+    //         64 KB of outstanding LDG.256 per SM fill the load/store unit's queues and stall every LDS/STS behind them
+    //         (measured: the table build took 2-3 us that way); the L2 prefetch of step 0 has the data on its way already.
+    const int first = row_lo + lgroup;
+    const int rows_mine = first < row_hi ? (row_hi - first + groups - 1) / groups : 0;
+    int blk = first * bpr + kblk_c;      // block index of the next row to issue (rows * bpr < 2^31: dispatcher)
+    const int blk_stride = groups * bpr;
     u32x8 w[U];
     uint32_t qa[U];
     float a2[U];
-    const int rows_mine = gid < N ? (N - gid + G - 1) / G : 0;
-    auto issue = [&](int batch) {
+    auto issue_row = [&](int i) {
+        w[i] = ldg_stream_256(a.Bq + (int64_t)blk * 32);
+        if (NESTED) {
+            qa[i] = __ldg(a.s.qabsmax + blk);
+            a2[i] = __ldg(a.s.absmax2 + (blk >> a.s.shift2));
+        } else {
+            a2[i] = __ldg(a.s.absmax + blk);
+        }
+        blk += blk_stride;
+    };
+    trace_mark(a, 1);
+    // ---- 2. lookup table: stage the 512 distinct words (loaded in step 0b), then replicate each 32x:
+    //         128-B segment 2b = half2{code[b>>4], code[b&15]}, segment 2b+1 = code2[b] (fp32).
+    {
+        __half2 h = __halves2half2(__float2half_rn(tab_a), __float2half_rn(tab_b));
+        if (tid < 256) s_words[tid] = *reinterpret_cast<uint32_t*>(&h);
+        if (nthr < 512) {  // fewer than 512 threads: each thread stages its pair word and its code2 word
+            if (tid < 256) s_words[256 + tid] = __float_as_uint(tab_c);
+        } else if (tid >= 256) {
+            s_words[tid] = __float_as_uint(tab_c);
+        }
+    }
+    __syncthreads();
+    trace_mark(a, 7);
+    for (int c = tid; c < kLutBytes / 16; c += nthr) {
+        const int seg = c >> 3;
+        if (NESTED || !(seg & 1)) {
+            const uint32_t word = s_words[(seg >> 1) | ((seg & 1) << 8)];
+            *reinterpret_cast<uint4*>(lut + c * 16) = make_uint4(word, word, word, word);
+        }
+    }
+
+    // ---- 3. first U rows in flight, requested after the table build (see step 1) and before the dependency wait: under
+    //         programmatic dependent launch they stream in while the previous kernel is still running.
 #pragma unroll
-        for (int i = 0; i < U; i++) {
-            const int r = gid + (batch * U + i) * G;
-            if (active && r < N) {
-                const int64_t blk = (int64_t)r * bpr + kblk;
-                w[i] = ldg_stream_256(Bq + blk * 32);
-                if (NESTED) {
-                    qa[i] = __ldg(s.qabsmax + blk);
-                    a2[i] = __ldg(s.absmax2 + (blk >> s.shift2));
-                } else {
-                    a2[i] = __ldg(s.absmax + blk);
-                }
-            } else {
+    for (int i = 0; i < U; i++) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) w[i].v[j] = 0;
-                qa[i] = 0;
-                a2[i] = 0.0f;
-            }
+        for (int j = 0; j < 8; j++) w[i].v[j] = 0;
+        qa[i] = 0;
+        a2[i] = 0.0f;
+        if (i < rows_mine) issue_row(i);
+    }
+    __syncthreads();  // lookup table visible
+    trace_mark(a, 2);
+
+    // ---- 4. everything below may read the previous kernel's output
+    pdl_wait();
+    trace_mark(a, 3);
+
+    // ---- 5. x -> half2, scaled by one power of two so that max|x| lands in [1,2) (fp16 cannot overflow; the products
+    //         are accumulated 8 deep in fp16, then in fp32).  Done once per CTA: threads convert 8 elements per step and
+    //         store them swizzled, then each thread fetches the 64 values of its own k-slice into registers.
+    const T* xg = reinterpret_cast<const T*>(a.x);
+    const int nchunk = K >> 3;  // 8-element chunks
+    auto load_chunk = [&](int c, float (&v)[8]) {
+        if constexpr (sizeof(T) == 2) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(xg) + c);
+            const float2 f0 = unpack2<T>(q.x), f1 = unpack2<T>(q.y), f2 = unpack2<T>(q.z), f3 = unpack2<T>(q.w);
+            v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+        } else {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(xg) + 2 * c);
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(xg) + 2 * c + 1);
+            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
         }
     };
-    issue(0);
-
-    // ---- 2. build the per-lane-replicated table: 128-B segment 2b = half2{code[b>>4], code[b&15]} x32,
-    //         segment 2b+1 = code2[b] x32.  The two source tables are staged in shared memory with ONE global round
-    //         trip; threads then write consecutive 16-B chunks (conflict-free).
-    float* s_src = s_part + 2 * groups * kw * U;  // [0,256): code2, [256,272): code
-    if (NESTED && tid < 256) s_src[tid] = __ldg(s.code2 + tid);
-    if (tid >= blockDim.x - 16) s_src[256 + (tid - (blockDim.x - 16))] = __ldg(code + (tid - (blockDim.x - 16)));
+    float m = 0.0f;
+    for (int c = tid; c < nchunk; c += nthr) {
+        float v[8];
+        load_chunk(c, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) m = fmaxf(m, fabsf(v[j]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
     __syncthreads();
-    for (int c = tid; c < kLutBytes / 16; c += blockDim.x) {
-        const int seg = c >> 3, b = seg >> 1;
-        uint32_t word;
-        if (seg & 1) {
-            word = NESTED ? __float_as_uint(s_src[b]) : 0u;
-        } else {
-            __half2 h = __halves2half2(__float2half_rn(s_src[256 + (b >> 4)]), __float2half_rn(s_src[256 + (b & 15)]));
-            word = *reinterpret_cast<uint32_t*>(&h);
+    m = 0.0f;
+    for (int i = 0; i < (nthr >> 5); i++) m = fmaxf(m, s_red[i]);
+    int e = (int)((__float_as_uint(m) >> 23) & 0xFF);  // biased exponent of the largest |x|
+    e = e < 1 ? 1 : (e > 253 ? 253 : e);
+    const float scale = __uint_as_float((uint32_t)(254 - e) << 23);  // 2^(127-e)
+    const float unscale = __uint_as_float((uint32_t)e << 23);        // 2^(e-127)
+    for (int c = tid; c < nchunk; c += nthr) {  // second pass hits L1
+        float v[8];
+        load_chunk(c, v);
+        uint32_t h[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            __half2 hh = __floats2half2_rn(v[2 * j] * scale, v[2 * j + 1] * scale);
+            h[j] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        *reinterpret_cast<uint4*>(smem + c * 16) = make_uint4(word, word, word, word);
+        const int kb = c >> 3, j = c & 7;
+        s_x[kb * 8 + (j ^ (kb & 7))] = make_uint4(h[0], h[1], h[2], h[3]);  // swizzle: conflict-free both ways
     }
-    const float offset = NESTED ? __ldg(s.offset) : 0.0f;
-
-    // ---- 3. everything below may read the previous kernel's output
-    pdl_wait();
-
-    // ---- 4. this thread's 64 activations -> half2 registers, scaled by a power of two so |x| < 2
+    __syncthreads();
     uint32_t xh[32];
-    float unscale = 1.0f;
-    if (active) {
-        float xf[64];
-        load_x64<T>(x + (int64_t)kblk * 64, xf);
-        float m = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 64; j++) m = fmaxf(m, fabsf(xf[j]));
-        int e = (int)((__float_as_uint(m) >> 23) & 0xFF);  // biased exponent of the largest |x|
-        e = e < 1 ? 1 : (e > 253 ? 253 : e);
-        const float scale = __uint_as_float((uint32_t)(254 - e) << 23);  // 2^(127-e): m*scale in [1,2)
-        unscale = __uint_as_float((uint32_t)e << 23);                     // 2^(e-127)
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            __half2 h = __floats2half2_rn(xf[2 * j] * scale, xf[2 * j + 1] * scale);
-            xh[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; j++) xh[j] = 0;
+    for (int j = 0; j < 8; j++) {
+        uint4 v = s_x[kblk_c * 8 + (j ^ (kblk_c & 7))];
+        if (!active) v = make_uint4(0, 0, 0, 0);
+        xh[4 * j] = v.x; xh[4 * j + 1] = v.y; xh[4 * j + 2] = v.z; xh[4 * j + 3] = v.w;
     }
-    __syncthreads();  // table visible
 
-    const uint32_t lane4 = lane * 4;  // < 256: the upper three bytes are the zeros PRMT index 5 picks up
+    trace_mark(a, 4);
+    // PRMT operand: {lane*4, 0, window bits 16-23, window bits 24-31}; selector 0x76i4 splices weight byte i into
+    // byte 1 -> lut_saddr + byte*256 + lane*4, a complete shared address
+    const uint32_t lane_base = lut_saddr | (uint32_t)(lane * 4);
     const int nbatch = (rows_mine + U - 1) / U;
     int buf = 0;
 
     for (int batch = 0; batch < nbatch; batch++) {
         float t[U];
+        const int n0 = batch * U;
 #pragma unroll
         for (int i = 0; i < U; i++) {
-            uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+            t[i] = 0.0f;
+            if (n0 + i < rows_mine) {  // warp-uniform: rows past the end cost nothing
+                uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+                if (a.debug_mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t wj = w[i].v[j];
-                // table offset = byte*256 + lane*4: one PRMT splices weight byte b into byte 1 above lane*4
-                acc0 = hfma2(lut_at(smem, __byte_perm(wj, lane4, 0x5504)), xh[4 * j + 0], acc0);
-                acc1 = hfma2(lut_at(smem, __byte_perm(wj, lane4, 0x5514)), xh[4 * j + 1], acc1);
-                acc2 = hfma2(lut_at(smem, __byte_perm(wj, lane4, 0x5524)), xh[4 * j + 2], acc2);
-                acc3 = hfma2(lut_at(smem, __byte_perm(wj, lane4, 0x5534)), xh[4 * j + 3], acc3);
+                    for (int j = 0; j < 8; j++) acc0 ^= w[i].v[j];
+                } else
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t wj = w[i].v[j];
+                    acc0 = hfma2(lds_u32<kImm>(__byte_perm(wj, lane_base, 0x7604)), xh[4 * j + 0], acc0);
+                    acc1 = hfma2(lds_u32<kImm>(__byte_perm(wj, lane_base, 0x7614)), xh[4 * j + 1], acc1);
+                    acc2 = hfma2(lds_u32<kImm>(__byte_perm(wj, lane_base, 0x7624)), xh[4 * j + 2], acc2);
+                    acc3 = hfma2(lds_u32<kImm>(__byte_perm(wj, lane_base, 0x7634)), xh[4 * j + 3], acc3);
+                }
+                const uint32_t sum = hadd2(hadd2(acc0, acc1), hadd2(acc2, acc3));
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&sum));
+                float am;
+                if (NESTED) {
+                    float o = off[0];
+                    if (MULTI) {
+                        const int r = first + (n0 + i) * groups;
+                        o = r < a.row_end[0] ? off[0] : (r < a.row_end[1] ? off[1] : (r < a.row_end[2] ? off[2] : off[3]));
+                    }
+                    const float c2 = lds_f32<kImm + 128>(__byte_perm(qa[i], lane_base, 0x7604));
+                    am = __fadd_rn(__fmul_rn(c2, a2[i]), o);  // reference: kernels.cu:552 then core.py:468
+                } else {
+                    am = a2[i];
+                }
+                t[i] = (f.x + f.y) * (am * unscale);
+                // register rotation: row i of the NEXT batch streams into the registers this row just vacated
+                if (n0 + U + i < rows_mine) issue_row(i);
             }
-            const uint32_t sum = hadd2(hadd2(acc0, acc1), hadd2(acc2, acc3));
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&sum));
-            float am;
-            if (NESTED) {
-                const float c2 = __uint_as_float(lut_at(smem, __byte_perm(qa[i], lane4, 0x5504) + 128));
-                am = __fadd_rn(__fmul_rn(c2, a2[i]), offset);  // reference: kernels.cu:552 then core.py:468
-            } else {
-                am = a2[i];
-            }
-            t[i] = (f.x + f.y) * (am * unscale);
         }
-        // next batch's loads go out before the reduction so they overlap it
-        if (batch + 1 < nbatch) issue(batch + 1);
 
         // ---- lane reduction: U=4 row sums over 32 lanes with a transposing butterfly
         {
@@ -236,15 +415,21 @@ gemv_lut256_kernel(const T* __restrict__ x, const uint8_t* __restrict__ Bq, Absm
                 }
                 buf ^= 1;
             }
-            const int r = gid + (batch * U + i) * G;
-            if (kpos == 0 && (lane & 7) == 0 && r < N) {
+            if (kpos == 0 && (lane & 7) == 0 && n0 + i < rows_mine) {
+                const int r = first + (n0 + i) * groups;
+                T* out = reinterpret_cast<T*>(a.out);
+                const T* bias = reinterpret_cast<const T*>(a.bias);
                 T y = Elem<T>::from_f32(total);
                 if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + Elem<T>::to_f32(bias[r]));  // torch `out += bias`
                 out[r] = y;
             }
         }
+        if (batch == 0) trace_mark(a, 5);
     }
+    trace_mark(a, 6);
 }
+
+unsigned long long* g_gemv_trace = nullptr;  // set by q4_debug_set_gemv_trace (developer tool, not part of the ABI)
 
 // ------------------------------------------------------------------------------------------------ generic path
 
@@ -329,31 +514,74 @@ static int launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t
 
 template <typename T>
 static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, const float* code, const T* bias, T* out,
-                         int64_t N, int64_t K, int blocksize, int flags, cudaStream_t stream)
+                         int64_t N, int64_t K, int blocksize, int flags, const void* next, int64_t next_bytes, cudaStream_t stream)
 {
     const AbsmaxView v = make_view(st);
     const bool nested = st->qabsmax != nullptr;
     const bool pdl = flags & Q4_GEMV_PDL;
     const int sms = sm_count();
     const int kw = (int)((K + 2047) / 2048);
-    const bool fast = !(flags & Q4_GEMV_EXACT_F32) && blocksize == 64 && (K % 64) == 0 && kw <= 16 && N < (1 << 30) &&
+    const bool fast = !(flags & Q4_GEMV_EXACT_F32) && blocksize == 64 && (K % 64) == 0 && kw <= 16 && K >= 64 && N * (K / 64) < (1ll << 31) && N < (1 << 30) &&
                       (reinterpret_cast<uintptr_t>(B) & 31) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                       (!nested || st->blocksize2 >= 64);
     if (fast) {
-        const int groups = 16 / kw;
+        static const int env_warps = getenv("Q4_GEMV_WARPS") ? atoi(getenv("Q4_GEMV_WARPS")) : 16;
+        const int warps = kw > env_warps ? kw : env_warps;  // warps per CTA
+        int groups = warps / kw;
+        while (groups * kw * 32 < 256) groups++;  // the table staging needs at least 256 threads
         const int threads = groups * kw * 32;
-        const size_t smem = kLutBytes + sizeof(float) * (2 * groups * kw * kRowsInFlight + 272);
-        auto kern = nested ? gemv_lut256_kernel<T, true> : gemv_lut256_kernel<T, false>;
-        static bool attr_set[2] = {false, false};
-        if (!attr_set[nested]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            if (e != cudaSuccess) return (int)e;
-            attr_set[nested] = true;
+        // shared-memory layout: COMPACT when dynamic shared memory starts kDynBase into the window (probed once)
+        static int dyn_base = -1;
+        if (dyn_base < 0) {
+            uint32_t* d = nullptr;
+            uint32_t h = 0;
+            if (cudaMalloc(&d, 4) == cudaSuccess) {
+                probe_dyn_smem_base<<<1, 32, 1024, stream>>>(d);
+                if (cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess)
+                    dyn_base = (int)(h & 0xFFFFu);
+                cudaFree(d);
+            }
+            if (dyn_base < 0) dyn_base = 0;
         }
+        static const int env_aligned = getenv("Q4_GEMV_ALIGNED") ? atoi(getenv("Q4_GEMV_ALIGNED")) : 0;
+        const size_t rest = 2 * (size_t)K + sizeof(float) * (2 * groups * kw * kRowsInFlight + 512 + 32);
+        const bool compact = dyn_base == kDynBase && !env_aligned && kLutBytes + rest <= 200 * 1024;
+        if (!compact && rest > 63 * 1024) return Q4_ERR_SHAPE;
+        const size_t smem = compact ? kLutBytes + rest : kSmemAligned;
+        auto kern = compact ? (nested ? gemv_lut256_kernel<T, true, false, true> : gemv_lut256_kernel<T, false, false, true>)
+                            : (nested ? gemv_lut256_kernel<T, true, false, false> : gemv_lut256_kernel<T, false, false, false>);
+        static bool attr_set[2][2] = {{false, false}, {false, false}};
+        if (!attr_set[compact][nested]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, compact ? 200 * 1024 : kSmemAligned);
+            if (e != cudaSuccess) return (int)e;
+            attr_set[compact][nested] = true;
+        }
+        GemvArgs a = {};
+        a.x = x;
+        a.code = code;
+        a.Bq = B;
+        a.s = v;
+        for (int m = 0; m < kMaxMats; m++) {
+            a.offsets[m] = nullptr;
+            a.row_end[m] = 0x7fffffff;
+        }
+        a.offsets[0] = v.offset;
+        a.out = out;
+        a.bias = bias;
+        a.rows = (int)N;
+        a.K = (int)K;
+        a.kw = kw;
+        a.groups = groups;
+        a.trace = g_gemv_trace;
+        static const int env_debug = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
+        a.debug_mode = env_debug;
+        a.next = (reinterpret_cast<uintptr_t>(next) & 15) == 0 ? (const uint8_t*)next : nullptr;
+        a.next_bytes = a.next ? next_bytes : 0;
         const int64_t want = (N + groups - 1) / groups;  // CTAs needed to give every group one row
-        const int grid = (int)(want < sms ? want : sms);
-        return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, pdl, x, B, v, code, bias, out, (int)N, (int)K, kw,
-                          groups);
+        int grid = (int)(want < sms ? want : sms);
+        a.rows_per_cta = (int)((N + grid - 1) / grid);
+        grid = (int)((N + a.rows_per_cta - 1) / a.rows_per_cta);
+        return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, pdl, a);
     }
     // generic: x as fp32 in shared memory
     const size_t smem = 128 + sizeof(float) * (size_t)K;
@@ -368,7 +596,8 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
 }
 
 int gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
-              int64_t N, int64_t K, int blocksize, int dtype, int flags, cudaStream_t stream)
+              int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* next, int64_t next_bytes,
+              cudaStream_t stream)
 {
     if (!valid_blocksize(blocksize)) return Q4_ERR_BLOCKSIZE;
     if (N < 0 || K < 0 || (K & 1)) return Q4_ERR_SHAPE;
@@ -379,13 +608,13 @@ int gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const f
         case Q4_F32:
             // fp32 activations ask for fp32 arithmetic (the reference's only wired instance): exact path
             return gemv_dispatch<float>((const float*)x, B, stats, code, (const float*)bias, (float*)out, N, K, blocksize,
-                                        flags | Q4_GEMV_EXACT_F32, stream);
+                                        flags | Q4_GEMV_EXACT_F32, next, next_bytes, stream);
         case Q4_F16:
             return gemv_dispatch<__half>((const __half*)x, B, stats, code, (const __half*)bias, (__half*)out, N, K, blocksize,
-                                         flags, stream);
+                                         flags, next, next_bytes, stream);
         case Q4_BF16:
             return gemv_dispatch<__nv_bfloat16>((const __nv_bfloat16*)x, B, stats, code, (const __nv_bfloat16*)bias,
-                                                (__nv_bfloat16*)out, N, K, blocksize, flags, stream);
+                                                (__nv_bfloat16*)out, N, K, blocksize, flags, next, next_bytes, stream);
         default: return Q4_ERR_DTYPE;
     }
 }

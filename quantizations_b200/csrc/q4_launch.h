@@ -22,7 +22,8 @@ int dequantize_8bit(const float* code, const uint8_t* A, const float* absmax, fl
 int dequantize_4bit(const uint8_t* A, const q4_absmax_t* stats, void* out, int blocksize, int64_t n, int quant_type,
                     int out_dtype, cudaStream_t stream);
 int gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
-              int64_t N, int64_t K, int blocksize, int dtype, int flags, cudaStream_t stream);
+              int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* next, int64_t next_bytes,
+              cudaStream_t stream);
 
 int sm_count();  // cached multiprocessor count of the current device
 

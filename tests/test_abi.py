@@ -61,19 +61,19 @@ def test_argument_errors_are_reported_not_launched(L):
     assert L.q4_dequantize_blockwise_4bit(one, ctypes.byref(st), one, 64, 64, 0, 1, null) == -3
     # shapes: negative n, odd K, n != 1 for the reference-named GEMV
     assert L.q4_quantize_blockwise_4bit(one, one, one, 64, -1, 1, 1, null) == -4
-    assert L.q4_gemv_4bit(one, one, ctypes.byref(st), one, null, one, 8, 7, 64, 1, 0, null) == -4
+    assert L.q4_gemv_4bit(one, one, ctypes.byref(st), one, null, one, 8, 7, 64, 1, 0, null, 0, null) == -4
     assert L.cgemm_4bit_inference_naive_fp32(8, 2, 64, one, one, one, one, one, 8, 32, 8, 64) == -4
     # NULL pointers
     assert L.q4_quantize_blockwise_4bit(null, one, one, 64, 64, 1, 1, null) == -5
-    assert L.q4_gemv_4bit(one, one, None, one, null, one, 8, 64, 64, 1, 0, null) == -5
+    assert L.q4_gemv_4bit(one, one, None, one, null, one, 8, 64, 64, 1, 0, null, 0, null) == -5
     nested_missing = AbsmaxStats(None, 4096, None, None, None, 256)
-    assert L.q4_gemv_4bit(one, one, ctypes.byref(nested_missing), one, null, one, 8, 64, 64, 1, 0, null) == -5
+    assert L.q4_gemv_4bit(one, one, ctypes.byref(nested_missing), one, null, one, 8, 64, 64, 1, 0, null, 0, null) == -5
     # alignment
     assert L.q4_quantize_blockwise_4bit(ctypes.c_void_p(4100), one, one, 64, 64, 1, 1, null) == -6
     # empty inputs are a no-op success (n == 0)
     assert L.q4_quantize_blockwise_4bit(null, null, null, 64, 0, 1, 1, null) == 0
     assert L.q4_dequantize_blockwise_4bit(null, ctypes.byref(st), null, 64, 0, 1, 1, null) == 0
-    assert L.q4_gemv_4bit(one, one, ctypes.byref(st), one, null, one, 0, 64, 64, 1, 0, null) == 0
+    assert L.q4_gemv_4bit(one, one, ctypes.byref(st), one, null, one, 0, 64, 64, 1, 0, null, 0, null) == 0
     assert b"blocksize" in L.q4_error_string(-1) and L.q4_error_string(0) == b"success"
 
 

@@ -72,6 +72,9 @@ def main():
     ap.add_argument("--iters", type=int, default=400)
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--only", default="", help="NxK: time just this shape")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--next", action="store_true", help="hint the next matrix of the pool for L2 prefetch")
     a = ap.parse_args()
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.dtype]
     dev = torch.device("cuda:0")
@@ -85,7 +88,8 @@ def main():
     if not a.no_ref and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_shim.so")):
         shim = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "ref_shim.so"))
     print(f"device {torch.cuda.get_device_name(0)}  dtype {a.dtype} quant {a.quant}  peak {peak} GB/s  flags {a.flags}")
-    for N, K in SHAPES:
+    shapes = [tuple(int(v) for v in a.only.split("x"))] if a.only else SHAPES
+    for N, K in shapes:
         per = N * K // 2
         nmat = max(2, min(64, a.pool_mb * (1 << 20) // per))
         torch.manual_seed(0)
@@ -107,13 +111,14 @@ def main():
 
         def ours(i):
             L.q4_gemv_4bit(x.data_ptr(), ptrs[i % nmat], stats, st0.code.data_ptr(), None, out.data_ptr(), N, K, 64, dcode,
-                           a.flags, torch.cuda.current_stream().cuda_stream)
+                           a.flags, ptrs[(i + 1) % nmat] if a.next else None, per if a.next else 0,
+                           torch.cuda.current_stream().cuda_stream)
 
         def ours_py(i):
             q.gemv_4bit(x, mats[i % nmat], out=out, state=st0)
 
         tp = time_fn(ours_py, a.iters)
-        t = time_graph(ours, nmat * 2)
+        t = time_fn(ours, a.iters) if a.no_graph else time_graph(ours, nmat * 2)
         B = algo_bytes(N, K, x.element_size())
         line = f"{N:6d}x{K:<6d} ours(graph) {t:8.2f} us  {B / t / 1e3:8.1f} GB/s ({B / t / 1e3 / peak * 100:5.1f}% of measured peak)  eager core.gemv_4bit {tp:8.2f} us"
         if shim is not None:

@@ -1,0 +1,53 @@
+"""Developer tool: phase timeline of the GEMV kernel (globaltimer stamps written by thread 0 of every CTA)."""
+import ctypes, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import quantizations_b200 as q
+from quantizations_b200 import _lib
+
+N, K = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "14336x4096").split("x"))
+flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+L = _lib.lib()
+L.q4_debug_set_gemv_trace.argtypes = [ctypes.c_void_p]
+dev = torch.device("cuda:0")
+W = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
+packed, st = q.quantize_4bit(W, quant_type="nf4")
+mats = [packed.clone() for _ in range(8)]
+x = torch.randn(1, 1, K, device=dev, dtype=torch.bfloat16)
+out = torch.empty(1, 1, N, device=dev, dtype=torch.bfloat16)
+NL = 6
+traces = [torch.zeros(148 * 8, dtype=torch.int64, device=dev) for _ in range(NL)]
+stream = torch.cuda.current_stream().cuda_stream
+def launch(i, tr):
+    L.q4_debug_set_gemv_trace(tr.data_ptr() if tr is not None else None)
+    L.q4_gemv_4bit(x.data_ptr(), mats[i % 8].data_ptr(), st.native_stats(), st.code.data_ptr(), None, out.data_ptr(), N, K, 64, 2,
+                   flags, None, 0, stream)
+for i in range(10):
+    launch(i, None)
+torch.cuda.synchronize()
+# flush L2
+junk = torch.empty(256 << 20, dtype=torch.uint8, device=dev); junk.fill_(1); torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    stream = s.cuda_stream
+    with torch.cuda.graph(g, stream=s):
+        for i in range(NL):
+            launch(i, traces[i])
+g.replay(); torch.cuda.synchronize()
+junk.fill_(2); torch.cuda.synchronize()
+g.replay(); torch.cuda.synchronize()
+L.q4_debug_set_gemv_trace(None)
+names = ["start", "issued", "lut", "waited", "x ready", "batch0", "end", "words"]
+t0 = None
+for i, tr in enumerate(traces):
+    t = tr.cpu().view(148, 8)
+    t = t[t[:, 0] > 0]
+    if t0 is None:
+        t0 = int(t[:, 0].min())
+    rel = (t - t0).float() / 1e3
+    print(f"launch {i}: CTAs {t.shape[0]}")
+    for j, n in enumerate(names):
+        col = rel[:, j]
+        print(f"   {n:8s} min {col.min():8.2f}  median {col.median():8.2f}  max {col.max():8.2f} us")
