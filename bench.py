@@ -169,22 +169,53 @@ def run_ours(args, rank, world, device):
 
         comm = dist
 
-    flags = _lib.Q4_GEMV_PDL if args.pdl else 0
+    pdl = _lib.Q4_GEMV_PDL if args.pdl else 0
+    # A decoder layer's Linear4bit calls form a small DAG: q/k/v share their input and are independent of each other, so do
+    # gate/up; o_proj and down_proj each depend on what precedes them.  The step is launched exactly like that: independent
+    # GEMVs go to parallel streams (parallel branches of the CUDA graph) with Q4_GEMV_SHARE_SM so they are co-resident on
+    # every SM; dependent ones follow in stream order with programmatic dependent launch.
+    side = [torch.cuda.Stream(device=device) for _ in range(2)] if args.branches else []
+    branch_of = {"q_proj": 0, "k_proj": 1, "v_proj": 2, "o_proj": 0, "gate_proj": 0, "up_proj": 1, "down_proj": 0}
+    forks = {"q_proj", "gate_proj"}            # a parallel section starts here ...
+    joins = {"o_proj", "down_proj"}            # ... and has ended before these
+
+    def run_stack(launch):
+        """walk the stack in model order, placing each Linear on its branch; `launch(i, m, flags)` issues the work"""
+        main = torch.cuda.current_stream()
+        for i, m in enumerate(mods):
+            b = branch_of[m.name_] if side else 0
+            if side and m.name_ in forks:
+                for st in side:
+                    st.wait_stream(main)
+            if side and m.name_ in joins:
+                for st in side:
+                    main.wait_stream(st)
+            shared = side and m.name_ not in joins
+            flags = pdl | (_lib.Q4_GEMV_SHARE_SM if shared else 0)
+            if b == 0:
+                launch(i, m, flags)
+            else:
+                with torch.cuda.stream(side[b - 1]):
+                    launch(i, m, flags)
+        for st in side:
+            main.wait_stream(st)
+
+    def launch_cabi(i, m, flags):
+        st = m.weight.quant_state
+        out = outs[(m.name_, m.out_features)]
+        nxt = mods[(i + 1) % len(mods)].weight if args.prefetch else None  # the following Linear's packed weight
+        rc = L.q4_gemv_4bit(x_in[m.in_features].data_ptr(), m.weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None,
+                            out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags,
+                            None if nxt is None else nxt.data_ptr(), 0 if nxt is None else nxt.numel(),
+                            torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc, "q4_gemv_4bit")
+        if comm is not None and m.parallel == "row":
+            comm.all_reduce(out)
 
     def step_cabi():
         """one decode token's worth of Linear4bit GEMVs straight through the C ABI"""
-        stream = torch.cuda.current_stream().cuda_stream
-        for i, m in enumerate(mods):
-            st = m.weight.quant_state
-            out = outs[(m.name_, m.out_features)]
-            nxt = mods[(i + 1) % len(mods)].weight if args.prefetch else None  # the following Linear's packed weight
-            rc = L.q4_gemv_4bit(x_in[m.in_features].data_ptr(), m.weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None,
-                                out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags,
-                                None if nxt is None else nxt.data_ptr(), 0 if nxt is None else nxt.numel(), stream)
-            if rc:
-                _lib.check(rc, "q4_gemv_4bit")
-            if comm is not None and m.parallel == "row":
-                comm.all_reduce(out)
+        run_stack(launch_cabi)
 
     # ---- value: CUDA-graph replay of the step, device-timed
     n0 = _lib.launch_count()
@@ -233,12 +264,16 @@ def run_ours(args, rank, world, device):
     y_host = {k: torch.empty(outs[k].shape, dtype=dtype).pin_memory() for k in out_keys}
     y_static = {}
 
+    def launch_api(i, m, flags):
+        m.gemv_flags = flags
+        m.prefetch_next = mods[(i + 1) % len(mods)].weight if args.prefetch else None
+        y = m(x_static[m.in_features])
+        if comm is not None and m.parallel == "row":
+            comm.all_reduce(y)
+        y_static[(m.name_, m.out_features)] = y
+
     def step_api():
-        for m in mods:
-            y = m(x_static[m.in_features])
-            if comm is not None and m.parallel == "row":
-                comm.all_reduce(y)
-            y_static[(m.name_, m.out_features)] = y
+        run_stack(launch_api)
 
     step_api()
     torch.cuda.synchronize()
@@ -286,7 +321,9 @@ def run_ours(args, rank, world, device):
             "shapes": sorted({f"{m.out_features}x{m.in_features}" for m in mods}),
             "packed_weight_bytes_per_gpu": packed_bytes, "algorithmic_bytes_per_step": step_bytes,
             "l2_policy": "inputs larger than L2: every layer has its own weights (3.5 GB/step >> 126 MB L2), no flush needed",
-            "launch": ("CUDA graph replay" if graph is not None else "eager") + (" + programmatic dependent launch" if args.pdl else ""),
+            "launch": ("CUDA graph replay" if graph is not None else "eager") + (" + programmatic dependent launch" if args.pdl else "")
+                      + (", q/k/v and gate/up as parallel graph branches (co-resident CTAs)" if args.branches else "")
+                      + (", next-layer weight L2 prefetch hint" if args.prefetch else ""),
             "parallelism": f"tp{world}" if world > 1 else "single GPU",
         },
         "pct_of_8TBs": round(value / world / 8000 * 100, 2),
@@ -446,6 +483,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false", help="do not hint the next layer's weight for L2 prefetch")
+    ap.add_argument("--branches", action="store_true",
+                    help="launch q/k/v and gate/up as parallel graph branches (measured slower than one stream + PDL: the graph's "
+                         "cross-stream edges cost more than the co-residency gains on 1-5 us kernels)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

@@ -103,11 +103,13 @@ int q4_dequantize_blockwise_4bit(const uint8_t* A, const q4_absmax_t* stats, voi
  * K must be even.  Replaces core.py:467-499 (3 launches) / ops.cu:167-171 / kernels.cu:1062.
  * flags: Q4_GEMV_EXACT_F32 forces the fp32-multiply path (reference arithmetic for T=float) for any dtype;
  *        Q4_GEMV_PDL launches with programmatic stream serialization (the kernel's prologue -- table build, first
- *        weight loads, L2 prefetch -- overlaps the previous kernel's tail; x is read only after it has completed).
+ *        weight loads, L2 prefetch -- overlaps the previous kernel's tail; x is read only after it has completed);
+ *        Q4_GEMV_SHARE_SM sizes the CTAs to half an SM because an independent launch runs concurrently on another
+ *        stream (q/k/v or gate/up of one layer): the two launches are then co-resident on every SM.
  * prefetch / prefetch_bytes (optional, NULL / 0): a byte range that the NEXT call will stream (typically the packed
  * weight of the following Linear4bit).  It is pulled into the 126 MB L2 with TMA bulk prefetches while this call
  * computes, so HBM never idles between dependent launches.  Purely a hint: results do not depend on it. */
-enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2 };
+enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2, Q4_GEMV_SHARE_SM = 4 };
 int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias,
                  void* out, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* prefetch,
                  int64_t prefetch_bytes, void* stream);

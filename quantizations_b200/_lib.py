@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libquantizations_b200.so")
 
 Q4_F32, Q4_F16, Q4_BF16 = 0, 1, 2
 Q4_GENERAL8BIT, Q4_FP4, Q4_NF4 = 0, 1, 2
-Q4_GEMV_DEFAULT, Q4_GEMV_EXACT_F32, Q4_GEMV_PDL = 0, 1, 2
+Q4_GEMV_DEFAULT, Q4_GEMV_EXACT_F32, Q4_GEMV_PDL, Q4_GEMV_SHARE_SM = 0, 1, 2, 4
 
 
 class Q4Error(RuntimeError):

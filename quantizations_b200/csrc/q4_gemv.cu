@@ -199,16 +199,19 @@ gemv_lut256_kernel(const GemvArgs a)
     trace_mark(a, 0);
 
     // ---- 0b. the small latency-critical loads go out FIRST (requests are served in order: behind 64 KB of weight
-    //          loads they would wait microseconds): code table, code2 table, offsets.  Thread t < 256 builds pair word t;
-    //          thread 256 + t (or the same thread when the CTA has fewer than 512 threads) carries code2[t].
-    float tab_a = 0.0f, tab_b = 0.0f, tab_c = 0.0f;
-    if (tid < 256) {
-        tab_a = __ldg(a.code + (tid >> 4));
-        tab_b = __ldg(a.code + (tid & 15));
-    }
-    if (NESTED) {
-        if (nthr < 512) { if (tid < 256) tab_c = __ldg(a.s.code2 + tid); }
-        else if (tid < 512) { if (tid >= 256) tab_c = __ldg(a.s.code2 + (tid - 256)); }
+    //          loads they would wait microseconds): code table, code2 table, offsets.  Word t < 256 of the staging area is
+    //          half2{code[t>>4], code[t&15]}, word 256 + t is code2[t]; a thread carries up to 4 of the 512 words.
+    float tab_a[4], tab_b[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int t = tid + q * nthr;
+        tab_a[q] = tab_b[q] = 0.0f;
+        if (t < 256) {
+            tab_a[q] = __ldg(a.code + (t >> 4));
+            tab_b[q] = __ldg(a.code + (t & 15));
+        } else if (NESTED && t < 512) {
+            tab_a[q] = __ldg(a.s.code2 + (t - 256));
+        }
     }
     float off[kMaxMats];
 #pragma unroll
@@ -217,7 +220,7 @@ gemv_lut256_kernel(const GemvArgs a)
     // ---- 0. stream the whole slice HBM -> L2 now, decoupled from the SM's own progress: the demand loads below then
     //         see L2 latency, and HBM has the entire matrix queued from the first microsecond.  Optionally also this
     //         CTA's share of the bytes the NEXT launch will read (weights of the following Linear).
-    const bool do_prefetch = a.debug_mode != 2;
+    const bool do_prefetch = a.debug_mode != 2 && a.debug_mode < 16;
     if (do_prefetch && warp == (nthr >> 5) - 1 && row_lo < row_hi) {
         prefetch_l2_range(a.Bq + (int64_t)row_lo * (K >> 1), (int64_t)(row_hi - row_lo) * (K >> 1), lane);
         if (NESTED) prefetch_l2_range(a.s.qabsmax + (int64_t)row_lo * bpr, (int64_t)(row_hi - row_lo) * bpr, lane);
@@ -240,8 +243,14 @@ gemv_lut256_kernel(const GemvArgs a)
     u32x8 w[U];
     uint32_t qa[U];
     float a2[U];
+    const int pf_rows = a.debug_mode >= 16 ? a.debug_mode - 16 : 0;  // experiment: per-row L2 prefetch distance (rows)
+    const int blk_end = (row_hi - 1) * bpr + kblk_c;                  // this thread's block in the slice's last row
     auto issue_row = [&](int i) {
         w[i] = ldg_stream_256(a.Bq + (int64_t)blk * 32);
+        if (pf_rows) {
+            const int pb = blk + pf_rows * blk_stride;
+            if (pb <= blk_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Bq + (int64_t)pb * 32));
+        }
         if (NESTED) {
             qa[i] = __ldg(a.s.qabsmax + blk);
             a2[i] = __ldg(a.s.absmax2 + (blk >> a.s.shift2));
@@ -253,13 +262,14 @@ gemv_lut256_kernel(const GemvArgs a)
     trace_mark(a, 1);
     // ---- 2. lookup table: stage the 512 distinct words (loaded in step 0b), then replicate each 32x:
     //         128-B segment 2b = half2{code[b>>4], code[b&15]}, segment 2b+1 = code2[b] (fp32).
-    {
-        __half2 h = __halves2half2(__float2half_rn(tab_a), __float2half_rn(tab_b));
-        if (tid < 256) s_words[tid] = *reinterpret_cast<uint32_t*>(&h);
-        if (nthr < 512) {  // fewer than 512 threads: each thread stages its pair word and its code2 word
-            if (tid < 256) s_words[256 + tid] = __float_as_uint(tab_c);
-        } else if (tid >= 256) {
-            s_words[tid] = __float_as_uint(tab_c);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int t = tid + q * nthr;
+        if (t < 256) {
+            __half2 h = __halves2half2(__float2half_rn(tab_a[q]), __float2half_rn(tab_b[q]));
+            s_words[t] = *reinterpret_cast<uint32_t*>(&h);
+        } else if (t < 512) {
+            s_words[t] = __float_as_uint(tab_a[q]);
         }
     }
     __syncthreads();
@@ -525,10 +535,16 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                       (reinterpret_cast<uintptr_t>(B) & 31) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                       (!nested || st->blocksize2 >= 64);
     if (fast) {
-        static const int env_warps = getenv("Q4_GEMV_WARPS") ? atoi(getenv("Q4_GEMV_WARPS")) : 16;
-        const int warps = kw > env_warps ? kw : env_warps;  // warps per CTA
+        // Warps per CTA.  16 (one CTA fills the SM) streams a large matrix fastest when the launch has the GPU to itself.
+        // 8 (<= 256 threads x 128 registers, ~75-95 KB shared memory) leaves half of every SM free, so that a second launch
+        // -- the next kernel's prologue under programmatic dependent launch, or an independent GEMV on another stream
+        // (q/k/v, gate/up) -- is co-resident: chosen for small matrices and when the caller passes Q4_GEMV_SHARE_SM.
+        static const int env_warps = getenv("Q4_GEMV_WARPS") ? atoi(getenv("Q4_GEMV_WARPS")) : 0;
+        const int64_t warp_rows_per_sm = N * kw / sms;
+        int target = env_warps ? env_warps : (((flags & Q4_GEMV_SHARE_SM) || warp_rows_per_sm <= 32) ? 8 : 16);
+        const int warps = kw > target ? kw : target;
         int groups = warps / kw;
-        while (groups * kw * 32 < 256) groups++;  // the table staging needs at least 256 threads
+        if (groups * kw * 32 < 128) groups = (128 + kw * 32 - 1) / (kw * 32);  // the table staging covers 512 words with 4 per thread
         const int threads = groups * kw * 32;
         // shared-memory layout: COMPACT when dynamic shared memory starts kDynBase into the window (probed once)
         static int dyn_base = -1;

@@ -11,7 +11,8 @@ from . import _lib
 from .core import Params4bit, QuantState, _dequantize_4bit_into, gemv_4bit
 
 
-def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: torch.Tensor = None, bias=None):
+def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: torch.Tensor = None, bias=None,
+                flags: int = _lib.Q4_GEMV_DEFAULT, prefetch: torch.Tensor = None):
     """A @ dequant(B)^T (+ bias).  reference modules.py:28-64.
 
     Decode (A is a single vector): one fused GEMV launch, bias included.
@@ -20,7 +21,7 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: 
     """
     assert quant_state is not None
     if A.numel() == A.shape[-1]:
-        return gemv_4bit(A, B, out, state=quant_state, bias=bias)
+        return gemv_4bit(A, B, out, state=quant_state, bias=bias, flags=flags, prefetch=prefetch)
     W = torch.empty(quant_state.shape, dtype=A.dtype, device=A.device)
     _dequantize_4bit_into(B, quant_state, W)
     return torch.nn.functional.linear(A, W, bias)
@@ -59,6 +60,10 @@ class Linear4bit(nn.Linear):
         self.compute_type_is_set = False
         self.quant_state = None
         self.quant_storage = quant_storage
+        # decode-launch hints (new; see include/quantizations_b200.h): programmatic dependent launch is always safe --
+        # the kernel reads x and writes its output only after the preceding kernel has completed
+        self.gemv_flags = _lib.Q4_GEMV_PDL
+        self.prefetch_next = None  # packed weight of the Linear that runs next (pulled into L2 while this one computes)
 
     def set_compute_type(self, x):
         """reference modules.py:112-122: fp32 / bf16 inputs set the compute dtype; fp16 keeps the configured one."""
@@ -80,5 +85,6 @@ class Linear4bit(nn.Linear):
         weight = self.weight
         if weight.quant_state is None:
             raise RuntimeError("Linear4bit weight is not quantized yet: move the module to a CUDA device first")
-        out = matmul_4bit(x, weight.data, bias=bias, quant_state=weight.quant_state)
+        out = matmul_4bit(x, weight.data, bias=bias, quant_state=weight.quant_state, flags=self.gemv_flags,
+                          prefetch=self.prefetch_next)
         return out if out.dtype == inp_dtype else out.to(inp_dtype)

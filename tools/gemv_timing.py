@@ -28,17 +28,31 @@ def algo_bytes(N, K, xbytes=2, nested=True):
     return b
 
 
+NSTREAMS = 1
+
+
 def time_graph(fn, nlaunch, replays=20):
-    """Capture `nlaunch` back-to-back launches into one CUDA graph and time its replays: no host launch cost."""
+    """Capture `nlaunch` back-to-back launches into one CUDA graph and time its replays: no host launch cost.
+    With NSTREAMS > 1 the launches are dealt round-robin to parallel capture branches (independent launches)."""
     s = torch.cuda.Stream()
+    side = [torch.cuda.Stream() for _ in range(NSTREAMS - 1)]
     with torch.cuda.stream(s):
         for i in range(nlaunch):
             fn(i)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
+            for t in side:
+                t.wait_stream(s)
             for i in range(nlaunch):
-                fn(i)
+                k = i % NSTREAMS
+                if k == 0:
+                    fn(i)
+                else:
+                    with torch.cuda.stream(side[k - 1]):
+                        fn(i)
+            for t in side:
+                s.wait_stream(t)
     for _ in range(3):
         g.replay()
     torch.cuda.synchronize()
@@ -75,7 +89,10 @@ def main():
     ap.add_argument("--only", default="", help="NxK: time just this shape")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--next", action="store_true", help="hint the next matrix of the pool for L2 prefetch")
+    ap.add_argument("--streams", type=int, default=1, help="parallel capture branches (independent launches)")
     a = ap.parse_args()
+    global NSTREAMS
+    NSTREAMS = a.streams
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.dtype]
     dev = torch.device("cuda:0")
     peaks = {}
@@ -103,6 +120,7 @@ def main():
             mats.append(p)
         x = torch.randn(1, 1, K, device=dev, dtype=dt)
         out = torch.empty(1, 1, N, device=dev, dtype=dt)
+        outs2 = [torch.empty(1, 1, N, device=dev, dtype=dt) for _ in range(4)]
         L = _lib.lib()
         stats = st0.native_stats()
         stream = torch.cuda.current_stream().cuda_stream
@@ -110,7 +128,7 @@ def main():
         ptrs = [m.data_ptr() for m in mats]
 
         def ours(i):
-            L.q4_gemv_4bit(x.data_ptr(), ptrs[i % nmat], stats, st0.code.data_ptr(), None, out.data_ptr(), N, K, 64, dcode,
+            L.q4_gemv_4bit(x.data_ptr(), ptrs[i % nmat], stats, st0.code.data_ptr(), None, outs2[i % NSTREAMS].data_ptr(), N, K, 64, dcode,
                            a.flags, ptrs[(i + 1) % nmat] if a.next else None, per if a.next else 0,
                            torch.cuda.current_stream().cuda_stream)
 
