@@ -482,7 +482,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="decoder layers in the stack (0 = the model's own count)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false")
-    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false", help="do not hint the next layer's weight for L2 prefetch")
+    ap.add_argument("--prefetch", action="store_true",
+                    help="pass the next layer's packed weight as the L2 prefetch hint (measured neutral on one stream; off by default so "
+                         "that every launch's DRAM traffic is exactly its own matrix)")
     ap.add_argument("--branches", action="store_true",
                     help="launch q/k/v and gate/up as parallel graph branches (measured slower than one stream + PDL: the graph's "
                          "cross-stream edges cost more than the co-residency gains on 1-5 us kernels)")
