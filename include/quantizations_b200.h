@@ -114,6 +114,14 @@ int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, cons
                  void* out, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* prefetch,
                  int64_t prefetch_bytes, void* stream);
 
+/* Prefill / batched path with the dequantisation fused into a tcgen05 tensor-core GEMM:
+ *     out[m, r] = sum_k X[m, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r]),   m in [0, M), r in [0, N)
+ * X [M, K], out [M, N], bias [N] are `dtype` (Q4_F16 or Q4_BF16), row-major contiguous; accumulation is fp32 (TMEM).
+ * blocksize must be 64 and K a multiple of 64.  Replaces modules.py:63-64 (dequantize_4bit + cast + F.linear): the dense
+ * weight is never written to memory. */
+int q4_gemm_4bit(const void* X, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
+                 int64_t M, int64_t N, int64_t K, int blocksize, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * 3. Introspection
  * ---------------------------------------------------------------------------------------------------------- */

@@ -10,6 +10,7 @@ from .core import (  # noqa: F401
     create_dynamic_map,
     dequantize_4bit,
     dequantize_blockwise,
+    gemm_4bit,
     gemv_4bit,
     get_4bit_type,
     quantize_4bit,

@@ -442,6 +442,35 @@ def gemv_4bit(
     return out
 
 
+def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """out[..., n] = sum_k A[..., k] * dequant(B)[n, k] (+ bias) for any number of rows of A, with the dequantisation fused
+    into a tcgen05 tensor-core GEMM (the dense weight is never materialised).  Replaces the prefill branch of reference
+    modules.py:63-64.  Requires fp16/bf16 activations, blocksize 64 and K % 64 == 0 (`fused_gemm_supported`)."""
+    if state is None:
+        raise ValueError("state cannot be None")
+    N, K = state.shape[0], state.shape[1]
+    if A.shape[-1] != K:
+        raise ValueError(f"A has {A.shape[-1]} features but the quantised weight expects {K}")
+    if not fused_gemm_supported(A, state):
+        raise NotImplementedError("fused 4-bit GEMM needs fp16/bf16 activations, blocksize 64 and K % 64 == 0")
+    A2 = A.reshape(-1, K)
+    if not A2.is_contiguous():
+        A2 = A2.contiguous()
+    M = A2.shape[0]
+    if out is None:
+        out = torch.empty(A.shape[:-1] + (N,), dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        check(_lib.lib().q4_gemm_4bit(A2.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
+                                      None if bias is None else bias.data_ptr(), out.data_ptr(), M, N, K, state.blocksize,
+                                      _DTYPE_CODE[A.dtype], _stream(A)), "gemm_4bit")
+    return out
+
+
+def fused_gemm_supported(A: Tensor, state: QuantState) -> bool:
+    return (A.dtype in (torch.float16, torch.bfloat16) and state.blocksize == 64 and len(state.shape) == 2
+            and state.shape[1] % 64 == 0 and A.data_ptr() % 16 == 0)
+
+
 def quantize_4bit(
     A: Tensor,
     blocksize=64,

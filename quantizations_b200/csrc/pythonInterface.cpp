@@ -109,6 +109,12 @@ int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, cons
                          (cudaStream_t)stream);
 }
 
+int q4_gemm_4bit(const void* X, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
+                 int64_t M, int64_t N, int64_t K, int blocksize, int dtype, void* stream)
+{
+    return q4::gemm_4bit(X, B, stats, code, bias, out, M, N, K, blocksize, dtype, (cudaStream_t)stream);
+}
+
 // developer hook (not declared in the public header): per-CTA phase timestamps of the GEMV kernel, see tools/
 void q4_debug_set_gemv_trace(unsigned long long* p) { q4::g_gemv_trace = p; }
 

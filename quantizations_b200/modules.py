@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .core import Params4bit, QuantState, _dequantize_4bit_into, gemv_4bit
+from .core import Params4bit, QuantState, _dequantize_4bit_into, fused_gemm_supported, gemm_4bit, gemv_4bit
 
 
 def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: torch.Tensor = None, bias=None,
@@ -16,12 +16,15 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: 
     """A @ dequant(B)^T (+ bias).  reference modules.py:28-64.
 
     Decode (A is a single vector): one fused GEMV launch, bias included.
-    Prefill: the weight is dequantised straight into A's dtype (one launch, no fp16 detour and no cast, unlike
-    modules.py:64) and contracted on the tensor cores.
+    Prefill: fp16/bf16 activations go to the fused dequantise + tcgen05 GEMM (`gemm_4bit`: the dense weight is never
+    written to memory); other cases dequantise straight into A's dtype (one launch, no fp16 detour and no cast, unlike
+    modules.py:64) and call F.linear.
     """
     assert quant_state is not None
     if A.numel() == A.shape[-1]:
         return gemv_4bit(A, B, out, state=quant_state, bias=bias, flags=flags, prefetch=prefetch)
+    if fused_gemm_supported(A, quant_state) and (bias is None or bias.dtype == A.dtype):
+        return gemm_4bit(A, B, quant_state, bias=bias, out=out)
     W = torch.empty(quant_state.shape, dtype=A.dtype, device=A.device)
     _dequantize_4bit_into(B, quant_state, W)
     return torch.nn.functional.linear(A, W, bias)
