@@ -36,7 +36,6 @@ namespace gemm {
 
 constexpr int kTileRows = 128;   // weight rows per CTA (UMMA M)
 constexpr int kBK = 64;          // k-block = one quantisation block = 128 bytes of fp16 = one swizzle atom row
-constexpr int kThreads = 256;
 constexpr int kDequantWarp0 = 4; // warps 4..7
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,8 +103,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr)
     return d;
 }
 
+constexpr int kSets = 3;         // dequantise warp sets (4 warps each); set j handles k-blocks j, j+kSets, ...
+constexpr int kThreads = 128 + 128 * kSets;
+
 struct Args {
-    const uint8_t* Bq;       // packed weight [N, K/2] (only used for address checks; data comes through map_w)
     AbsmaxView s;
     const float* code;       // 16-entry code table
     const void* bias;        // [N] or nullptr
@@ -113,29 +114,41 @@ struct Args {
     int M, N, K;
     int bn;                  // tokens per tile (16..256, multiple of 16)
     int stages;
+    int splits;              // split-K factor = cluster size along z (1, 2, 4 or 8)
 };
 
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // shared memory plan (dynamic, 1024-byte aligned): [A tiles: stages x 16 KB][B tiles: stages x bn*128][packed: stages x 4 KB]
-// [byte-pair table 256 x 4 B x 32 lanes = 32 KB][code2 table 1 KB][barriers][tmem base]
+// [byte-pair table 256 x 4 B x 32 lanes = 32 KB][code2 table 1 KB][256 staged words][barriers][tmem base].
+// With split-K the stage memory doubles as the leader's reduction buffer after the main loop: (splits-1) x [bn][128] fp32.
 template <typename T, bool NESTED>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Args a)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int stages = a.stages, bn = a.bn;
+    const int stages = a.stages, bn = a.bn, splits = a.splits;
     uint8_t* s_a = smem;                                   // stages x [128 rows x 128 B], swizzled
     uint8_t* s_b = s_a + stages * (kTileRows * 128);       // stages x [bn rows x 128 B], swizzled by TMA
     uint8_t* s_p = s_b + stages * (bn * 128);              // stages x [128 rows x 32 B] packed
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_p + stages * (kTileRows * 32));  // [256][32] pair words
     float* s_code2 = reinterpret_cast<float*>(s_lut + 256 * 32);                     // [256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_code2 + 256);
+    uint32_t* s_words = reinterpret_cast<uint32_t*>(s_code2 + 256);                  // [256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_words + 256);
     // barrier order: full_tma[stages], full_a[stages], empty[stages], tmem_full
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kTileRows;   // first weight row of this tile
     const int tok0 = blockIdx.y * bn;          // first token
-    const int nkb = a.K / kBK;
+    const int split = blockIdx.z;              // == rank in the (1,1,splits) cluster
+    const int nkb_all = a.K / kBK;
+    const int kb_lo = (int)((int64_t)nkb_all * split / splits), kb_hi = (int)((int64_t)nkb_all * (split + 1) / splits);
+    const int nkb = kb_hi - kb_lo;             // k-blocks of this CTA (>= 1: dispatcher keeps splits <= nkb_all)
     auto full_tma = [&](int s) { return smem_u32(bars + s); };
     auto full_a = [&](int s) { return smem_u32(bars + stages + s); };
     auto empty = [&](int s) { return smem_u32(bars + 2 * stages + s); };
@@ -160,14 +173,17 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // tables: pair word b = {code[b>>4], code[b&15]} in T, replicated per lane (conflict-free lookups); code2 as is
-    for (int i = tid; i < 256 * 32; i += kThreads) {
-        const int b = i >> 5;
-        const float hi = __ldg(a.code + (b >> 4)), lo = __ldg(a.code + (b & 15));
-        s_lut[i] = pack2<__half>(hi, lo);  // codes are kept in fp16 for both compute types (|code| <= 1)
+    // tables: pair word b = half2{code[b>>4], code[b&15]} staged once, then replicated per lane (conflict-free lookups)
+    if (tid < 256) {
+        s_words[tid] = pack2<__half>(__ldg(a.code + (tid >> 4)), __ldg(a.code + (tid & 15)));  // |code| <= 1: fp16 for both types
+        if (NESTED) s_code2[tid] = __ldg(a.s.code2 + tid);
     }
-    if (NESTED) s_code2[tid] = __ldg(a.s.code2 + tid);
     const float offset = NESTED ? __ldg(a.s.offset) : 0.0f;
+    __syncthreads();
+    for (int c = tid; c < 256 * 32 / 4; c += kThreads) {
+        const uint32_t wv = s_words[c >> 3];
+        reinterpret_cast<uint4*>(s_lut)[c] = make_uint4(wv, wv, wv, wv);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -177,9 +193,9 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         // ===== TMA producer
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)(bn * 128 + kTileRows * 32);
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % stages;
-                if (kb >= stages) mbar_wait(empty(s), ((kb / stages) - 1) & 1);
+            for (int i = 0; i < nkb; i++) {
+                const int s = i % stages, kb = kb_lo + i;
+                if (i >= stages) mbar_wait(empty(s), ((i / stages) - 1) & 1);
                 mbar_expect_tx(full_tma(s), bytes);
                 tma_load_2d(smem_u32(s_b + s * (bn * 128)), &map_x, kb * kBK, tok0, full_tma(s));
                 tma_load_2d(smem_u32(s_p + s * (kTileRows * 32)), &map_w, kb * 32, row0, full_tma(s));
@@ -188,11 +204,11 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     } else if (warp == 1) {
         // ===== MMA issuer
         // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16 or bf16, both K-major, N = bn, M = 128
-        const uint32_t fmt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+        const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % stages;
-            const uint32_t ph = (kb / stages) & 1;
+        for (int i = 0; i < nkb; i++) {
+            const int s = i % stages;
+            const uint32_t ph = (i / stages) & 1;
             mbar_wait(full_tma(s), ph);
             mbar_wait(full_a(s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -201,22 +217,23 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 const uint64_t bdesc = make_desc_sw128(smem_u32(s_b + s * (bn * 128)));
 #pragma unroll
                 for (int k = 0; k < kBK / 16; k++)  // 16 elements = 32 bytes = +2 in the (>>4) address field
-                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                umma_commit(empty(s));                       // stage reusable once these MMAs have read it
-                if (kb == nkb - 1) umma_commit(tmem_full);   // accumulator complete
+                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) != 0);
+                umma_commit(empty(s));                      // stage reusable once these MMAs have read it
+                if (i == nkb - 1) umma_commit(tmem_full);   // accumulator complete
             }
             __syncwarp();
         }
     } else if (warp >= kDequantWarp0) {
-        // ===== dequantise: thread t = weight row row0 + t
-        const int t = tid - kDequantWarp0 * 32;
+        // ===== dequantise: set j = (warp-4)/4 handles k-blocks j, j+kSets, ...; thread t of a set = weight row row0 + t
+        const int set = (warp - kDequantWarp0) >> 2;
+        const int t = (tid - kDequantWarp0 * 32) & 127;
         const int row = row0 + t;
         const bool row_ok = row < a.N;
         const int bpr = a.K >> 6;
         const uint32_t lut_lane = smem_u32(s_lut) + lane * 4;
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % stages;
-            const uint32_t ph = (kb / stages) & 1;
+        for (int i = set; i < nkb; i += kSets) {
+            const int s = i % stages, kb = kb_lo + i;
+            const uint32_t ph = (i / stages) & 1;
             // this block's absmax (independent of the pipeline)
             float am = 0.0f;
             if (row_ok) {
@@ -225,8 +242,8 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 else am = __ldg(a.s.absmax + blk);
             }
             const uint32_t am2 = pack2<__half>(am, am);
-            if (kb >= stages) mbar_wait(empty(s), ((kb / stages) - 1) & 1);  // A tile of this stage no longer read by the MMA
-            mbar_wait(full_tma(s), ph);                                      // packed bytes have landed
+            if (i >= stages) mbar_wait(empty(s), ((i / stages) - 1) & 1);  // A tile of this stage no longer read by the MMA
+            mbar_wait(full_tma(s), ph);                                    // packed bytes have landed
             const uint4* pk = reinterpret_cast<const uint4*>(s_p + s * (kTileRows * 32) + t * 32);
             const uint4 p0 = pk[0], p1 = pk[1];
             const uint32_t wd[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -252,15 +269,32 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             mbar_arrive(full_a(s));
         }
-        // ===== epilogue: TMEM lane = weight row, column = token
-        mbar_wait(tmem_full, 0);
+        mbar_wait(tmem_full, 0);  // every MMA of this CTA has completed: TMEM final, stage memory free
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;  // this warp may only touch TMEM lanes [32q, 32q+32)
-        const int erow = row0 + q * 32 + lane;
+    }
+
+    // ===== split-K: the CTAs of a cluster hold partial sums of the same output tile.  After every CTA's main loop is over
+    // (first cluster barrier) the peers push their fp32 partials into the leader's freed stage memory over DSMEM, laid out
+    // [peer][token][row] so that a warp's 32 rows are one 128-byte store; second barrier; the leader adds them.
+    float* s_red = reinterpret_cast<float*>(smem);
+    if (splits > 1) cluster_sync_all();
+
+    if (warp >= kDequantWarp0) {
+        // ===== epilogue: TMEM lane = weight row, column = token.  Warp w may only touch TMEM lanes [32 (w&3), +32); the
+        // kSets warps sharing a quarter split the token columns between them.
+        const int set = (warp - kDequantWarp0) >> 2;
+        const int q = warp & 3;
+        const int erow_t = q * 32 + lane;  // row inside the tile
+        const int erow = row0 + erow_t;
         T* out = reinterpret_cast<T*>(a.out);
         const T* bias = reinterpret_cast<const T*>(a.bias);
         const float bv = (bias && erow < a.N) ? Elem<T>::to_f32(bias[erow]) : 0.0f;
-        for (int c0 = 0; c0 < bn; c0 += 16) {
+        uint32_t red_remote = 0;
+        if (splits > 1 && split > 0) {
+            const uint32_t local = smem_u32(s_red + (size_t)(split - 1) * bn * kTileRows);
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(red_remote) : "r"(local), "r"(0));
+        }
+        for (int c0 = set * 16; c0 < bn; c0 += 16 * kSets) {
             uint32_t r[16];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
             asm volatile(
@@ -269,18 +303,54 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (erow < a.N) {
+            if (splits > 1 && split > 0) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int tok = tok0 + c0 + j;
-                    if (tok < a.M) {
-                        T y = Elem<T>::from_f32(__uint_as_float(r[j]));
-                        if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + bv);
-                        out[(int64_t)tok * a.N + erow] = y;
+                for (int j = 0; j < 16; j++)
+                    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(red_remote + (uint32_t)(((c0 + j) * kTileRows + erow_t) * 4)), "r"(r[j]) : "memory");
+            } else if (splits == 1) {
+                if (erow < a.N) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int tok = tok0 + c0 + j;
+                        if (tok < a.M) {
+                            T y = Elem<T>::from_f32(__uint_as_float(r[j]));
+                            if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + bv);
+                            out[(int64_t)tok * a.N + erow] = y;
+                        }
                     }
                 }
             }
         }
+        if (splits > 1) {
+            cluster_sync_all();  // peers' partials have landed in the leader's shared memory
+            if (split == 0) {
+                for (int c0 = set * 16; c0 < bn; c0 += 16 * kSets) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (erow < a.N) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int tok = tok0 + c0 + j;
+                            float acc = __uint_as_float(r[j]);
+                            for (int p = 0; p < splits - 1; p++) acc += s_red[((size_t)p * bn + (c0 + j)) * kTileRows + erow_t];
+                            if (tok < a.M) {
+                                T y = Elem<T>::from_f32(acc);
+                                if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + bv);
+                                out[(int64_t)tok * a.N + erow] = y;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (splits > 1) {
+        cluster_sync_all();  // warps 0-3 take part in the second cluster barrier too
     }
 
     // ---- teardown
@@ -341,11 +411,21 @@ static int launch(const T* X, const uint8_t* B, const q4_absmax_t* st, const flo
     const bool nested = st->qabsmax != nullptr;
     const int bn = pick_bn(M);
     const size_t per_stage = kTileRows * 128 + (size_t)bn * 128 + kTileRows * 32;
-    const size_t fixed = 256 * 32 * 4 + 1024 + 8 * 64 + 64;
+    const size_t fixed = 256 * 32 * 4 + 1024 + 1024 + 8 * 64 + 64;
     int stages = (int)((200 * 1024 - fixed) / per_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) return Q4_ERR_SHAPE;
     const size_t smem = stages * per_stage + fixed + 1024;
+
+    // split-K over a thread-block cluster when the tile grid cannot fill the GPU (small token counts): the largest power
+    // of two <= 8 that keeps tiles * splits <= ~2 CTAs per SM, leaves >= 4 k-blocks per CTA and fits the reduction buffer
+    const int64_t tiles = ((N + kTileRows - 1) / kTileRows) * ((M + bn - 1) / bn);
+    static const int env_splits = getenv("Q4_GEMM_SPLITS") ? atoi(getenv("Q4_GEMM_SPLITS")) : 0;
+    int splits = 1;
+    while (splits < 8 && tiles * splits * 2 <= 2 * sm_count() && (K / kBK) / (splits * 2) >= 4 &&
+           (size_t)(splits * 2 - 1) * bn * kTileRows * 4 <= stages * per_stage)
+        splits *= 2;
+    if (env_splits) splits = env_splits;
 
     CUtensorMap map_x, map_w;
     const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -356,7 +436,6 @@ static int launch(const T* X, const uint8_t* B, const q4_absmax_t* st, const flo
         return Q4_ERR_DEVICE;
 
     Args a;
-    a.Bq = B;
     a.s = v;
     a.code = code;
     a.bias = bias;
@@ -366,11 +445,24 @@ static int launch(const T* X, const uint8_t* B, const q4_absmax_t* st, const flo
     a.K = (int)K;
     a.bn = bn;
     a.stages = stages;
+    a.splits = splits;
     auto kern = nested ? gemm_dequant_tcgen05_kernel<T, true> : gemm_dequant_tcgen05_kernel<T, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)((N + kTileRows - 1) / kTileRows), (unsigned)((M + bn - 1) / bn));
-    kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((N + kTileRows - 1) / kTileRows), (unsigned)((M + bn - 1) / bn), (unsigned)splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, map_x, map_w, a);
+    if (e != cudaSuccess) return (int)e;
     return finish_launch();
 }
 

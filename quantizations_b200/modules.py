@@ -4,6 +4,8 @@ reference: /root/reference/modules.py:28-64 (matmul_4bit), :67-151 (Linear4bit).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -23,11 +25,28 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: 
     assert quant_state is not None
     if A.numel() == A.shape[-1]:
         return gemv_4bit(A, B, out, state=quant_state, bias=bias, flags=flags, prefetch=prefetch)
-    if fused_gemm_supported(A, quant_state) and (bias is None or bias.dtype == A.dtype):
+    if _use_fused_gemm(A, quant_state, bias):
         return gemm_4bit(A, B, quant_state, bias=bias, out=out)
     W = torch.empty(quant_state.shape, dtype=A.dtype, device=A.device)
     _dequantize_4bit_into(B, quant_state, W)
     return torch.nn.functional.linear(A, W, bias)
+
+
+def _use_fused_gemm(A, quant_state, bias) -> bool:
+    """Prefill dispatch.  Q4_PREFILL=fused|cublas forces a path; `auto` (default) takes the fused tcgen05 kernel where it
+    measured faster than dequantise + cuBLAS on B200 (profiles/): up to 64 tokens on every Llama-3 shape, up to 128 tokens on
+    the 14336-wide ones; beyond that the dense GEMM dominates and cuBLAS' 2-CTA kernels are still ahead of this round's
+    single-CTA pipeline."""
+    if not fused_gemm_supported(A, quant_state) or not (bias is None or bias.dtype == A.dtype):
+        return False
+    mode = os.environ.get("Q4_PREFILL", "auto")
+    if mode == "fused":
+        return True
+    if mode == "cublas":
+        return False
+    M = A.numel() // A.shape[-1]
+    n, k = quant_state.shape
+    return M <= 64 or (M <= 128 and n * k >= 32 * 1024 * 1024)
 
 
 class Linear4bit(nn.Linear):

@@ -30,7 +30,7 @@ def test_header_declares_the_reference_entry_points():
     for ref in ("cgemm_4bit_inference_naive_fp32", "cquantize_blockwise_fp16_fp4", "cdequantize_blockwise_fp16_fp4",
                 "cquantize_blockwise_fp32", "cdequantize_blockwise_fp32"):  # reference pythonInterface.cpp:154-161
         assert ref in names
-    assert len(names) >= 14
+    assert len(names) >= 15 and "q4_gemm_4bit" in names
 
 
 def test_library_exports_every_declared_symbol(L):
@@ -63,6 +63,9 @@ def test_argument_errors_are_reported_not_launched(L):
     assert L.q4_quantize_blockwise_4bit(one, one, one, 64, -1, 1, 1, null) == -4
     assert L.q4_gemv_4bit(one, one, ctypes.byref(st), one, null, one, 8, 7, 64, 1, 0, null, 0, null) == -4
     assert L.cgemm_4bit_inference_naive_fp32(8, 2, 64, one, one, one, one, one, 8, 32, 8, 64) == -4
+    assert L.q4_gemm_4bit(one, one, ctypes.byref(st), one, null, one, 4, 8, 100, 64, 1, null) == -4   # K % 64
+    assert L.q4_gemm_4bit(one, one, ctypes.byref(st), one, null, one, 4, 8, 128, 128, 1, null) == -1  # blocksize != 64
+    assert L.q4_gemm_4bit(one, one, ctypes.byref(st), one, null, one, 4, 8, 128, 64, 0, null) == -2   # fp32 not supported
     # NULL pointers
     assert L.q4_quantize_blockwise_4bit(null, one, one, 64, 64, 1, 1, null) == -5
     assert L.q4_gemv_4bit(one, one, None, one, null, one, 8, 64, 64, 1, 0, null, 0, null) == -5

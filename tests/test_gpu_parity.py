@@ -316,3 +316,58 @@ def test_linear4bit_module_decode_and_prefill(q):
     old = lin.weight
     rebuilt = q.Params4bit(old.data, requires_grad=False, **old.__dict__).to(DEV)
     assert rebuilt.quant_state is old.quant_state and rebuilt.bnb_quantized
+
+
+# ------------------------------------------------------------------------------------------------ prefill (fused tcgen05 GEMM)
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("quant_type,nested", [("fp4", True), ("nf4", True), ("nf4", False)])
+@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (1, 256, 256), (33, 384, 512), (100, 200, 1024), (128, 1024, 4096),
+                                   (300, 512, 2048), (17, 4096, 4096), (64, 1024, 14336)])
+def test_fused_gemm_vs_fp64_truth(q, oracle, dtype, quant_type, nested, M, N, K):
+    """gemm_4bit (dequantise fused into tcgen05 MMA) against an fp64 product of the ORACLE's dequantised weight.
+    tolerance: max|y - truth| <= 1e-2 * max|truth|; ragged M and N (not multiples of the 16..256 x 128 tiles) included."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    W = dev((rng.standard_normal((N, K)) * 0.02).astype(np.float32), TDT[dtype])
+    packed, state = q.quantize_4bit(W, quant_type=quant_type, compress_statistics=nested)
+    X = dev(rng.standard_normal((M, K)).astype(np.float32), TDT[dtype])
+    bias = dev(rng.standard_normal(N).astype(np.float32), TDT[dtype])
+    y = q.gemm_4bit(X.reshape(1, M, K), packed, state, bias=bias)
+    assert y.shape == (1, M, N) and y.dtype == TDT[dtype]
+    st = oracle.quantize_4bit(f32(W), 64, quant_type, offset=float(state.offset.item()) if nested else None,
+                              compress_statistics=nested)
+    wdeq = oracle.dequantize_4bit(st, "float32")
+    truth = f32(X).astype(np.float64) @ wdeq.astype(np.float64).T + f32(bias).astype(np.float64)
+    err = np.abs(f32(y).reshape(M, N) - truth).max()
+    assert err <= 1e-2 * np.abs(truth).max(), f"max err {err:.3e} vs scale {np.abs(truth).max():.3e}"
+    y0 = q.gemm_4bit(X, packed, state)
+    np.testing.assert_allclose(f32(y0), truth - f32(bias), rtol=0, atol=1.2e-2 * np.abs(truth).max())
+
+
+def test_fused_gemm_matches_gemv_and_cublas_path(q, monkeypatch):
+    """The three routes through matmul_4bit agree: GEMV (one token), fused GEMM, dequantise + F.linear."""
+    torch.manual_seed(3)
+    lin = q.Linear4bit(1024, 768, bias=True, compute_dtype=torch.float16, quant_type="nf4").to(DEV)
+    lin.bias.data = lin.bias.data.half()
+    x = torch.randn(1, 24, 1024, device=DEV, dtype=torch.float16)
+    monkeypatch.setenv("Q4_PREFILL", "fused")
+    y_fused = lin(x)
+    monkeypatch.setenv("Q4_PREFILL", "cublas")
+    y_cublas = lin(x)
+    y_gemv = torch.cat([lin(x[:, i : i + 1]) for i in range(24)], dim=1)
+    scale = y_cublas.float().abs().max().item()
+    assert (y_fused.float() - y_cublas.float()).abs().max().item() <= 5e-3 * scale
+    assert (y_fused.float() - y_gemv.float()).abs().max().item() <= 5e-3 * scale
+
+
+def test_fused_gemm_error_behaviour(q):
+    W = torch.randn(128, 192, device=DEV, dtype=torch.float16)
+    packed, state = q.quantize_4bit(W)
+    with pytest.raises(ValueError):
+        q.gemm_4bit(torch.randn(4, 128, device=DEV, dtype=torch.float16), packed, state)
+    with pytest.raises(NotImplementedError):
+        q.gemm_4bit(torch.randn(4, 192, device=DEV, dtype=torch.float32), packed, state)
+    packed128, state128 = q.quantize_4bit(W, blocksize=128)
+    with pytest.raises(NotImplementedError):
+        q.gemm_4bit(torch.randn(4, 192, device=DEV, dtype=torch.float16), packed128, state128)
