@@ -1,0 +1,187 @@
+"""Minimal batch-1 Llama decoder built on Linear4bit -- the end-to-end harness for BASELINE.json config 3/5.
+
+Not a model zoo: it exists so that the 4-bit Linear hot path can be measured inside a real decode loop (KV cache, RoPE, GQA
+attention, RMSNorm, SwiGLU) without HF generate()'s host overhead, and so that one decode step can be captured into a CUDA
+graph (every kernel of this library runs on the current stream; the reference's run on the legacy default stream and cannot be
+captured).  Weights are random-init (no checkpoints offline); shapes follow Llama-3.
+
+`linear_factory(in_features, out_features, name) -> nn.Module` decides what each projection is: quantizations_b200.Linear4bit
+(default), a dense nn.Linear (the "HF native" baseline), or the reference-kernel module of oracle/ (tests/bench only).
+Tensor parallelism: q/k/v/gate/up column-parallel, o/down row-parallel with an all-reduce after each.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass
+class LlamaConfig:
+    hidden: int = 4096
+    inter: int = 14336
+    layers: int = 32
+    heads: int = 32
+    kv_heads: int = 8
+    vocab: int = 128256
+    rope_theta: float = 500000.0
+    eps: float = 1e-5
+    max_len: int = 256
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+
+LLAMA3_8B = LlamaConfig()
+LLAMA3_70B = LlamaConfig(hidden=8192, inter=28672, layers=80, heads=64, kv_heads=8)
+
+
+class DecoderLayer(nn.Module):
+    def __init__(self, cfg: LlamaConfig, layer: int, make: Callable, tp: int):
+        super().__init__()
+        h, hd = cfg.hidden, cfg.head_dim
+        self.nh, self.nkv, self.hd = cfg.heads // tp, cfg.kv_heads // tp, hd
+        self.q_proj = make(h, self.nh * hd, f"L{layer}.q_proj")
+        self.k_proj = make(h, self.nkv * hd, f"L{layer}.k_proj")
+        self.v_proj = make(h, self.nkv * hd, f"L{layer}.v_proj")
+        self.o_proj = make(self.nh * hd, h, f"L{layer}.o_proj")
+        self.gate_proj = make(h, cfg.inter // tp, f"L{layer}.gate_proj")
+        self.up_proj = make(h, cfg.inter // tp, f"L{layer}.up_proj")
+        self.down_proj = make(cfg.inter // tp, h, f"L{layer}.down_proj")
+        self.ln1 = nn.Parameter(torch.ones(h))
+        self.ln2 = nn.Parameter(torch.ones(h))
+
+
+class Llama(nn.Module):
+    def __init__(self, cfg: LlamaConfig, linear_factory: Callable, device, dtype=torch.bfloat16, tp: int = 1, group=None):
+        super().__init__()
+        self.cfg, self.tp, self.group, self.dtype = cfg, tp, group, dtype
+        g = torch.Generator(device=device).manual_seed(1234)
+        self.embed = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
+        self.lm_head = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
+        self.norm = torch.ones(cfg.hidden, device=device, dtype=dtype)
+        self.layers = nn.ModuleList([DecoderLayer(cfg, i, linear_factory, tp) for i in range(cfg.layers)])
+        for layer in self.layers:
+            layer.ln1.data = layer.ln1.data.to(device=device, dtype=dtype)
+            layer.ln2.data = layer.ln2.data.to(device=device, dtype=dtype)
+        hd = cfg.head_dim
+        inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, device=device, dtype=torch.float32) / hd))
+        ang = torch.arange(cfg.max_len, device=device, dtype=torch.float32)[:, None] * inv[None, :]
+        self.cos, self.sin = ang.cos().to(dtype), ang.sin().to(dtype)      # [max_len, hd/2]
+        nkv = cfg.kv_heads // tp
+        self.k_cache = torch.zeros(cfg.layers, nkv, cfg.max_len, hd, device=device, dtype=dtype)
+        self.v_cache = torch.zeros(cfg.layers, nkv, cfg.max_len, hd, device=device, dtype=dtype)
+        self.positions = torch.arange(cfg.max_len, device=device)
+
+    def _rope(self, x, cos, sin):  # x [T, heads, hd]; cos/sin [T, hd/2]  (HF "rotate_half" convention)
+        x1, x2 = x[..., : self.cfg.head_dim // 2], x[..., self.cfg.head_dim // 2:]
+        c, s = cos[:, None, :], sin[:, None, :]
+        return torch.cat((x1 * c - x2 * s, x2 * c + x1 * s), dim=-1)
+
+    def _allreduce(self, t):
+        if self.tp > 1:
+            torch.distributed.all_reduce(t, group=self.group)
+        return t
+
+    @torch.no_grad()
+    def forward(self, tokens: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+        """tokens [T] int64, pos [T] int64 (absolute positions, consecutive).  Returns logits of the LAST token [vocab].
+        T == 1 is the decode step (static shapes: capturable in a CUDA graph with device-resident `tokens` / `pos`)."""
+        cfg, T = self.cfg, tokens.shape[0]
+        x = self.embed.index_select(0, tokens).unsqueeze(0)                 # [1, T, h]
+        cos, sin = self.cos.index_select(0, pos), self.sin.index_select(0, pos)
+        # causal mask over the whole static cache: key j visible to query i iff j <= pos[i]
+        mask = self.positions[None, :] <= pos[:, None]                      # [T, max_len]
+        for li, L in enumerate(self.layers):
+            h = F.rms_norm(x, (cfg.hidden,), L.ln1, cfg.eps)
+            q = L.q_proj(h).view(T, L.nh, L.hd)
+            k = L.k_proj(h).view(T, L.nkv, L.hd)
+            v = L.v_proj(h).view(T, L.nkv, L.hd)
+            q, k = self._rope(q, cos, sin), self._rope(k, cos, sin)
+            self.k_cache[li].index_copy_(1, pos, k.transpose(0, 1))
+            self.v_cache[li].index_copy_(1, pos, v.transpose(0, 1))
+            a = F.scaled_dot_product_attention(q.transpose(0, 1).unsqueeze(0), self.k_cache[li].unsqueeze(0),
+                                               self.v_cache[li].unsqueeze(0), attn_mask=mask, enable_gqa=True)  # [1, nh, T, hd]
+            a = a.squeeze(0).transpose(0, 1).reshape(1, T, L.nh * L.hd)
+            x = x + self._allreduce(L.o_proj(a))
+            h = F.rms_norm(x, (cfg.hidden,), L.ln2, cfg.eps)
+            x = x + self._allreduce(L.down_proj(F.silu(L.gate_proj(h)) * L.up_proj(h)))
+        x = F.rms_norm(x[:, -1:], (cfg.hidden,), self.norm, cfg.eps)
+        return F.linear(x, self.lm_head).view(-1)
+
+    @torch.no_grad()
+    def generate(self, prompt: torch.Tensor, new_tokens: int, use_graph: bool = True):
+        """Greedy decode: prefill `prompt` [P], then `new_tokens` decode steps.  Returns (tokens [new_tokens], decode seconds)."""
+        import time
+
+        dev = prompt.device
+        P = prompt.shape[0]
+        logits = self.forward(prompt, torch.arange(P, device=dev))
+        tok = logits.argmax().view(1)
+        pos = torch.full((1,), P, device=dev, dtype=torch.int64)
+        out = torch.empty(new_tokens, dtype=torch.int64, device=dev)
+
+        def step():
+            lg = self.forward(tok, pos)
+            tok.copy_(lg.argmax().view(1))
+            pos.add_(1)
+
+        graph = None
+        if use_graph:
+            from .graphs import capture
+
+            tok0, pos0 = tok.clone(), pos.clone()
+            graph = capture(step, warmup=2)           # warm-up + capture advance tok/pos: restore them
+            tok.copy_(tok0)
+            pos.copy_(pos0)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(new_tokens):
+            out[i : i + 1].copy_(tok)
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+        torch.cuda.synchronize(dev)
+        return out, time.perf_counter() - t0
+
+
+def linear4bit_factory(device, dtype=torch.bfloat16, quant_type="nf4", seed=0, tp_rank=0, tp=1, col_names=("q_proj", "k_proj", "v_proj", "gate_proj", "up_proj")):
+    """Random-init Linear4bit projections (weights ~ N(0, 0.02^2), HF initializer_range), quantised on creation.
+    Under TP every rank draws the FULL weight from the shared seed and quantises its own slice."""
+    from .core import Params4bit
+    from .modules import Linear4bit
+
+    counter = [seed]
+
+    def make(fin, fout, name):
+        counter[0] += 1
+        g = torch.Generator(device=device).manual_seed(counter[0])
+        col = name.split(".")[-1] in col_names
+        full_out, full_in = (fout * tp, fin) if col else (fout, fin * tp)
+        W = (torch.randn(full_out, full_in, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
+        if tp > 1:
+            W = (W[tp_rank * fout:(tp_rank + 1) * fout] if col else W[:, tp_rank * fin:(tp_rank + 1) * fin]).contiguous()
+        lin = Linear4bit(fin, fout, bias=False, compute_dtype=dtype, quant_type=quant_type, device="meta")
+        lin.weight = Params4bit(W, requires_grad=False, quant_type=quant_type, module=lin).to(device)
+        return lin
+
+    return make
+
+
+def dense_factory(device, dtype=torch.bfloat16, seed=0):
+    """Unquantised nn.Linear projections from the same seeds (the "HF native" baseline of the reference's README)."""
+    counter = [seed]
+
+    def make(fin, fout, name):
+        counter[0] += 1
+        g = torch.Generator(device=device).manual_seed(counter[0])
+        lin = nn.Linear(fin, fout, bias=False, device=device, dtype=dtype)
+        lin.weight.data = (torch.randn(fout, fin, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
+        return lin
+
+    return make
