@@ -340,7 +340,35 @@ def run_ours(args, rank, world, device):
     }
     if world == 1 and not args.no_cpu:
         res["cpu_baseline"] = cpu_baseline(mods[:7], x_in, budget_s=args.cpu_seconds)
+    if world == 1 and not args.no_decode:
+        del mods, graph, g2
+        torch.cuda.empty_cache()
+        res["decode"] = decode_tok_s(args, device, "ours")
     return res
+
+
+def decode_tok_s(args, device, impl):
+    """Second half of BASELINE's metric: Llama-3-8B batch-1 greedy decode tok/s (random-init, 32-token prompt, 60 new tokens,
+    best of 3) inside quantizations_b200.llama -- ours under a CUDA graph; the reference's kernels eagerly on the legacy
+    default stream (they cannot be captured), same NF4 / bf16 configuration."""
+    from quantizations_b200 import llama
+
+    cfg = llama.LlamaConfig(layers=args.layers or 32)
+    prompt = torch.arange(1, 33, device=device)
+    if impl == "ours":
+        model = llama.Llama(cfg, llama.linear4bit_factory(device, torch.bfloat16, "nf4"), device, torch.bfloat16)
+        ctx, graph = torch.cuda.stream(torch.cuda.Stream(device=device)), True
+    else:
+        from oracle import ref_linear
+
+        model = llama.Llama(cfg, ref_linear.ref_factory(device, torch.bfloat16, "nf4", torch.bfloat16), device, torch.bfloat16)
+        ctx, graph = torch.cuda.stream(torch.cuda.default_stream(device)), False
+    with ctx:
+        model.generate(prompt, 8, use_graph=False)
+        best = min(model.generate(prompt, 60, use_graph=graph)[1] for _ in range(3))
+    return {"tok_s": round(60 / best, 1), "ms_per_token": round(best / 60 * 1e3, 3),
+            "config": f"Llama-3-8B shapes, {cfg.layers} layers, random-init, NF4 + double-quant Linear4bit, bf16, bs=1, 32-token prompt, "
+                      f"60 new tokens, greedy, {'CUDA-graph decode step' if graph else 'eager (legacy default stream)'}"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle/ port)
@@ -450,7 +478,8 @@ def run_reference(args, rank, world, device):
                                  "sample": "whole step; the reference's implementation of this path is CUDA (it has no CPU path), "
                                            "so it is timed on the same B200 rather than on host cores"},
                 "e2e": {"value": round(step_bytes / (wall_ms * 1e-3) / 1e9, 1), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "clocks": clk.summary(), "gpu_launches": 3 * len(mods) * args.steps}
+                "clocks": clk.summary(), "gpu_launches": 3 * len(mods) * args.steps,
+                **({} if args.no_decode else {"decode": decode_tok_s(args, device, "reference")})}
     # no GPU / no compiled reference: the oracle port on host cores
     from oracle import q4_oracle as orc  # noqa: F401
     import numpy as np
@@ -489,6 +518,7 @@ def main():
                     help="launch q/k/v and gate/up as parallel graph branches (measured slower than one stream + PDL: the graph's "
                          "cross-stream edges cost more than the co-residency gains on 1-5 us kernels)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the end-to-end Llama-3-8B decode tok/s leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
 

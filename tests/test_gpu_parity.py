@@ -371,3 +371,41 @@ def test_fused_gemm_error_behaviour(q):
     packed128, state128 = q.quantize_4bit(W, blocksize=128)
     with pytest.raises(NotImplementedError):
         q.gemm_4bit(torch.randn(4, 192, device=DEV, dtype=torch.float16), packed128, state128)
+
+
+# ------------------------------------------------------------------------------------------------ end-to-end decode loop
+
+
+def test_llama_decode_matches_dense_model_with_dequantised_weights(q):
+    """The whole chain inside a real decoder (quantizations_b200/llama.py): prefill through the fused GEMM / cuBLAS path,
+    decode through the GEMV, eager and CUDA-graph replay -- against the same model with dense nn.Linear layers holding the
+    DEQUANTISED weights (so the only differences are kernel arithmetic, not quantisation error)."""
+    from quantizations_b200 import llama
+
+    cfg = llama.LlamaConfig(hidden=512, inter=1024, layers=2, heads=8, kv_heads=2, vocab=1000, max_len=64)
+    dev_ = torch.device(DEV)
+    mq = llama.Llama(cfg, llama.linear4bit_factory(dev_, torch.bfloat16, "nf4"), dev_, torch.bfloat16)
+
+    def dense_from(mod):
+        W = q.dequantize_4bit(mod.weight.data, mod.weight.quant_state).t().contiguous()
+        lin = torch.nn.Linear(W.shape[1], W.shape[0], bias=False, device=dev_, dtype=torch.bfloat16)
+        lin.weight.data = W
+        return lin
+
+    md = llama.Llama(cfg, llama.dense_factory(dev_, torch.bfloat16), dev_, torch.bfloat16)
+    for Lq, Ld in zip(mq.layers, md.layers):
+        for name in ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"):
+            setattr(Ld, name, dense_from(getattr(Lq, name)))
+    md.embed, md.lm_head = mq.embed, mq.lm_head
+    prompt = torch.arange(1, 20, device=dev_)
+    lq = mq.forward(prompt, torch.arange(19, device=dev_)).float()
+    ld = md.forward(prompt, torch.arange(19, device=dev_)).float()
+    assert (lq - ld).abs().max().item() <= 3e-2 * ld.abs().max().item()
+    # one decode step on top of the prefilled caches
+    tok, pos = torch.tensor([5], device=dev_), torch.tensor([19], device=dev_)
+    sq, sd = mq.forward(tok, pos).float(), md.forward(tok, pos).float()
+    assert (sq - sd).abs().max().item() <= 3e-2 * sd.abs().max().item()
+    # greedy generation: graph replay reproduces the eager tokens exactly (same kernels, same order)
+    t_eager, _ = mq.generate(prompt, 12, use_graph=False)
+    t_graph, _ = mq.generate(prompt, 12, use_graph=True)
+    assert torch.equal(t_eager, t_graph)
