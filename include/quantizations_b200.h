@@ -114,6 +114,16 @@ int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, cons
                  void* out, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* prefetch,
                  int64_t prefetch_bytes, void* stream);
 
+/* Grouped decode GEMV: up to 4 Linear4bit weights that share the activation vector (q/k/v, gate/up) in ONE launch.
+ * The matrices must be stored back to back: B = packed bytes of all `rows` = sum N_i rows, `stats->qabsmax` / `stats->absmax2`
+ * (or `stats->absmax`) likewise concatenated (each N_i*K/64 a multiple of blocksize2 so nested blocks do not straddle
+ * matrices), `out` / `bias` are [rows].  Only the double-quant offset is per matrix: offsets[i] (device pointers, nested only;
+ * stats->offset is ignored), row_end[i] = exclusive end row of matrix i (host array, row_end[nmat-1] == rows).
+ * Same arithmetic as q4_gemv_4bit per matrix; blocksize 64, K % 64 == 0, fp16/bf16 only. */
+int q4_gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* const* offsets,
+                         const int* row_end, int nmat, const float* code, const void* bias, void* out, int64_t rows, int64_t K,
+                         int blocksize, int dtype, int flags, const void* prefetch, int64_t prefetch_bytes, void* stream);
+
 /* Prefill / batched path with the dequantisation fused into a tcgen05 tensor-core GEMM:
  *     out[m, r] = sum_k X[m, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r]),   m in [0, M), r in [0, N)
  * X [M, K], out [M, N], bias [N] are `dtype` (Q4_F16 or Q4_BF16), row-major contiguous; accumulation is fp32 (TMEM).

@@ -16,6 +16,6 @@ from .core import (  # noqa: F401
     quantize_4bit,
     quantize_blockwise,
 )
-from .modules import Linear4bit, matmul_4bit  # noqa: F401
+from .modules import Linear4bit, Linear4bitGroup, matmul_4bit  # noqa: F401
 
 __version__ = "0.1.0"

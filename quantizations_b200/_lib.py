@@ -46,6 +46,8 @@ _SIGNATURES = {
     "q4_quantize_blockwise_8bit": [_vp, _vp, _vp, _vp, _i, _i64, _vp],
     "q4_dequantize_blockwise_8bit": [_vp, _vp, _vp, _vp, _i, _i64, _vp],
     "q4_dequantize_blockwise_4bit": [_vp, ctypes.POINTER(AbsmaxStats), _vp, _i, _i64, _i, _i, _vp],
+    "q4_gemv_4bit_grouped": [_vp, _vp, ctypes.POINTER(AbsmaxStats), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), _i,
+                             _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
     "q4_gemm_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
     "q4_gemv_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
 }

@@ -109,6 +109,14 @@ int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, cons
                          (cudaStream_t)stream);
 }
 
+int q4_gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* const* offsets,
+                         const int* row_end, int nmat, const float* code, const void* bias, void* out, int64_t rows, int64_t K,
+                         int blocksize, int dtype, int flags, const void* prefetch, int64_t prefetch_bytes, void* stream)
+{
+    return q4::gemv_4bit_grouped(x, B, stats, offsets, row_end, nmat, code, bias, out, rows, K, blocksize, dtype, flags, prefetch,
+                                 prefetch_bytes, (cudaStream_t)stream);
+}
+
 int q4_gemm_4bit(const void* X, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
                  int64_t M, int64_t N, int64_t K, int blocksize, int dtype, void* stream)
 {

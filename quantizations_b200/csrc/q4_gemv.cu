@@ -524,7 +524,8 @@ static int launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t
 
 template <typename T>
 static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, const float* code, const T* bias, T* out,
-                         int64_t N, int64_t K, int blocksize, int flags, const void* next, int64_t next_bytes, cudaStream_t stream)
+                         int64_t N, int64_t K, int blocksize, int flags, const void* next, int64_t next_bytes, cudaStream_t stream,
+                         int nmat = 1, const float* const* offsets = nullptr, const int* row_end = nullptr)
 {
     const AbsmaxView v = make_view(st);
     const bool nested = st->qabsmax != nullptr;
@@ -564,13 +565,16 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         const bool compact = dyn_base == kDynBase && !env_aligned && kLutBytes + rest <= 200 * 1024;
         if (!compact && rest > 63 * 1024) return Q4_ERR_SHAPE;
         const size_t smem = compact ? kLutBytes + rest : kSmemAligned;
-        auto kern = compact ? (nested ? gemv_lut256_kernel<T, true, false, true> : gemv_lut256_kernel<T, false, false, true>)
-                            : (nested ? gemv_lut256_kernel<T, true, false, false> : gemv_lut256_kernel<T, false, false, false>);
-        static bool attr_set[2][2] = {{false, false}, {false, false}};
-        if (!attr_set[compact][nested]) {
+        const bool multi = nmat > 1 && nested;  // without nested statistics a group is just a taller matrix
+        auto kern = compact ? (nested ? (multi ? gemv_lut256_kernel<T, true, true, true> : gemv_lut256_kernel<T, true, false, true>)
+                                      : gemv_lut256_kernel<T, false, false, true>)
+                            : (nested ? (multi ? gemv_lut256_kernel<T, true, true, false> : gemv_lut256_kernel<T, true, false, false>)
+                                      : gemv_lut256_kernel<T, false, false, false>);
+        static bool attr_set[2][2][2] = {};
+        if (!attr_set[compact][nested][multi]) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, compact ? 200 * 1024 : kSmemAligned);
             if (e != cudaSuccess) return (int)e;
-            attr_set[compact][nested] = true;
+            attr_set[compact][nested][multi] = true;
         }
         GemvArgs a = {};
         a.x = x;
@@ -582,6 +586,13 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             a.row_end[m] = 0x7fffffff;
         }
         a.offsets[0] = v.offset;
+        if (multi) {
+            for (int m = 0; m < nmat; m++) {
+                a.offsets[m] = offsets[m];
+                a.row_end[m] = row_end[m];
+            }
+            a.row_end[nmat - 1] = 0x7fffffff;
+        }
         a.out = out;
         a.bias = bias;
         a.rows = (int)N;
@@ -599,6 +610,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         grid = (int)((N + a.rows_per_cta - 1) / a.rows_per_cta);
         return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, pdl, a);
     }
+    if (nmat > 1) return Q4_ERR_SHAPE;  // grouped launches exist only on the fast path
     // generic: x as fp32 in shared memory
     const size_t smem = 128 + sizeof(float) * (size_t)K;
     if (smem > 200 * 1024) return Q4_ERR_SHAPE;
@@ -609,6 +621,36 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
     const int64_t cap = (int64_t)sms * (smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
     const int grid = (int)(want < cap ? want : cap);
     return launch_pdl(kern, dim3(grid), dim3(256), smem, stream, pdl, x, B, v, code, bias, out, N, K, ilog2(blocksize));
+}
+
+int gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* const* offsets, const int* row_end,
+                      int nmat, const float* code, const void* bias, void* out, int64_t rows, int64_t K, int blocksize, int dtype,
+                      int flags, const void* next, int64_t next_bytes, cudaStream_t stream)
+{
+    if (!valid_blocksize(blocksize)) return Q4_ERR_BLOCKSIZE;
+    if (rows < 0 || K < 0 || (K & 1) || nmat < 1 || nmat > kMaxMats) return Q4_ERR_SHAPE;
+    if (rows == 0) return 0;
+    if (!x || !B || !code || !out || !row_end) return Q4_ERR_NULL;
+    if (int e = check_stats(stats)) return e;
+    if (stats->qabsmax) {
+        if (!offsets) return Q4_ERR_NULL;
+        for (int m = 0; m < nmat; m++)
+            if (!offsets[m]) return Q4_ERR_NULL;
+    }
+    for (int m = 0; m < nmat; m++)
+        if (row_end[m] <= (m ? row_end[m - 1] : 0) || row_end[m] > rows) return Q4_ERR_SHAPE;
+    if (row_end[nmat - 1] != rows) return Q4_ERR_SHAPE;
+    flags &= ~Q4_GEMV_EXACT_F32;
+    switch (dtype) {
+        case Q4_F16:
+            return gemv_dispatch<__half>((const __half*)x, B, stats, code, (const __half*)bias, (__half*)out, rows, K, blocksize,
+                                         flags, next, next_bytes, stream, nmat, offsets, row_end);
+        case Q4_BF16:
+            return gemv_dispatch<__nv_bfloat16>((const __nv_bfloat16*)x, B, stats, code, (const __nv_bfloat16*)bias,
+                                                (__nv_bfloat16*)out, rows, K, blocksize, flags, next, next_bytes, stream, nmat,
+                                                offsets, row_end);
+        default: return Q4_ERR_DTYPE;
+    }
 }
 
 int gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,

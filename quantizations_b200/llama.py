@@ -54,6 +54,16 @@ class DecoderLayer(nn.Module):
         self.down_proj = make(cfg.inter // tp, h, f"L{layer}.down_proj")
         self.ln1 = nn.Parameter(torch.ones(h))
         self.ln2 = nn.Parameter(torch.ones(h))
+        # siblings that read the same activation are served by one grouped decode launch when they are Linear4bit
+        self.qkv = self.gate_up = None
+        try:
+            from .modules import Linear4bit, Linear4bitGroup
+
+            if all(isinstance(m, Linear4bit) for m in (self.q_proj, self.k_proj, self.v_proj, self.gate_proj, self.up_proj)):
+                self.qkv = Linear4bitGroup([self.q_proj, self.k_proj, self.v_proj])
+                self.gate_up = Linear4bitGroup([self.gate_proj, self.up_proj])
+        except ValueError:
+            self.qkv = self.gate_up = None
 
 
 class Llama(nn.Module):
@@ -98,9 +108,11 @@ class Llama(nn.Module):
         mask = self.positions[None, :] <= pos[:, None]                      # [T, max_len]
         for li, L in enumerate(self.layers):
             h = F.rms_norm(x, (cfg.hidden,), L.ln1, cfg.eps)
-            q = L.q_proj(h).view(T, L.nh, L.hd)
-            k = L.k_proj(h).view(T, L.nkv, L.hd)
-            v = L.v_proj(h).view(T, L.nkv, L.hd)
+            if L.qkv is not None and T == 1:
+                q, k, v = L.qkv(h)
+            else:
+                q, k, v = L.q_proj(h), L.k_proj(h), L.v_proj(h)
+            q, k, v = q.reshape(T, L.nh, L.hd), k.reshape(T, L.nkv, L.hd), v.reshape(T, L.nkv, L.hd)
             q, k = self._rope(q, cos, sin), self._rope(k, cos, sin)
             self.k_cache[li].index_copy_(1, pos, k.transpose(0, 1))
             self.v_cache[li].index_copy_(1, pos, v.transpose(0, 1))
@@ -109,7 +121,11 @@ class Llama(nn.Module):
             a = a.squeeze(0).transpose(0, 1).reshape(1, T, L.nh * L.hd)
             x = x + self._allreduce(L.o_proj(a))
             h = F.rms_norm(x, (cfg.hidden,), L.ln2, cfg.eps)
-            x = x + self._allreduce(L.down_proj(F.silu(L.gate_proj(h)) * L.up_proj(h)))
+            if L.gate_up is not None and T == 1:
+                g, u = L.gate_up(h)
+            else:
+                g, u = L.gate_proj(h), L.up_proj(h)
+            x = x + self._allreduce(L.down_proj(F.silu(g) * u))
         x = F.rms_norm(x[:, -1:], (cfg.hidden,), self.norm, cfg.eps)
         return F.linear(x, self.lm_head).view(-1)
 

@@ -110,3 +110,91 @@ class Linear4bit(nn.Linear):
         out = matmul_4bit(x, weight.data, bias=bias, quant_state=weight.quant_state, flags=self.gemv_flags,
                           prefetch=self.prefetch_next)
         return out if out.dtype == inp_dtype else out.to(inp_dtype)
+
+
+class Linear4bitGroup(nn.Module):
+    """Several quantised Linear4bit layers that consume the same activation (q/k/v, gate/up), served by ONE decode launch.
+
+    The members' packed weights and statistics are re-laid back to back in one allocation (each member keeps working on its
+    own: its `weight.data` / QuantState tensors become views of the shared buffers), and a single-vector forward runs
+    q4_gemv_4bit_grouped over the concatenated rows: one prologue (table build, activation staging) instead of one per
+    member, and a grid sized for the sum of the rows.  Anything else (prefill, unsupported dtype) falls back to the members.
+    Requirements: all quantised, same in_features / blocksize 64 / quant_type / nesting, no bias, and for nested statistics
+    N_i * K / 64 a multiple of 256 so that no second-level block straddles two members.
+    """
+
+    def __init__(self, linears):
+        super().__init__()
+        import ctypes
+
+        from ._lib import AbsmaxStats
+
+        self.members = nn.ModuleList(linears)
+        first = linears[0].weight.quant_state
+        K = linears[0].in_features
+        nested = first.nested
+        for lin in linears:
+            qs = lin.weight.quant_state
+            if qs is None or lin.in_features != K or qs.blocksize != 64 or qs.quant_type != first.quant_type or qs.nested != nested:
+                raise ValueError("Linear4bitGroup members must be quantised alike and share in_features")
+            if lin.bias is not None:
+                raise ValueError("Linear4bitGroup does not support biases")
+            if nested and (lin.out_features * K // 64) % qs.state2.blocksize:
+                raise ValueError("nested statistics would straddle two members")
+        if len(linears) > 4 or K % 64:
+            raise ValueError("at most 4 members, in_features a multiple of 64")
+        dev = linears[0].weight.device
+        self.in_features, self.splits = K, [lin.out_features for lin in linears]
+        self.out_features = sum(self.splits)
+        self.packed = torch.cat([lin.weight.data.reshape(-1) for lin in linears]).reshape(-1, 1)
+        self.absmax = torch.cat([lin.weight.quant_state.absmax for lin in linears])
+        self.absmax2 = torch.cat([lin.weight.quant_state.state2.absmax for lin in linears]) if nested else None
+        o_p = o_a = o_a2 = 0
+        for lin in linears:  # members become views of the shared buffers
+            qs = lin.weight.quant_state
+            n_p, n_a = lin.weight.data.numel(), qs.absmax.numel()
+            lin.weight.data = self.packed[o_p:o_p + n_p]
+            qs.absmax = self.absmax[o_a:o_a + n_a]
+            if nested:
+                n_a2 = qs.state2.absmax.numel()
+                qs.state2.absmax = self.absmax2[o_a2:o_a2 + n_a2]
+                qs.state2._stats = None
+                o_a2 += n_a2
+            qs._stats = None
+            o_p, o_a = o_p + n_p, o_a + n_a
+        self.code, self.blocksize, self.nested = first.code, 64, nested
+        if nested:
+            self._stats = AbsmaxStats(None, self.absmax.data_ptr(), first.state2.code.data_ptr(), self.absmax2.data_ptr(),
+                                      first.offset.data_ptr(), int(first.state2.blocksize))
+            self._offsets = (ctypes.c_void_p * len(linears))(*[lin.weight.quant_state.offset.data_ptr() for lin in linears])
+        else:
+            self._stats = AbsmaxStats(self.absmax.data_ptr(), None, None, None, None, 0)
+            self._offsets = None
+        ends, acc = [], 0
+        for n in self.splits:
+            acc += n
+            ends.append(acc)
+        self._row_end = (ctypes.c_int * len(linears))(*ends)
+        self.gemv_flags = _lib.Q4_GEMV_PDL
+        self.prefetch_next = None
+        self.device_ = dev
+
+    def forward_fused(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """[.., K] single vector -> [.., sum N_i] (concatenated member outputs)."""
+        if out is None:
+            out = torch.empty(x.shape[:-1] + (self.out_features,), dtype=x.dtype, device=x.device)
+        pf = self.prefetch_next
+        rc = _lib.lib().q4_gemv_4bit_grouped(
+            x.data_ptr(), self.packed.data_ptr(), self._stats, self._offsets, self._row_end, len(self.splits), self.code.data_ptr(),
+            None, out.data_ptr(), self.out_features, self.in_features, 64, {torch.float16: _lib.Q4_F16, torch.bfloat16: _lib.Q4_BF16}[x.dtype],
+            self.gemv_flags, None if pf is None else pf.data_ptr(), 0 if pf is None else pf.numel() * pf.element_size(),
+            torch.cuda.current_stream(x.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "q4_gemv_4bit_grouped")
+        return out
+
+    def forward(self, x: torch.Tensor):
+        """Returns one output per member, like calling them in turn."""
+        if x.numel() == x.shape[-1] and x.dtype in (torch.float16, torch.bfloat16) and x.is_contiguous():
+            return self.forward_fused(x).split(self.splits, dim=-1)
+        return tuple(lin(x) for lin in self.members)

@@ -409,3 +409,31 @@ def test_llama_decode_matches_dense_model_with_dequantised_weights(q):
     t_eager, _ = mq.generate(prompt, 12, use_graph=False)
     t_graph, _ = mq.generate(prompt, 12, use_graph=True)
     assert torch.equal(t_eager, t_graph)
+
+
+@pytest.mark.parametrize("nested", [True, False])
+@pytest.mark.parametrize("quant_type", ["nf4", "fp4"])
+def test_grouped_gemv_equals_member_gemvs(q, nested, quant_type):
+    """Linear4bitGroup (q/k/v in one launch) returns bit-identical outputs to the members called one by one: same kernel
+    arithmetic per row, only the launch is shared; the members keep working on their re-laid (view) storage."""
+    torch.manual_seed(5)
+    K, Ns = 1024, [1024, 256, 512]
+    lins = []
+    for n in Ns:
+        lin = q.Linear4bit(K, n, bias=False, compute_dtype=torch.bfloat16, compress_statistics=nested, quant_type=quant_type)
+        lins.append(lin.to(DEV))
+    x = torch.randn(1, 1, K, device=DEV, dtype=torch.bfloat16)
+    before = [lin(x).clone() for lin in lins]
+    grp = q.Linear4bitGroup(lins)
+    outs = grp(x)
+    after = [lin(x) for lin in lins]
+    assert [o.shape[-1] for o in outs] == Ns
+    for b, o, a_ in zip(before, outs, after):
+        assert torch.equal(b, a_), "re-laying the storage changed a member's output"
+        assert torch.equal(b, o), "grouped launch differs from the member launch"
+    # prefill falls back to the members
+    xp = torch.randn(1, 5, K, device=DEV, dtype=torch.bfloat16)
+    op = grp(xp)
+    assert [o.shape for o in op] == [(1, 5, n) for n in Ns]
+    with pytest.raises(ValueError):
+        q.Linear4bitGroup([lins[0], q.Linear4bit(512, 64, quant_type=quant_type, compress_statistics=nested).to(DEV)])
