@@ -153,6 +153,17 @@ def run_ours(args, rank, world, device):
     layers = args.layers or cfg["layers"]
     tp = world
     mods = build_stack(cfg, tp, rank, device, dtype, "nf4", layers, q)
+    # launch units: with grouping (default) q/k/v and gate/up of a layer are one grouped launch each (Linear4bitGroup)
+    units = []
+    if args.group:
+        for l0 in range(0, len(mods), 7):
+            qm, km, vm, om, gm, um, dm = mods[l0:l0 + 7]
+            for u in (q.Linear4bitGroup([qm, km, vm]), om, q.Linear4bitGroup([gm, um]), dm):
+                units.append(u)
+        for u, name, par in zip(units, ["qkv_proj", "o_proj", "gate_up_proj", "down_proj"] * layers, ["col", "row", "col", "row"] * layers):
+            u.name_, u.parallel = name, par
+    else:
+        units = list(mods)
     step_bytes_local = sum(algo_bytes(m.out_features, m.in_features) for m in mods)
     step_bytes = step_bytes_local * world  # every rank streams its own shard
     packed_bytes = sum(m.weight.numel() for m in mods)
@@ -161,7 +172,7 @@ def run_ours(args, rank, world, device):
     torch.manual_seed(1)
     x_in = {K: torch.randn(1, 1, K, device=device, dtype=dtype) for K in {m.in_features for m in mods}}
     outs = {}
-    for m in mods:
+    for m in units:
         outs.setdefault((m.name_, m.out_features), torch.empty(1, 1, m.out_features, device=device, dtype=dtype))
     comm = None
     if world > 1:
@@ -175,14 +186,15 @@ def run_ours(args, rank, world, device):
     # GEMVs go to parallel streams (parallel branches of the CUDA graph) with Q4_GEMV_SHARE_SM so they are co-resident on
     # every SM; dependent ones follow in stream order with programmatic dependent launch.
     side = [torch.cuda.Stream(device=device) for _ in range(2)] if args.branches else []
-    branch_of = {"q_proj": 0, "k_proj": 1, "v_proj": 2, "o_proj": 0, "gate_proj": 0, "up_proj": 1, "down_proj": 0}
+    branch_of = {"q_proj": 0, "k_proj": 1, "v_proj": 2, "o_proj": 0, "gate_proj": 0, "up_proj": 1, "down_proj": 0,
+                 "qkv_proj": 0, "gate_up_proj": 0}
     forks = {"q_proj", "gate_proj"}            # a parallel section starts here ...
     joins = {"o_proj", "down_proj"}            # ... and has ended before these
 
     def run_stack(launch):
         """walk the stack in model order, placing each Linear on its branch; `launch(i, m, flags)` issues the work"""
         main = torch.cuda.current_stream()
-        for i, m in enumerate(mods):
+        for i, m in enumerate(units):
             b = branch_of[m.name_] if side else 0
             if side and m.name_ in forks:
                 for st in side:
@@ -200,14 +212,22 @@ def run_ours(args, rank, world, device):
         for st in side:
             main.wait_stream(st)
 
+    def packed_of(u):
+        return u.packed if isinstance(u, q.Linear4bitGroup) else u.weight
+
     def launch_cabi(i, m, flags):
-        st = m.weight.quant_state
         out = outs[(m.name_, m.out_features)]
-        nxt = mods[(i + 1) % len(mods)].weight if args.prefetch else None  # the following Linear's packed weight
-        rc = L.q4_gemv_4bit(x_in[m.in_features].data_ptr(), m.weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None,
-                            out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags,
-                            None if nxt is None else nxt.data_ptr(), 0 if nxt is None else nxt.numel(),
-                            torch.cuda.current_stream().cuda_stream)
+        nxt = packed_of(units[(i + 1) % len(units)]) if args.prefetch else None  # the following launch's packed weight
+        npt, nby = (None, 0) if nxt is None else (nxt.data_ptr(), nxt.numel())
+        stream = torch.cuda.current_stream().cuda_stream
+        if isinstance(m, q.Linear4bitGroup):
+            rc = L.q4_gemv_4bit_grouped(x_in[m.in_features].data_ptr(), m.packed.data_ptr(), m._stats, m._offsets, m._row_end,
+                                        len(m.splits), m.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, 64,
+                                        _lib.Q4_BF16, flags, npt, nby, stream)
+        else:
+            st = m.weight.quant_state
+            rc = L.q4_gemv_4bit(x_in[m.in_features].data_ptr(), m.weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None,
+                                out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags, npt, nby, stream)
         if rc:
             _lib.check(rc, "q4_gemv_4bit")
         if comm is not None and m.parallel == "row":
@@ -266,8 +286,8 @@ def run_ours(args, rank, world, device):
 
     def launch_api(i, m, flags):
         m.gemv_flags = flags
-        m.prefetch_next = mods[(i + 1) % len(mods)].weight if args.prefetch else None
-        y = m(x_static[m.in_features])
+        m.prefetch_next = packed_of(units[(i + 1) % len(units)]) if args.prefetch else None
+        y = m.forward_fused(x_static[m.in_features]) if isinstance(m, q.Linear4bitGroup) else m(x_static[m.in_features])
         if comm is not None and m.parallel == "row":
             comm.all_reduce(y)
         y_static[(m.name_, m.out_features)] = y
@@ -317,7 +337,8 @@ def run_ours(args, rank, world, device):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": f"{args.model} Linear4bit stack, NF4 + double-quant, blocksize 64, bs=1 decode: {layers} layers x "
-                        f"(q,k,v,o,gate,up,down) = {len(mods)} GEMVs/step per GPU" + (f", tensor-parallel tp{world} (NCCL all-reduce after o_proj/down_proj)" if world > 1 else ""),
+                        f"(q,k,v,o,gate,up,down) = {len(mods)} GEMVs/step per GPU"
+                        + (f" in {len(units)} launches (q/k/v and gate/up grouped: they share their input)" if args.group else "") + (f", tensor-parallel tp{world} (NCCL all-reduce after o_proj/down_proj)" if world > 1 else ""),
             "shapes": sorted({f"{m.out_features}x{m.in_features}" for m in mods}),
             "packed_weight_bytes_per_gpu": packed_bytes, "algorithmic_bytes_per_step": step_bytes,
             "l2_policy": "inputs larger than L2: every layer has its own weights (3.5 GB/step >> 126 MB L2), no flush needed",
@@ -330,7 +351,7 @@ def run_ours(args, rank, world, device):
         "decode_linear_tok_s": round(1e3 / ms_per_step, 1),
         "e2e": {"value": round(step_bytes / (e2e_ms * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "quantizations_b200.Linear4bit.forward x%d under quantizations_b200.graphs.capture, pinned-host x in / y out" % len(mods)},
+                "api": "quantizations_b200.Linear4bit / Linear4bitGroup forward x%d under quantizations_b200.graphs.capture, pinned-host x in / y out" % len(units)},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": "q4::gemv_lut256_kernel<bf16, nested>", "achieved": round(value / world, 1), "peak": peak,
@@ -517,6 +538,7 @@ def main():
     ap.add_argument("--branches", action="store_true",
                     help="launch q/k/v and gate/up as parallel graph branches (measured slower than one stream + PDL: the graph's "
                          "cross-stream edges cost more than the co-residency gains on 1-5 us kernels)")
+    ap.add_argument("--no-group", dest="group", action="store_false", help="one launch per Linear instead of grouped q/k/v and gate/up")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the end-to-end Llama-3-8B decode tok/s leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -260,7 +260,7 @@ gemv_lut256_kernel(const GemvArgs a)
         blk += blk_stride;
     };
     trace_mark(a, 1);
-    // ---- 2. lookup table: stage the 512 distinct words (loaded in step 0b), then replicate each 32x:
+    // ---- 3. lookup table: stage the 512 distinct words (loaded in step 0b), then replicate each 32x:
     //         128-B segment 2b = half2{code[b>>4], code[b&15]}, segment 2b+1 = code2[b] (fp32).
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -281,9 +281,8 @@ gemv_lut256_kernel(const GemvArgs a)
             *reinterpret_cast<uint4*>(lut + c * 16) = make_uint4(word, word, word, word);
         }
     }
-
-    // ---- 3. first U rows in flight, requested after the table build (see step 1) and before the dependency wait: under
-    //         programmatic dependent launch they stream in while the previous kernel is still running.
+    // ---- 3b. first U rows in flight: after the table build (see step 1), before the dependency wait -- under programmatic
+    //          dependent launch they stream in while the previous kernel is still running.
 #pragma unroll
     for (int i = 0; i < U; i++) {
 #pragma unroll
@@ -292,18 +291,28 @@ gemv_lut256_kernel(const GemvArgs a)
         a2[i] = 0.0f;
         if (i < rows_mine) issue_row(i);
     }
-    __syncthreads();  // lookup table visible
     trace_mark(a, 2);
 
-    // ---- 4. everything below may read the previous kernel's output
+    // ---- everything below may read the previous kernel's output
     pdl_wait();
     trace_mark(a, 3);
-
-    // ---- 5. x -> half2, scaled by one power of two so that max|x| lands in [1,2) (fp16 cannot overflow; the products
-    //         are accumulated 8 deep in fp16, then in fp32).  Done once per CTA: threads convert 8 elements per step and
-    //         store them swizzled, then each thread fetches the 64 values of its own k-slice into registers.
     const T* xg = reinterpret_cast<const T*>(a.x);
-    const int nchunk = K >> 3;  // 8-element chunks
+    const int nchunk = K >> 3;  // 8-element (16-byte for 16-bit types) chunks of x
+    constexpr int XR = 8;       // raw chunks a thread may hold: covers K <= 64 * blockDim (dispatcher)
+    constexpr bool kRawX = sizeof(T) == 2;
+    uint4 xraw[kRawX ? XR : 1];
+    if constexpr (kRawX) {
+#pragma unroll
+        for (int j = 0; j < XR; j++) {
+            const int c = tid + j * nthr;
+            xraw[j] = make_uint4(0, 0, 0, 0);
+            if (c < nchunk) xraw[j] = __ldg(reinterpret_cast<const uint4*>(xg) + c);
+        }
+    }
+
+    // ---- 4. x -> half2, scaled by one power of two so that max|x| lands in [1,2) (fp16 cannot overflow; the products
+    //         are accumulated 8 deep in fp16, then in fp32).  Done once per CTA from the raw chunks already in registers:
+    //         CTA-wide max, convert, store swizzled; then each thread fetches the 64 values of its own k-slice.
     auto load_chunk = [&](int c, float (&v)[8]) {
         if constexpr (sizeof(T) == 2) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(xg) + c);
@@ -315,26 +324,41 @@ gemv_lut256_kernel(const GemvArgs a)
             v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
         }
     };
+    auto unpack_raw = [&](const uint4& q, float (&v)[8]) {
+        using T16 = typename std::conditional<sizeof(T) == 2, T, __half>::type;
+        const float2 f0 = unpack2<T16>(q.x), f1 = unpack2<T16>(q.y), f2 = unpack2<T16>(q.z), f3 = unpack2<T16>(q.w);
+        v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+    };
     float m = 0.0f;
-    for (int c = tid; c < nchunk; c += nthr) {
-        float v[8];
-        load_chunk(c, v);
+    if constexpr (kRawX) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) m = fmaxf(m, fabsf(v[j]));
+        for (int j = 0; j < XR; j++) {
+            if (tid + j * nthr < nchunk) {
+                float v[8];
+                unpack_raw(xraw[j], v);
+#pragma unroll
+                for (int e8 = 0; e8 < 8; e8++) m = fmaxf(m, fabsf(v[e8]));
+            }
+        }
+    } else {
+        for (int c = tid; c < nchunk; c += nthr) {
+            float v[8];
+            load_chunk(c, v);
+#pragma unroll
+            for (int j = 0; j < 8; j++) m = fmaxf(m, fabsf(v[j]));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) s_red[warp] = m;
-    __syncthreads();
+    __syncthreads();  // also: lookup table visible
     m = 0.0f;
     for (int i = 0; i < (nthr >> 5); i++) m = fmaxf(m, s_red[i]);
     int e = (int)((__float_as_uint(m) >> 23) & 0xFF);  // biased exponent of the largest |x|
     e = e < 1 ? 1 : (e > 253 ? 253 : e);
     const float scale = __uint_as_float((uint32_t)(254 - e) << 23);  // 2^(127-e)
     const float unscale = __uint_as_float((uint32_t)e << 23);        // 2^(e-127)
-    for (int c = tid; c < nchunk; c += nthr) {  // second pass hits L1
-        float v[8];
-        load_chunk(c, v);
+    auto store_chunk = [&](int c, const float (&v)[8]) {
         uint32_t h[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -343,7 +367,25 @@ gemv_lut256_kernel(const GemvArgs a)
         }
         const int kb = c >> 3, j = c & 7;
         s_x[kb * 8 + (j ^ (kb & 7))] = make_uint4(h[0], h[1], h[2], h[3]);  // swizzle: conflict-free both ways
+    };
+    if constexpr (kRawX) {
+#pragma unroll
+        for (int j = 0; j < XR; j++) {
+            const int c = tid + j * nthr;
+            if (c < nchunk) {
+                float v[8];
+                unpack_raw(xraw[j], v);
+                store_chunk(c, v);
+            }
+        }
+    } else {
+        for (int c = tid; c < nchunk; c += nthr) {  // second pass hits L1
+            float v[8];
+            load_chunk(c, v);
+            store_chunk(c, v);
+        }
     }
+
     __syncthreads();
     uint32_t xh[32];
 #pragma unroll
