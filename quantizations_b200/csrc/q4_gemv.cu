@@ -102,6 +102,8 @@ struct GemvArgs {
     int kw;      // warps that together cover one row: ceil(K / 2048)
     int groups;  // row groups per CTA: blockDim / (32 * kw)
     int rows_per_cta;
+    int lut_iters;   // ceil(4096 / blockDim)
+    int x_iters;     // ceil(K / 8 / blockDim): raw activation chunks per thread
     int debug_mode;             // developer experiments (env Q4_GEMV_DEBUG): 1 = skip the table lookups
     unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA; nullptr = off
 };
@@ -274,7 +276,8 @@ gemv_lut256_kernel(const GemvArgs a)
     }
     __syncthreads();
     trace_mark(a, 7);
-    for (int c = tid; c < kLutBytes / 16; c += nthr) {
+    for (int it = 0, c = tid; it < a.lut_iters; it++, c += nthr) {  // trip count from the host: no integer division here
+        if (c >= kLutBytes / 16) break;
         const int seg = c >> 3;
         if (NESTED || !(seg & 1)) {
             const uint32_t word = s_words[(seg >> 1) | ((seg & 1) << 8)];
@@ -306,7 +309,7 @@ gemv_lut256_kernel(const GemvArgs a)
         for (int j = 0; j < XR; j++) {
             const int c = tid + j * nthr;
             xraw[j] = make_uint4(0, 0, 0, 0);
-            if (c < nchunk) xraw[j] = __ldg(reinterpret_cast<const uint4*>(xg) + c);
+            if (j < a.x_iters && c < nchunk) xraw[j] = __ldg(reinterpret_cast<const uint4*>(xg) + c);
         }
     }
 
@@ -333,9 +336,9 @@ gemv_lut256_kernel(const GemvArgs a)
     if constexpr (kRawX) {
 #pragma unroll
         for (int j = 0; j < XR; j++) {
-            if (tid + j * nthr < nchunk) {
+            if (j < a.x_iters) {  // uniform: K = 4096 needs one chunk per thread, not eight
                 float v[8];
-                unpack_raw(xraw[j], v);
+                unpack_raw(xraw[j], v);  // chunks past the end are zeros
 #pragma unroll
                 for (int e8 = 0; e8 < 8; e8++) m = fmaxf(m, fabsf(v[e8]));
             }
@@ -372,7 +375,7 @@ gemv_lut256_kernel(const GemvArgs a)
 #pragma unroll
         for (int j = 0; j < XR; j++) {
             const int c = tid + j * nthr;
-            if (c < nchunk) {
+            if (j < a.x_iters && c < nchunk) {
                 float v[8];
                 unpack_raw(xraw[j], v);
                 store_chunk(c, v);
@@ -641,6 +644,8 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         a.K = (int)K;
         a.kw = kw;
         a.groups = groups;
+        a.lut_iters = (kLutBytes / 16 + threads - 1) / threads;
+        a.x_iters = (int)((K / 8 + threads - 1) / threads);
         a.trace = g_gemv_trace;
         static const int env_debug = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
         a.debug_mode = env_debug;
