@@ -124,6 +124,33 @@ int q4_gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* sta
                          const int* row_end, int nmat, const float* code, const void* bias, void* out, int64_t rows, int64_t K,
                          int blocksize, int dtype, int flags, const void* prefetch, int64_t prefetch_bytes, void* stream);
 
+/* Decode GEMV with the surrounding elementwise glue of a transformer block fused in (everything optional, NULL = off):
+ *   rms_weight : the activation is RMS-normalised first, x * rsqrt(mean(x^2) + rms_eps) * rms_weight  (fp32, rounded to dtype)
+ *   x_gate     : the activation is silu(x_gate[k]) * x[k]  (SwiGLU: x = up-projection output, x_gate = gate output)
+ *   bias       : added to the output; it may alias `out`, which makes it a residual stream updated in place
+ *   nmat > 1   : grouped launch, see q4_gemv_4bit_grouped (offsets / row_end as there; NULL for a single matrix)
+ * so a decoder layer's Linear4bit work is four launches: norm+qkv, o+residual, norm+gate/up, swiglu+down+residual.
+ * fp16/bf16 activations, blocksize 64, K % 64 == 0; with rms_weight K <= 16384. */
+typedef struct q4_gemv_fused_t {
+    const void* x;
+    const void* x_gate;
+    const void* rms_weight;
+    float rms_eps;
+    const uint8_t* B;
+    const q4_absmax_t* stats;
+    const float* const* offsets;
+    const int* row_end;
+    int nmat;
+    const float* code;
+    const void* bias;
+    void* out;
+    int64_t rows, K;
+    int blocksize, dtype, flags;
+    const void* prefetch;
+    int64_t prefetch_bytes;
+} q4_gemv_fused_t;
+int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
+
 /* Prefill / batched path with the dequantisation fused into a tcgen05 tensor-core GEMM:
  *     out[m, r] = sum_k X[m, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r]),   m in [0, M), r in [0, N)
  * X [M, K], out [M, N], bias [N] are `dtype` (Q4_F16 or Q4_BF16), row-major contiguous; accumulation is fp32 (TMEM).

@@ -11,6 +11,7 @@ from .core import (  # noqa: F401
     dequantize_4bit,
     dequantize_blockwise,
     gemm_4bit,
+    gemv_4bit_fused,
     gemv_4bit,
     get_4bit_type,
     quantize_4bit,

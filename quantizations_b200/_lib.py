@@ -33,6 +33,18 @@ class AbsmaxStats(ctypes.Structure):
     ]
 
 
+class GemvFused(ctypes.Structure):
+    """q4_gemv_fused_t"""
+
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("x_gate", ctypes.c_void_p), ("rms_weight", ctypes.c_void_p), ("rms_eps", ctypes.c_float),
+        ("B", ctypes.c_void_p), ("stats", ctypes.POINTER(AbsmaxStats)), ("offsets", ctypes.POINTER(ctypes.c_void_p)),
+        ("row_end", ctypes.POINTER(ctypes.c_int)), ("nmat", ctypes.c_int), ("code", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("K", ctypes.c_int64), ("blocksize", ctypes.c_int),
+        ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("prefetch", ctypes.c_void_p), ("prefetch_bytes", ctypes.c_int64),
+    ]  # fmt: skip
+
+
 _vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 _SIGNATURES = {
     # reference names (pythonInterface.cpp:154-161)
@@ -48,6 +60,7 @@ _SIGNATURES = {
     "q4_dequantize_blockwise_4bit": [_vp, ctypes.POINTER(AbsmaxStats), _vp, _i, _i64, _i, _i, _vp],
     "q4_gemv_4bit_grouped": [_vp, _vp, ctypes.POINTER(AbsmaxStats), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), _i,
                              _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
+    "q4_gemv_4bit_fused": [ctypes.POINTER(GemvFused), _vp],
     "q4_gemm_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
     "q4_gemv_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
 }

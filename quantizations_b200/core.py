@@ -553,3 +553,60 @@ def dequantize_4bit(
     out = torch.empty(quant_state.shape, dtype=quant_state.dtype, device=A.device)
     _dequantize_4bit_into(A, quant_state, out)
     return out.t()
+
+
+def gemv_4bit_fused(
+    A: Tensor,
+    B: Tensor,
+    state: Optional[QuantState] = None,
+    *,
+    group=None,
+    gate: Optional[Tensor] = None,
+    rms_weight: Optional[Tensor] = None,
+    rms_eps: float = 1e-5,
+    residual: Optional[Tensor] = None,
+    out: Optional[Tensor] = None,
+    flags: int = _lib.Q4_GEMV_PDL,
+    prefetch: Optional[Tensor] = None,
+) -> Tensor:
+    """Decode GEMV with a transformer block's elementwise glue fused in (include/quantizations_b200.h: q4_gemv_4bit_fused):
+
+        x_eff = A                                   (default)
+              = rms_norm(A) * rms_weight            (rms_weight given)
+              = silu(gate) * A                      (gate given: A is the up-projection output)
+        out   = x_eff @ dequant(B)^T  (+ residual)  (residual may be `out` itself: in-place residual stream)
+
+    `group` (a Linear4bitGroup) runs the grouped launch over its members instead of a single (B, state)."""
+    if A.numel() != A.shape[-1]:
+        raise ValueError("gemv_4bit_fused needs a single activation vector")
+    if A.dtype not in (torch.float16, torch.bfloat16):
+        raise NotImplementedError("fused decode GEMV needs fp16/bf16 activations")
+    import ctypes
+
+    if group is not None:
+        rows, K, stats, code, packed = group.out_features, group.in_features, group._stats, group.code, group.packed
+        offsets, row_end, nmat, blocksize = group._offsets, group._row_end, len(group.splits), 64
+    else:
+        if state is None:
+            raise ValueError("state cannot be None")
+        rows, K, stats, code, packed = state.shape[0], state.shape[1], state.native_stats(), state.code, B
+        offsets, row_end, nmat, blocksize = None, None, 1, state.blocksize
+    if A.shape[-1] != K:
+        raise ValueError(f"A has {A.shape[-1]} features but the quantised weight expects {K}")
+    for t in (gate, rms_weight):
+        if t is not None and (t.dtype != A.dtype or t.numel() != K):
+            raise ValueError("gate / rms_weight must match the activation's dtype and length")
+    if residual is not None and (residual.dtype != A.dtype or residual.numel() != rows):
+        raise ValueError("residual must match the output's dtype and length")
+    if out is None:
+        out = torch.empty(A.shape[:-1] + (rows,), dtype=A.dtype, device=A.device)
+    f = _lib.GemvFused(
+        A.data_ptr(), None if gate is None else gate.data_ptr(), None if rms_weight is None else rms_weight.data_ptr(), float(rms_eps),
+        packed.data_ptr(), ctypes.pointer(stats), offsets, row_end, nmat, code.data_ptr(),
+        None if residual is None else residual.data_ptr(), out.data_ptr(), rows, K, blocksize, _DTYPE_CODE[A.dtype], flags,
+        None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
+    )
+    rc = _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
+    if rc:
+        check(rc, "gemv_4bit_fused")
+    return out

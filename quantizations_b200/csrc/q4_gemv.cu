@@ -95,7 +95,10 @@ struct GemvArgs {
     const float* offsets[kMaxMats];  // nested: per-matrix offset scalars (device pointers)
     int row_end[kMaxMats];     // exclusive end row of each matrix (INT_MAX for unused slots)
     void* out;                 // [rows]
-    const void* bias;          // [rows] or nullptr
+    const void* bias;          // [rows] or nullptr (may alias `out`: a residual stream updated in place)
+    const void* x_gate;        // optional: the effective activation is silu(x_gate[k]) * x[k]   (SwiGLU, fused)
+    const void* rms_weight;    // optional: the effective activation is x * rsqrt(mean(x^2) + rms_eps) * rms_weight  (RMSNorm, fused)
+    float rms_eps;
     const uint8_t* next;       // optional: bytes the NEXT launch will stream (pulled into L2 while this one computes)
     int64_t next_bytes;
     int rows, K;
@@ -310,6 +313,63 @@ gemv_lut256_kernel(const GemvArgs a)
             const int c = tid + j * nthr;
             xraw[j] = make_uint4(0, 0, 0, 0);
             if (j < a.x_iters && c < nchunk) xraw[j] = __ldg(reinterpret_cast<const uint4*>(xg) + c);
+        }
+        // ---- fused input transforms (decode glue that would otherwise be separate launches and HBM round trips).  Both
+        //      leave a "virtual x" in xraw, rounded to T exactly where the separate torch kernels round.
+        using T16 = typename std::conditional<sizeof(T) == 2, T, __half>::type;
+        if (a.x_gate) {  // SwiGLU: silu(gate) * up, F.silu then multiply, each rounded to T
+#pragma unroll
+            for (int j = 0; j < XR; j++) {
+                const int c = tid + j * nthr;
+                if (j < a.x_iters && c < nchunk) {
+                    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(a.x_gate) + c);
+                    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+                    uint32_t uw[4] = {xraw[j].x, xraw[j].y, xraw[j].z, xraw[j].w};
+#pragma unroll
+                    for (int q2 = 0; q2 < 4; q2++) {
+                        const float2 g = unpack2<T16>(gw[q2]), u = unpack2<T16>(uw[q2]);
+                        const float2 sg = unpack2<T16>(pack2<T16>(g.x / (1.0f + expf(-g.x)), g.y / (1.0f + expf(-g.y))));
+                        uw[q2] = pack2<T16>(sg.x * u.x, sg.y * u.y);
+                    }
+                    xraw[j] = make_uint4(uw[0], uw[1], uw[2], uw[3]);
+                }
+            }
+        }
+        if (a.rms_weight) {  // RMSNorm in fp32 over the whole vector (every CTA stages all of x), rounded to T once
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < XR; j++) {
+                if (j < a.x_iters) {
+                    const uint32_t xw[4] = {xraw[j].x, xraw[j].y, xraw[j].z, xraw[j].w};
+#pragma unroll
+                    for (int q2 = 0; q2 < 4; q2++) {
+                        const float2 f = unpack2<T16>(xw[q2]);
+                        ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) s_red[16 + warp] = ss;
+            __syncthreads();
+            ss = 0.0f;
+            for (int i = 0; i < (nthr >> 5); i++) ss += s_red[16 + i];
+            const float rs = rsqrtf(ss / (float)K + a.rms_eps);
+#pragma unroll
+            for (int j = 0; j < XR; j++) {
+                const int c = tid + j * nthr;
+                if (j < a.x_iters && c < nchunk) {
+                    const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(a.rms_weight) + c);
+                    const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                    uint32_t xw[4] = {xraw[j].x, xraw[j].y, xraw[j].z, xraw[j].w};
+#pragma unroll
+                    for (int q2 = 0; q2 < 4; q2++) {
+                        const float2 f = unpack2<T16>(xw[q2]), g = unpack2<T16>(ww[q2]);
+                        xw[q2] = pack2<T16>(f.x * rs * g.x, f.y * rs * g.y);
+                    }
+                    xraw[j] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+                }
+            }
         }
     }
 
@@ -549,6 +609,12 @@ gemv_generic_kernel(const T* __restrict__ x, const uint8_t* __restrict__ Bq, Abs
 
 // ------------------------------------------------------------------------------------------------ host dispatch
 
+struct GemvPrologue {  // optional fused input transforms (16-bit activations only)
+    const void* x_gate = nullptr;
+    const void* rms_weight = nullptr;
+    float rms_eps = 0.0f;
+};
+
 template <typename K, typename... Args>
 static int launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args)
 {
@@ -570,7 +636,8 @@ static int launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t
 template <typename T>
 static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, const float* code, const T* bias, T* out,
                          int64_t N, int64_t K, int blocksize, int flags, const void* next, int64_t next_bytes, cudaStream_t stream,
-                         int nmat = 1, const float* const* offsets = nullptr, const int* row_end = nullptr)
+                         int nmat = 1, const float* const* offsets = nullptr, const int* row_end = nullptr,
+                         const GemvPrologue* pro = nullptr)
 {
     const AbsmaxView v = make_view(st);
     const bool nested = st->qabsmax != nullptr;
@@ -640,6 +707,13 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         }
         a.out = out;
         a.bias = bias;
+        if (pro) {
+            if (sizeof(T) != 2) return Q4_ERR_DTYPE;
+            if ((reinterpret_cast<uintptr_t>(pro->x_gate) & 15) || (reinterpret_cast<uintptr_t>(pro->rms_weight) & 15)) return Q4_ERR_ALIGN;
+            a.x_gate = pro->x_gate;
+            a.rms_weight = pro->rms_weight;
+            a.rms_eps = pro->rms_eps;
+        }
         a.rows = (int)N;
         a.K = (int)K;
         a.kw = kw;
@@ -657,7 +731,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         grid = (int)((N + a.rows_per_cta - 1) / a.rows_per_cta);
         return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, pdl, a);
     }
-    if (nmat > 1) return Q4_ERR_SHAPE;  // grouped launches exist only on the fast path
+    if (nmat > 1 || (pro && (pro->x_gate || pro->rms_weight))) return Q4_ERR_SHAPE;  // only the fast path groups / fuses
     // generic: x as fp32 in shared memory
     const size_t smem = 128 + sizeof(float) * (size_t)K;
     if (smem > 200 * 1024) return Q4_ERR_SHAPE;
@@ -668,6 +742,41 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
     const int64_t cap = (int64_t)sms * (smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
     const int grid = (int)(want < cap ? want : cap);
     return launch_pdl(kern, dim3(grid), dim3(256), smem, stream, pdl, x, B, v, code, bias, out, N, K, ilog2(blocksize));
+}
+
+int gemv_4bit_fused(const q4_gemv_fused_t* f, cudaStream_t stream)
+{
+    if (!f) return Q4_ERR_NULL;
+    if (!valid_blocksize(f->blocksize)) return Q4_ERR_BLOCKSIZE;
+    const int nmat = f->nmat < 1 ? 1 : f->nmat;
+    if (f->rows < 0 || f->K < 0 || (f->K & 1) || nmat > kMaxMats) return Q4_ERR_SHAPE;
+    if (f->rows == 0) return 0;
+    if (!f->x || !f->B || !f->code || !f->out) return Q4_ERR_NULL;
+    if (int e = check_stats(f->stats)) return e;
+    int one_end[1] = {(int)f->rows};
+    const int* row_end = f->row_end ? f->row_end : one_end;
+    const float* one_off[1] = {f->stats->offset};
+    const float* const* offsets = f->offsets ? f->offsets : one_off;
+    if (nmat > 1 && (!f->row_end || (f->stats->qabsmax && !f->offsets))) return Q4_ERR_NULL;
+    for (int m = 0; m < nmat; m++)
+        if (row_end[m] <= (m ? row_end[m - 1] : 0) || row_end[m] > f->rows) return Q4_ERR_SHAPE;
+    if (row_end[nmat - 1] != f->rows) return Q4_ERR_SHAPE;
+    GemvPrologue pro;
+    pro.x_gate = f->x_gate;
+    pro.rms_weight = f->rms_weight;
+    pro.rms_eps = f->rms_eps;
+    const int flags = f->flags & ~Q4_GEMV_EXACT_F32;
+    switch (f->dtype) {
+        case Q4_F16:
+            return gemv_dispatch<__half>((const __half*)f->x, f->B, f->stats, f->code, (const __half*)f->bias, (__half*)f->out,
+                                         f->rows, f->K, f->blocksize, flags, f->prefetch, f->prefetch_bytes, stream, nmat, offsets,
+                                         row_end, &pro);
+        case Q4_BF16:
+            return gemv_dispatch<__nv_bfloat16>((const __nv_bfloat16*)f->x, f->B, f->stats, f->code, (const __nv_bfloat16*)f->bias,
+                                                (__nv_bfloat16*)f->out, f->rows, f->K, f->blocksize, flags, f->prefetch,
+                                                f->prefetch_bytes, stream, nmat, offsets, row_end, &pro);
+        default: return Q4_ERR_DTYPE;
+    }
 }
 
 int gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* const* offsets, const int* row_end,

@@ -18,6 +18,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .core import gemv_4bit_fused
+
 
 @dataclass
 class LlamaConfig:
@@ -70,6 +72,7 @@ class Llama(nn.Module):
     def __init__(self, cfg: LlamaConfig, linear_factory: Callable, device, dtype=torch.bfloat16, tp: int = 1, group=None):
         super().__init__()
         self.cfg, self.tp, self.group, self.dtype = cfg, tp, group, dtype
+        self.fuse_glue = True  # fold RMSNorm / SwiGLU / residual adds into the decode GEMV launches (Linear4bit layers only)
         g = torch.Generator(device=device).manual_seed(1234)
         self.embed = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
         self.lm_head = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
@@ -107,8 +110,11 @@ class Llama(nn.Module):
         # causal mask over the whole static cache: key j visible to query i iff j <= pos[i]
         mask = self.positions[None, :] <= pos[:, None]                      # [T, max_len]
         for li, L in enumerate(self.layers):
-            h = F.rms_norm(x, (cfg.hidden,), L.ln1, cfg.eps)
-            if L.qkv is not None and T == 1:
+            fused = L.qkv is not None and T == 1 and self.fuse_glue
+            h = None if fused else F.rms_norm(x, (cfg.hidden,), L.ln1, cfg.eps)
+            if fused:  # RMSNorm folded into the grouped q/k/v launch: the norm kernel and its round trip disappear
+                q, k, v = gemv_4bit_fused(x, None, group=L.qkv, rms_weight=L.ln1, rms_eps=cfg.eps).split(L.qkv.splits, dim=-1)
+            elif L.qkv is not None and T == 1:
                 q, k, v = L.qkv(h)
             else:
                 q, k, v = L.q_proj(h), L.k_proj(h), L.v_proj(h)
@@ -119,6 +125,14 @@ class Llama(nn.Module):
             a = F.scaled_dot_product_attention(q.transpose(0, 1).unsqueeze(0), self.k_cache[li].unsqueeze(0),
                                                self.v_cache[li].unsqueeze(0), attn_mask=mask, enable_gqa=True)  # [1, nh, T, hd]
             a = a.squeeze(0).transpose(0, 1).reshape(1, T, L.nh * L.hd)
+            if fused and self.tp == 1:
+                # o_proj adds the residual stream in its epilogue; norm folded into gate/up; SwiGLU folded into down_proj's
+                # activation staging, residual again in its epilogue: four launches for the layer's seven Linears + glue
+                qs = L.o_proj.weight.quant_state
+                x = gemv_4bit_fused(a, L.o_proj.weight.data, qs, residual=x)
+                g, u = gemv_4bit_fused(x, None, group=L.gate_up, rms_weight=L.ln2, rms_eps=cfg.eps).split(L.gate_up.splits, dim=-1)
+                x = gemv_4bit_fused(u, L.down_proj.weight.data, L.down_proj.weight.quant_state, gate=g, residual=x)
+                continue
             x = x + self._allreduce(L.o_proj(a))
             h = F.rms_norm(x, (cfg.hidden,), L.ln2, cfg.eps)
             if L.gate_up is not None and T == 1:

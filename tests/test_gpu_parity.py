@@ -437,3 +437,35 @@ def test_grouped_gemv_equals_member_gemvs(q, nested, quant_type):
     assert [o.shape for o in op] == [(1, 5, n) for n in Ns]
     with pytest.raises(ValueError):
         q.Linear4bitGroup([lins[0], q.Linear4bit(512, 64, quant_type=quant_type, compress_statistics=nested).to(DEV)])
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_fused_decode_glue_matches_separate_torch_ops(q, dtype):
+    """gemv_4bit_fused: RMSNorm / SwiGLU folded into the activation staging and the residual add into the epilogue give the
+    same result as the separate torch kernels followed by the plain GEMV (tolerance: one rounding of the output type)."""
+    torch.manual_seed(9)
+    dt = TDT[dtype]
+    K, N = 4096, 1024
+    W = (torch.randn(N, K, device=DEV) * 0.02).to(dt)
+    packed, state = q.quantize_4bit(W, quant_type="nf4")
+    x = torch.randn(1, 1, K, device=DEV, dtype=dt) * 3
+    gamma = (1 + 0.1 * torch.randn(K, device=DEV)).to(dt)
+    res = torch.randn(1, 1, N, device=DEV, dtype=dt)
+    gate = torch.randn(1, 1, K, device=DEV, dtype=dt)
+    tol = {"bfloat16": 1.6e-2, "float16": 2e-3}[dtype]
+
+    ref = q.gemv_4bit(torch.nn.functional.rms_norm(x, (K,), gamma, 1e-5), packed, state=state).float() + res.float()
+    got = q.gemv_4bit_fused(x, packed, state, rms_weight=gamma, rms_eps=1e-5, residual=res).float()
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+    ref = q.gemv_4bit(torch.nn.functional.silu(gate) * x, packed, state=state).float()
+    got = q.gemv_4bit_fused(x, packed, state, gate=gate).float()
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+    # in-place residual stream: out aliases residual
+    stream = res.clone()
+    q.gemv_4bit_fused(x, packed, state, residual=stream, out=stream)
+    ref = q.gemv_4bit(x, packed, state=state).float() + res.float()
+    assert (stream.float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+    # plain call through the fused entry point is bit-identical to gemv_4bit
+    assert torch.equal(q.gemv_4bit_fused(x, packed, state), q.gemv_4bit(x, packed, state=state))
