@@ -215,23 +215,31 @@ def run_ours(args, rank, world, device):
     def packed_of(u):
         return u.packed if isinstance(u, q.Linear4bitGroup) else u.weight
 
+    fused_args = {}
+
     def launch_cabi(i, m, flags):
-        out = outs[(m.name_, m.out_features)]
-        nxt = packed_of(units[(i + 1) % len(units)]) if args.prefetch else None  # the following launch's packed weight
-        npt, nby = (None, 0) if nxt is None else (nxt.data_ptr(), nxt.numel())
-        stream = torch.cuda.current_stream().cuda_stream
-        if isinstance(m, q.Linear4bitGroup):
-            rc = L.q4_gemv_4bit_grouped(x_in[m.in_features].data_ptr(), m.packed.data_ptr(), m._stats, m._offsets, m._row_end,
-                                        len(m.splits), m.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, 64,
-                                        _lib.Q4_BF16, flags, npt, nby, stream)
-        else:
-            st = m.weight.quant_state
-            rc = L.q4_gemv_4bit(x_in[m.in_features].data_ptr(), m.weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None,
-                                out.data_ptr(), m.out_features, m.in_features, st.blocksize, _lib.Q4_BF16, flags, npt, nby, stream)
+        """q4_gemv_4bit_fused (include/quantizations_b200.h) with the prebuilt table image; argument structs are built once"""
+        key = (i, flags)
+        f = fused_args.get(key)
+        if f is None:
+            out = outs[(m.name_, m.out_features)]
+            nxt = packed_of(units[(i + 1) % len(units)]) if args.prefetch else None  # the following launch's packed weight
+            npt, nby = (None, 0) if nxt is None else (nxt.data_ptr(), nxt.numel())
+            if isinstance(m, q.Linear4bitGroup):
+                f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.packed.data_ptr(), ctypes.pointer(m._stats), m._offsets,
+                                   m._row_end, len(m.splits), m.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, 64,
+                                   _lib.Q4_BF16, flags, npt, nby, m.lut(dtype).data_ptr())
+            else:
+                st = m.weight.quant_state
+                f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.weight.data_ptr(), ctypes.pointer(st.native_stats()), None,
+                                   None, 1, st.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, st.blocksize,
+                                   _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr())
+            fused_args[key] = f
+        rc = L.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream().cuda_stream)
         if rc:
-            _lib.check(rc, "q4_gemv_4bit")
+            _lib.check(rc, "q4_gemv_4bit_fused")
         if comm is not None and m.parallel == "row":
-            comm.all_reduce(out)
+            comm.all_reduce(outs[(m.name_, m.out_features)])
 
     def step_cabi():
         """one decode token's worth of Linear4bit GEMVs straight through the C ABI"""
@@ -354,7 +362,7 @@ def run_ours(args, rank, world, device):
                 "api": "quantizations_b200.Linear4bit / Linear4bitGroup forward x%d under quantizations_b200.graphs.capture, pinned-host x in / y out" % len(units)},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk.summary(),
-        "roofline": {"bound": "hbm", "kernel": "q4::gemv_lut256_kernel<bf16, nested>", "achieved": round(value / world, 1), "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "q4::gemv_mma_kernel<bf16, nested>", "achieved": round(value / world, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(value / world / peak, 4), "peak_source": peak_src,
                      "avg_launch_us": round(per_launch_us, 3), "algorithmic_bytes_per_launch": step_bytes_local // launches_per_step,
                      "traffic": None, "timed_blocks_ms": [round(t, 3) for t in times[:5]]},

@@ -148,8 +148,17 @@ typedef struct q4_gemv_fused_t {
     int blocksize, dtype, flags;
     const void* prefetch;
     int64_t prefetch_bytes;
+    const void* lut; /* optional: table image from q4_gemv_lut_build for this code / stats->code2 / dtype (NULL: built per launch) */
 } q4_gemv_fused_t;
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
+
+/* The decode GEMV decodes one packed BYTE per shared-memory lookup through a 64-KB table derived from the 16-entry 4-bit code
+ * and the 256-entry absmax code (reference: `T quant_map[16]` in kernels.cu:1115-1121 and `code[q]` in kernels.cu:552).  The
+ * table depends only on (code, code2, dtype), i.e. it is the same for every Linear4bit of a model: build it once into
+ * Q4_GEMV_LUT_BYTES of 16-byte aligned device memory and pass it as q4_gemv_fused_t.lut; each launch then fetches it with one
+ * TMA bulk copy instead of rebuilding it.  code2 may be NULL (no nested statistics).  dtype: Q4_F16 or Q4_BF16. */
+#define Q4_GEMV_LUT_BYTES 65536
+int q4_gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, void* stream);
 
 /* Prefill / batched path with the dequantisation fused into a tcgen05 tensor-core GEMM:
  *     out[m, r] = sum_k X[m, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r]),   m in [0, M), r in [0, N)

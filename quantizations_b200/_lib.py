@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libquantizations_b200.so")
 Q4_F32, Q4_F16, Q4_BF16 = 0, 1, 2
 Q4_GENERAL8BIT, Q4_FP4, Q4_NF4 = 0, 1, 2
 Q4_GEMV_DEFAULT, Q4_GEMV_EXACT_F32, Q4_GEMV_PDL, Q4_GEMV_SHARE_SM = 0, 1, 2, 4
+Q4_GEMV_LUT_BYTES = 65536
 
 
 class Q4Error(RuntimeError):
@@ -42,6 +43,7 @@ class GemvFused(ctypes.Structure):
         ("row_end", ctypes.POINTER(ctypes.c_int)), ("nmat", ctypes.c_int), ("code", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("K", ctypes.c_int64), ("blocksize", ctypes.c_int),
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("prefetch", ctypes.c_void_p), ("prefetch_bytes", ctypes.c_int64),
+        ("lut", ctypes.c_void_p),
     ]  # fmt: skip
 
 
@@ -61,6 +63,7 @@ _SIGNATURES = {
     "q4_gemv_4bit_grouped": [_vp, _vp, ctypes.POINTER(AbsmaxStats), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), _i,
                              _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
     "q4_gemv_4bit_fused": [ctypes.POINTER(GemvFused), _vp],
+    "q4_gemv_lut_build": [_vp, _vp, _i, _vp, _vp],
     "q4_gemm_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
     "q4_gemv_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
 }

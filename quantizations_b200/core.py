@@ -46,6 +46,36 @@ def _stream(t: Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+# Decode-GEMV table images (include/quantizations_b200.h: q4_gemv_lut_build), one per (device, dtype, table contents): every
+# Linear4bit of a model shares a single 64-KB image, so it stays L2-resident and each launch fetches it with one bulk copy.
+_gemv_luts = {}
+
+
+def gemv_lut(code: Tensor, code2: Optional[Tensor], dtype: torch.dtype) -> Tensor:
+    """Table image for the given 4-bit code / 8-bit absmax code / activation dtype; built once per distinct contents.
+    The first call for a given pair of tensors reads them back to the host (1 KB) to key the cache -- do it outside CUDA-graph
+    capture (quantize_4bit does it at load time)."""
+    key = (code.device, dtype, code.data_ptr(), 0 if code2 is None else code2.data_ptr(), code._version,
+           0 if code2 is None else code2._version)
+    hit = _gemv_luts.get(key)
+    if hit is not None:
+        return hit[0]
+    content = (code.device, dtype, code.detach().float().cpu().numpy().tobytes(),
+               b"" if code2 is None else code2.detach().float().cpu().numpy().tobytes())
+    hit = _gemv_luts.get(content)
+    if hit is None:
+        lut = torch.empty(_lib.Q4_GEMV_LUT_BYTES, dtype=torch.uint8, device=code.device)
+        c32 = code.detach().float().contiguous()
+        c2 = None if code2 is None else code2.detach().float().contiguous()
+        with torch.cuda.device(code.device):
+            check(_lib.lib().q4_gemv_lut_build(c32.data_ptr(), None if c2 is None else c2.data_ptr(), _DTYPE_CODE[dtype],
+                                               lut.data_ptr(), _stream(code)), "gemv_lut_build")
+        hit = (lut,)
+        _gemv_luts[content] = hit
+    _gemv_luts[key] = (hit[0], code, code2)  # keeps the keyed tensors alive: their addresses cannot be recycled
+    return hit[0]
+
+
 class QuantState:
     """Container for the quantisation statistics of one tensor; layout of reference core.py:23-88.
 
@@ -85,6 +115,7 @@ class QuantState:
         self.state2 = state2
         self.nested = state2 is not None
         self._stats = None  # cached C struct of pointers (see native_stats)
+        self._luts = {}     # decode-GEMV table image per activation dtype (see gemv_lut)
 
     def to(self, device):
         """Move the statistics to `device` (reference core.py:78-88; also handles a non-nested state)."""
@@ -97,6 +128,15 @@ class QuantState:
             self.state2.code = self.state2.code.to(device)
             self.state2._stats = None
         self._stats = None
+        self._luts = {}
+
+    def lut(self, dtype: torch.dtype) -> Tensor:
+        """Decode-GEMV table image for activations of `dtype` (fp16 / bf16)."""
+        t = self._luts.get(dtype)
+        if t is None:
+            t = gemv_lut(self.code, self.state2.code if self.nested else None, dtype)
+            self._luts[dtype] = t
+        return t
 
     def native_stats(self) -> AbsmaxStats:
         """q4_absmax_t view of this state (include/quantizations_b200.h); cached until the tensors move."""
@@ -430,6 +470,20 @@ def gemv_4bit(
     if not A.is_contiguous():
         A = A.contiguous()
     lib = _lib.lib()
+    if A.dtype != torch.float32 and state.blocksize == 64 and not (flags & _lib.Q4_GEMV_EXACT_F32):
+        # 16-bit decode path: same kernel, but with the prebuilt table image (one bulk copy instead of a per-launch build)
+        import ctypes
+
+        f = _lib.GemvFused(
+            A.data_ptr(), None, None, 0.0, B.data_ptr(), ctypes.pointer(state.native_stats()), None, None, 1, state.code.data_ptr(),
+            None if bias is None else bias.data_ptr(), out.data_ptr(), bout, k, state.blocksize, _DTYPE_CODE[A.dtype], flags,
+            None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
+            state.lut(A.dtype).data_ptr(),
+        )
+        rc = lib.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
+        if rc != 0:
+            check(rc, "gemv_4bit")
+        return out
     code = lib.q4_gemv_4bit(
         A.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
         None if bias is None else bias.data_ptr(), out.data_ptr(), bout, k, state.blocksize,
@@ -515,6 +569,8 @@ def quantize_4bit(
     else:
         state = QuantState(absmax=absmax, shape=input_shape, dtype=A.dtype, blocksize=blocksize, code=code,
                            quant_type=quant_type)
+    if blocksize == 64 and A.dtype in (torch.float16, torch.bfloat16):
+        state.lut(A.dtype)  # decode table for the likely compute dtype, keyed now so that decode can run under graph capture
     return out, state
 
 
@@ -586,11 +642,13 @@ def gemv_4bit_fused(
     if group is not None:
         rows, K, stats, code, packed = group.out_features, group.in_features, group._stats, group.code, group.packed
         offsets, row_end, nmat, blocksize = group._offsets, group._row_end, len(group.splits), 64
+        lut = group.lut(A.dtype)
     else:
         if state is None:
             raise ValueError("state cannot be None")
         rows, K, stats, code, packed = state.shape[0], state.shape[1], state.native_stats(), state.code, B
         offsets, row_end, nmat, blocksize = None, None, 1, state.blocksize
+        lut = state.lut(A.dtype)
     if A.shape[-1] != K:
         raise ValueError(f"A has {A.shape[-1]} features but the quantised weight expects {K}")
     for t in (gate, rms_weight):
@@ -605,6 +663,7 @@ def gemv_4bit_fused(
         packed.data_ptr(), ctypes.pointer(stats), offsets, row_end, nmat, code.data_ptr(),
         None if residual is None else residual.data_ptr(), out.data_ptr(), rows, K, blocksize, _DTYPE_CODE[A.dtype], flags,
         None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
+        lut.data_ptr(),
     )
     rc = _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
     if rc:

@@ -119,6 +119,11 @@ int q4_gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* sta
 
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream) { return q4::gemv_4bit_fused(args, (cudaStream_t)stream); }
 
+int q4_gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, void* stream)
+{
+    return q4::gemv_lut_build(code, code2, dtype, lut, (cudaStream_t)stream);
+}
+
 int q4_gemm_4bit(const void* X, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
                  int64_t M, int64_t N, int64_t K, int blocksize, int dtype, void* stream)
 {

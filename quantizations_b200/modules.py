@@ -179,19 +179,15 @@ class Linear4bitGroup(nn.Module):
         self.prefetch_next = None
         self.device_ = dev
 
+    def lut(self, dtype):
+        """Decode table image shared by the members (same code tables by construction)."""
+        return self.members[0].weight.quant_state.lut(dtype)
+
     def forward_fused(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
         """[.., K] single vector -> [.., sum N_i] (concatenated member outputs)."""
-        if out is None:
-            out = torch.empty(x.shape[:-1] + (self.out_features,), dtype=x.dtype, device=x.device)
-        pf = self.prefetch_next
-        rc = _lib.lib().q4_gemv_4bit_grouped(
-            x.data_ptr(), self.packed.data_ptr(), self._stats, self._offsets, self._row_end, len(self.splits), self.code.data_ptr(),
-            None, out.data_ptr(), self.out_features, self.in_features, 64, {torch.float16: _lib.Q4_F16, torch.bfloat16: _lib.Q4_BF16}[x.dtype],
-            self.gemv_flags, None if pf is None else pf.data_ptr(), 0 if pf is None else pf.numel() * pf.element_size(),
-            torch.cuda.current_stream(x.device).cuda_stream)
-        if rc:
-            _lib.check(rc, "q4_gemv_4bit_grouped")
-        return out
+        from .core import gemv_4bit_fused
+
+        return gemv_4bit_fused(x, None, group=self, out=out, flags=self.gemv_flags, prefetch=self.prefetch_next)
 
     def forward(self, x: torch.Tensor):
         """Returns one output per member, like calling them in turn."""

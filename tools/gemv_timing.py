@@ -88,6 +88,7 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--only", default="", help="NxK: time just this shape")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-lut", action="store_true", help="no prebuilt table image: the kernel builds its table per launch")
     ap.add_argument("--next", action="store_true", help="hint the next matrix of the pool for L2 prefetch")
     ap.add_argument("--streams", type=int, default=1, help="parallel capture branches (independent launches)")
     a = ap.parse_args()
@@ -127,10 +128,22 @@ def main():
         dcode = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[dt]
         ptrs = [m.data_ptr() for m in mats]
 
+        lut = None if (a.no_lut or dt == torch.float32) else st0.lut(dt)
+        fused = [_lib.GemvFused(x.data_ptr(), None, None, 0.0, ptrs[i], ctypes.pointer(stats), None, None, 1, st0.code.data_ptr(), None,
+                                outs2[i % NSTREAMS].data_ptr(), N, K, 64, dcode, a.flags, ptrs[(i + 1) % nmat] if a.next else None,
+                                per if a.next else 0, None if lut is None else lut.data_ptr()) for i in range(nmat)]
+
         def ours(i):
-            L.q4_gemv_4bit(x.data_ptr(), ptrs[i % nmat], stats, st0.code.data_ptr(), None, outs2[i % NSTREAMS].data_ptr(), N, K, 64, dcode,
-                           a.flags, ptrs[(i + 1) % nmat] if a.next else None, per if a.next else 0,
-                           torch.cuda.current_stream().cuda_stream)
+            if dt == torch.float32:
+                L.q4_gemv_4bit(x.data_ptr(), ptrs[i % nmat], stats, st0.code.data_ptr(), None, outs2[i % NSTREAMS].data_ptr(), N, K, 64,
+                               dcode, a.flags, None, 0, torch.cuda.current_stream().cuda_stream)
+            else:
+                L.q4_gemv_4bit_fused(ctypes.byref(fused[i % nmat]), torch.cuda.current_stream().cuda_stream)
+
+        # accuracy against an fp32 matmul of the dequantised weight
+        ours(0)
+        truth = (x.double().view(1, K) @ q.dequantize_4bit(mats[0], st0).double()).view(-1)
+        err = ((outs2[0].double().view(-1) - truth).abs().max() / truth.abs().max()).item()
 
         def ours_py(i):
             q.gemv_4bit(x, mats[i % nmat], out=out, state=st0)
@@ -138,7 +151,7 @@ def main():
         tp = time_fn(ours_py, a.iters)
         t = time_fn(ours, a.iters) if a.no_graph else time_graph(ours, nmat * 2)
         B = algo_bytes(N, K, x.element_size())
-        line = f"{N:6d}x{K:<6d} ours(graph) {t:8.2f} us  {B / t / 1e3:8.1f} GB/s ({B / t / 1e3 / peak * 100:5.1f}% of measured peak)  eager core.gemv_4bit {tp:8.2f} us"
+        line = f"{N:6d}x{K:<6d} ours(graph) {t:8.2f} us  {B / t / 1e3:8.1f} GB/s ({B / t / 1e3 / peak * 100:5.1f}% of measured peak)  err {err:.1e}  eager core.gemv_4bit {tp:8.2f} us"
         if shim is not None:
             absmax = (q.dequantize_blockwise(st0.absmax, st0.state2) + st0.offset).contiguous()
             fn = {torch.float32: shim.ref_gemv_fp32, torch.float16: shim.ref_gemv_fp16, torch.bfloat16: shim.ref_gemv_bf16}[dt]

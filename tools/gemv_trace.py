@@ -19,10 +19,13 @@ out = torch.empty(1, 1, N, device=dev, dtype=torch.bfloat16)
 NL = 6
 traces = [torch.zeros(148 * 8, dtype=torch.int64, device=dev) for _ in range(NL)]
 stream = torch.cuda.current_stream().cuda_stream
+lut = None if os.environ.get("NO_LUT") else st.lut(torch.bfloat16)
+stats = st.native_stats()
+fused = [_lib.GemvFused(x.data_ptr(), None, None, 0.0, m.data_ptr(), ctypes.pointer(stats), None, None, 1, st.code.data_ptr(), None,
+                        out.data_ptr(), N, K, 64, 2, flags, None, 0, None if lut is None else lut.data_ptr()) for m in mats]
 def launch(i, tr):
     L.q4_debug_set_gemv_trace(tr.data_ptr() if tr is not None else None)
-    L.q4_gemv_4bit(x.data_ptr(), mats[i % 8].data_ptr(), st.native_stats(), st.code.data_ptr(), None, out.data_ptr(), N, K, 64, 2,
-                   flags, None, 0, stream)
+    L.q4_gemv_4bit_fused(ctypes.byref(fused[i % 8]), stream)
 for i in range(10):
     launch(i, None)
 torch.cuda.synchronize()
@@ -39,7 +42,7 @@ g.replay(); torch.cuda.synchronize()
 junk.fill_(2); torch.cuda.synchronize()
 g.replay(); torch.cuda.synchronize()
 L.q4_debug_set_gemv_trace(None)
-names = ["start", "issued", "lut", "waited", "x ready", "batch0", "end", "words"]
+names = ["start", "issued", "waited", "x staged", "loop done", "end", "table ok"]
 t0 = None
 for i, tr in enumerate(traces):
     t = tr.cpu().view(148, 8)
