@@ -216,6 +216,7 @@ def run_ours(args, rank, world, device):
         return u.packed if isinstance(u, q.Linear4bitGroup) else u.weight
 
     fused_args = {}
+    ws_ptr, ws_bytes = q.core._ws_args(device)  # (None, 0) unless Q4_GEMV_TC=1: the mma.sync kernel is the default
 
     def launch_cabi(i, m, flags):
         """q4_gemv_4bit_fused (include/quantizations_b200.h) with the prebuilt table image; argument structs are built once"""
@@ -228,12 +229,12 @@ def run_ours(args, rank, world, device):
             if isinstance(m, q.Linear4bitGroup):
                 f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.packed.data_ptr(), ctypes.pointer(m._stats), m._offsets,
                                    m._row_end, len(m.splits), m.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, 64,
-                                   _lib.Q4_BF16, flags, npt, nby, m.lut(dtype).data_ptr())
+                                   _lib.Q4_BF16, flags, npt, nby, m.lut(dtype).data_ptr(), ws_ptr, ws_bytes)
             else:
                 st = m.weight.quant_state
                 f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.weight.data_ptr(), ctypes.pointer(st.native_stats()), None,
                                    None, 1, st.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, st.blocksize,
-                                   _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr())
+                                   _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr(), ws_ptr, ws_bytes)
             fused_args[key] = f
         rc = L.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream().cuda_stream)
         if rc:

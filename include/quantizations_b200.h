@@ -149,6 +149,10 @@ typedef struct q4_gemv_fused_t {
     const void* prefetch;
     int64_t prefetch_bytes;
     const void* lut; /* optional: table image from q4_gemv_lut_build for this code / stats->code2 / dtype (NULL: built per launch) */
+    void* workspace; /* optional: Q4_GEMV_WORKSPACE_BYTES of device memory, zeroed ONCE by the caller, owned by one stream at a time.
+                      * With lut and workspace the tcgen05 kernel runs (row tiles split along K across CTAs, partial sums combined
+                      * through the workspace in a fixed order; it leaves the workspace zeroed); without, the mma.sync kernel. */
+    int64_t workspace_bytes;
 } q4_gemv_fused_t;
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
 
@@ -158,6 +162,7 @@ int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
  * Q4_GEMV_LUT_BYTES of 16-byte aligned device memory and pass it as q4_gemv_fused_t.lut; each launch then fetches it with one
  * TMA bulk copy instead of rebuilding it.  code2 may be NULL (no nested statistics).  dtype: Q4_F16 or Q4_BF16. */
 #define Q4_GEMV_LUT_BYTES 65536
+#define Q4_GEMV_WORKSPACE_BYTES (8 << 20)
 int q4_gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, void* stream);
 
 /* Prefill / batched path with the dequantisation fused into a tcgen05 tensor-core GEMM:

@@ -9,12 +9,13 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libquantizations_b200.so")
+LIB_PATH = os.environ.get("Q4_LIB_PATH") or os.path.join(_HERE, "libquantizations_b200.so")  # override: developer A/B builds
 
 Q4_F32, Q4_F16, Q4_BF16 = 0, 1, 2
 Q4_GENERAL8BIT, Q4_FP4, Q4_NF4 = 0, 1, 2
 Q4_GEMV_DEFAULT, Q4_GEMV_EXACT_F32, Q4_GEMV_PDL, Q4_GEMV_SHARE_SM = 0, 1, 2, 4
 Q4_GEMV_LUT_BYTES = 65536
+Q4_GEMV_WORKSPACE_BYTES = 8 << 20
 
 
 class Q4Error(RuntimeError):
@@ -43,7 +44,7 @@ class GemvFused(ctypes.Structure):
         ("row_end", ctypes.POINTER(ctypes.c_int)), ("nmat", ctypes.c_int), ("code", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("K", ctypes.c_int64), ("blocksize", ctypes.c_int),
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("prefetch", ctypes.c_void_p), ("prefetch_bytes", ctypes.c_int64),
-        ("lut", ctypes.c_void_p),
+        ("lut", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
     ]  # fmt: skip
 
 

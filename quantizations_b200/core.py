@@ -16,6 +16,7 @@ There is no CPU path: a non-CUDA tensor raises NotImplementedError exactly where
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -44,6 +45,31 @@ _NF4_VALUES = [
 
 def _stream(t: Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+# Split-K workspace of the tcgen05 decode GEMV (include/quantizations_b200.h: q4_gemv_fused_t.workspace): zeroed once, one per
+# (device, stream) because launches on different streams may run concurrently.
+_gemv_workspaces = {}
+
+
+# The tcgen05 kernel is opt-in (Q4_GEMV_TC=1): on B200 it currently measures slower than the mma.sync kernel.
+_USE_TC = os.environ.get("Q4_GEMV_TC", "0") == "1"
+
+
+def _ws_args(device):
+    """(pointer, bytes) of the split-K workspace to pass with a decode GEMV: (None, 0) selects the mma.sync kernel."""
+    if not _USE_TC:
+        return None, 0
+    return gemv_workspace(device).data_ptr(), _lib.Q4_GEMV_WORKSPACE_BYTES
+
+
+def gemv_workspace(device) -> Tensor:
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _gemv_workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.Q4_GEMV_WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+        _gemv_workspaces[key] = ws
+    return ws
 
 
 # Decode-GEMV table images (include/quantizations_b200.h: q4_gemv_lut_build), one per (device, dtype, table contents): every
@@ -478,7 +504,7 @@ def gemv_4bit(
             A.data_ptr(), None, None, 0.0, B.data_ptr(), ctypes.pointer(state.native_stats()), None, None, 1, state.code.data_ptr(),
             None if bias is None else bias.data_ptr(), out.data_ptr(), bout, k, state.blocksize, _DTYPE_CODE[A.dtype], flags,
             None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
-            state.lut(A.dtype).data_ptr(),
+            state.lut(A.dtype).data_ptr(), *_ws_args(A.device),
         )
         rc = lib.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
         if rc != 0:
@@ -663,7 +689,7 @@ def gemv_4bit_fused(
         packed.data_ptr(), ctypes.pointer(stats), offsets, row_end, nmat, code.data_ptr(),
         None if residual is None else residual.data_ptr(), out.data_ptr(), rows, K, blocksize, _DTYPE_CODE[A.dtype], flags,
         None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
-        lut.data_ptr(),
+        lut.data_ptr(), *_ws_args(A.device),
     )
     rc = _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
     if rc:

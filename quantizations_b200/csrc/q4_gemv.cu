@@ -20,6 +20,7 @@
 
 #include "q4_common.cuh"
 #include "q4_gemv_mma.cuh"
+#include "q4_gemv_tc.cuh"
 #include "q4_launch.h"
 
 namespace q4 {
@@ -96,6 +97,8 @@ struct GemvPrologue {  // optional fused input transforms (16-bit activations on
     const void* rms_weight = nullptr;
     float rms_eps = 0.0f;
     const void* lut = nullptr;  // prebuilt table image (q4_gemv_lut_build) for this code / code2 / dtype
+    void* workspace = nullptr;  // split-K workspace of the tcgen05 kernel (zeroed once by the caller)
+    int64_t workspace_bytes = 0;
 };
 
 template <typename K, typename... Args>
@@ -135,6 +138,91 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         const bool mma_ok = fast && (K % 128) == 0 && K <= 32768 &&
                             (!nested || ((reinterpret_cast<uintptr_t>(st->qabsmax) & 1) == 0 && st->blocksize2 >= 128)) &&
                             (nested || (reinterpret_cast<uintptr_t>(st->absmax) & 7) == 0);
+        // where does dynamic shared memory start in the CTA's window?  (probed once; the compact table layout depends on it)
+        static int dyn_base = -1;
+        if (dyn_base < 0) {
+            uint32_t* d = nullptr;
+            uint32_t h = 0;
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(stream, &cap);
+            if (cap == cudaStreamCaptureStatusNone && cudaMalloc(&d, 4) == cudaSuccess) {
+                probe_dyn_smem_base_kernel<<<1, 32, 1024, stream>>>(d);
+                if (cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess)
+                    dyn_base = (int)h;
+                cudaFree(d);
+            }
+        }
+        static const int env_impl = getenv("Q4_GEMV_IMPL") ? atoi(getenv("Q4_GEMV_IMPL")) : 0;  // 1: force the mma.sync kernel
+        // tcgen05 kernel (q4_gemv_tc.cuh): needs the prebuilt table image and the split-K workspace
+        if (fast && env_impl != 1 && pro && pro->lut && pro->workspace && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&
+            (reinterpret_cast<uintptr_t>(pro->workspace) & 15) == 0) {
+            const int bpr = (int)(K / 64);
+            const int rt_total = (int)((N + kTcRows - 1) / kTcRows);
+            const int64_t U = (int64_t)rt_total * bpr;
+            int grid = (int)(U / kTcGroups < sms ? U / kTcGroups : sms);
+            const size_t smem = (size_t)kLutBytes + (size_t)K * 2 + kTcXPad + 128 + (1 + 6 * kTcGroups) * 8 + 128;
+            if (grid >= 1 && smem <= 226 * 1024) {
+                const int G2 = kTcGroups * grid;
+                auto run_of = [&](int64_t u) { return (int)(((u + 1) * G2 - 1) / U); };
+                int max_seg = 1;
+                for (int rt = 0; rt < rt_total; rt++) {
+                    const int n = run_of((int64_t)rt * bpr + bpr - 1) - run_of((int64_t)rt * bpr) + 1;
+                    if (n > max_seg) max_seg = n;
+                }
+                // counters live in a FIXED region at the start (they must stay zero between launches of any shape), partials after it
+                const size_t cnt_bytes = 64 * 1024;
+                if ((size_t)rt_total * 4 > cnt_bytes) return Q4_ERR_SHAPE;
+                const size_t need = cnt_bytes + (size_t)rt_total * max_seg * kTcRows * 4;
+                if ((int64_t)need <= pro->workspace_bytes) {
+                    const bool multi = nmat > 1 && nested;
+                    TcGemvArgs a = {};
+                    a.x = x;
+                    a.lut = pro->lut;
+                    a.Bq = B;
+                    a.s = v;
+                    for (int m = 0; m < kMaxMats; m++) {
+                        a.offsets[m] = nullptr;
+                        a.row_end[m] = 0x7fffffff;
+                    }
+                    a.offsets[0] = v.offset;
+                    if (multi) {
+                        for (int m = 0; m < nmat; m++) {
+                            a.offsets[m] = offsets[m];
+                            a.row_end[m] = row_end[m];
+                        }
+                        a.row_end[nmat - 1] = 0x7fffffff;
+                    }
+                    a.out = out;
+                    a.bias = bias;
+                    if ((reinterpret_cast<uintptr_t>(pro->x_gate) & 15) || (reinterpret_cast<uintptr_t>(pro->rms_weight) & 15) ||
+                        (reinterpret_cast<uintptr_t>(pro->lut) & 15))
+                        return Q4_ERR_ALIGN;
+                    a.x_gate = pro->x_gate;
+                    a.rms_weight = pro->rms_weight;
+                    a.rms_eps = pro->rms_eps;
+                    a.next = (reinterpret_cast<uintptr_t>(next) & 15) == 0 ? (const uint8_t*)next : nullptr;
+                    a.next_bytes = a.next ? next_bytes : 0;
+                    a.ws_count = reinterpret_cast<int*>(pro->workspace);
+                    a.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pro->workspace) + cnt_bytes);
+                    a.max_seg = max_seg;
+                    a.rows = (int)N;
+                    a.K = (int)K;
+                    a.rt_total = rt_total;
+                    a.trace = g_gemv_trace;
+                    static const int env_debug = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
+                    a.debug = env_debug;
+                    auto kern = nested ? (multi ? gemv_tc_kernel<T, true, true> : gemv_tc_kernel<T, true, false>) : gemv_tc_kernel<T, false, false>;
+                    static bool attr_set[2][2] = {};
+                    if (!attr_set[nested][multi]) {
+                        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+                        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                        if (e != cudaSuccess) return (int)e;
+                        attr_set[nested][multi] = true;
+                    }
+                    return launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, stream, pdl, a);
+                }
+            }
+        }
         if (mma_ok) {
             const bool multi = nmat > 1 && nested;
             MmaGemvArgs a = {};
@@ -174,20 +262,8 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             constexpr int threads = kMmaThreads;
             a.x_iters = (a.kt * 64 + threads - 1) / threads;
             a.trace = g_gemv_trace;
-            // where does dynamic shared memory start in the CTA's window?  (probed once; the compact layout depends on it)
-            static int dyn_base = -1;
-            if (dyn_base < 0) {
-                uint32_t* d = nullptr;
-                uint32_t h = 0;
-                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-                cudaStreamIsCapturing(stream, &cap);
-                if (cap == cudaStreamCaptureStatusNone && cudaMalloc(&d, 4) == cudaSuccess) {
-                    probe_dyn_smem_base_kernel<<<1, 32, 1024, stream>>>(d);
-                    if (cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess)
-                        dyn_base = (int)h;
-                    cudaFree(d);
-                }
-            }
+            static const int env_debug_mma = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
+            a.debug = env_debug_mma;
             static const int env_aligned = getenv("Q4_GEMV_ALIGNED") ? atoi(getenv("Q4_GEMV_ALIGNED")) : 0;
             // two CTAs per SM for matrices that keep an SM busy for several microseconds (the loop is bound by the legacy tensor
             // pipe and wants all 16 warps); one for small ones (the next launch's prologue shares the SM instead)
@@ -257,6 +333,8 @@ int gemv_4bit_fused(const q4_gemv_fused_t* f, cudaStream_t stream)
     pro.rms_weight = f->rms_weight;
     pro.rms_eps = f->rms_eps;
     pro.lut = f->lut;
+    pro.workspace = f->workspace;
+    pro.workspace_bytes = f->workspace_bytes;
     const int flags = f->flags & ~Q4_GEMV_EXACT_F32;
     switch (f->dtype) {
         case Q4_F16:

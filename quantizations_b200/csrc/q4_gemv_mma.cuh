@@ -61,6 +61,7 @@ struct MmaGemvArgs {
     int kt;        // ceil(K / 512): k tiles per row tile
     int x_iters;   // ceil(kt * 64 / blockDim): 16-byte activation chunks per thread
     unsigned long long* trace;
+    int debug;  // developer experiments (env Q4_GEMV_DEBUG)
 };
 
 template <typename T> struct Hmma;
@@ -122,13 +123,13 @@ struct TileRegs {
 // Activation staging with the decode glue fused in (rare path, kept out of line so the main kernel stays small):
 //   x_gate:      x_eff = silu(gate) * x, F.silu rounded to T, then the product rounded to T (as the separate torch kernels round)
 //   rms_weight:  x_eff = x * rsqrt(mean(x^2) + eps) * weight in fp32, rounded to T once
-template <typename T>
+template <typename T, bool SWZ>
 __device__ __noinline__ void stage_x_fused(const void* x, const void* x_gate, const void* rms_weight, float rms_eps, int K, uint4* s_x,
                                            float* s_red, int nchunk, int npad)
 {
     struct { const void *x, *x_gate, *rms_weight; float rms_eps; int K; } a = {x, x_gate, rms_weight, rms_eps, K};
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    auto slot = [](int c) { return (c & ~7) | ((c ^ (c >> 3)) & 7); };
+    auto slot = [](int c) { return SWZ ? ((c & ~7) | ((c ^ (c >> 3)) & 7)) : c; };  // SWZ: the mma.sync kernel's bank swizzle
     float ss = 0.0f;
 #pragma unroll 1
     for (int c = tid; c < npad; c += nthr) {
@@ -301,7 +302,7 @@ gemv_mma_kernel(const MmaGemvArgs a)
         const int nchunk = K >> 3;  // 16-byte chunks of x
         const int npad = KT * 64;   // staged chunks (zero tail up to whole tiles)
         if (a.x_gate || a.rms_weight) {
-            stage_x_fused<T>(a.x, a.x_gate, a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, npad);
+            stage_x_fused<T, true>(a.x, a.x_gate, a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, npad);
         } else {
             // chunk c = (block c>>3, piece c&7) goes to piece (c&7) ^ (block&7): the eight lanes that later fetch eight
             // different blocks piece by piece hit eight different bank groups
@@ -379,8 +380,18 @@ gemv_mma_kernel(const MmaGemvArgs a)
         for (int j = 0; j < 16; j++) {
             if (j + kAhead < 16) fetch(f[(j + kAhead) % (kAhead + 1)], j + kAhead);
             uint32_t(&a4)[4] = f[j % (kAhead + 1)];
+#ifdef Q4_GEMV_EXPERIMENT_FMA  // developer experiment (wrong results): the same lookups feeding the FMA pipe instead of the tensor pipe
+            {
+                uint32_t* c32 = reinterpret_cast<uint32_t*>(j & 1 ? co : ce);
+                asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(c32[0]) : "r"(a4[0]), "r"(xr[2 * j]));
+                asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(c32[1]) : "r"(a4[1]), "r"(xr[2 * j]));
+                asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(c32[2]) : "r"(a4[2]), "r"(xr[2 * j + 1]));
+                asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(c32[3]) : "r"(a4[3]), "r"(xr[2 * j + 1]));
+            }
+#else
             if (j & 1) Hmma<T>::run(co, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
             else Hmma<T>::run(ce, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
+#endif
         }
         // the lane's two useful sums: blocks 2t, 2t+1 of the tile (columns 2t, 2t+1; first half -> rows 0-7, second -> 8-15)
         const float u0 = t4 < 2 ? ce[0] + co[0] : ce[2] + co[2];

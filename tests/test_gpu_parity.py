@@ -469,3 +469,37 @@ def test_fused_decode_glue_matches_separate_torch_ops(q, dtype):
     assert (stream.float() - ref).abs().max().item() <= tol * ref.abs().max().item()
     # plain call through the fused entry point is bit-identical to gemv_4bit
     assert torch.equal(q.gemv_4bit_fused(x, packed, state), q.gemv_4bit(x, packed, state=state))
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (14336, 4096), (4096, 14336), (1000, 512), (136, 256)])
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_tcgen05_gemv_matches_mma_sync_gemv(q, shape, dtype):
+    """The tcgen05 decode kernel (q4_gemv_tc.cuh: lut + workspace given) and the mma.sync kernel (no workspace) compute the
+    same sums in a different order: outputs agree to the rounding of the output type, on repeated calls with one workspace
+    (its counters must return to zero), including shapes whose last row tile is ragged and after a launch of another shape."""
+    import ctypes
+
+    from quantizations_b200 import _lib
+
+    N, K = shape
+    dt = TDT[dtype]
+    torch.manual_seed(3)
+    W = (torch.randn(N, K, device=DEV) * 0.02).to(dt)
+    packed, st = q.quantize_4bit(W, quant_type="nf4")
+    stats, lut = st.native_stats(), st.lut(dt)
+    ws = torch.zeros(_lib.Q4_GEMV_WORKSPACE_BYTES, dtype=torch.uint8, device=DEV)
+    ws[65536:].fill_(0x7F)  # the partial-sum area may hold anything; only the counters must start at zero
+    bias = torch.randn(N, device=DEV, dtype=dt)
+    for rep in range(3):
+        x = torch.randn(1, 1, K, device=DEV, dtype=dt)
+        outs = []
+        for w in (ws, None):
+            out = torch.full((N,), 3.0, device=DEV, dtype=dt)
+            f = _lib.GemvFused(x.data_ptr(), None, None, 0.0, packed.data_ptr(), ctypes.pointer(stats), None, None, 1, st.code.data_ptr(),
+                               bias.data_ptr(), out.data_ptr(), N, K, 64, {"bfloat16": _lib.Q4_BF16, "float16": _lib.Q4_F16}[dtype], 0, None, 0,
+                               lut.data_ptr(), None if w is None else w.data_ptr(), 0 if w is None else w.numel())
+            assert _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream().cuda_stream) == 0
+            outs.append(out.float())
+        tol = {"bfloat16": 1e-2, "float16": 2e-3}[dtype] * outs[1].abs().max().item()
+        assert (outs[0] - outs[1]).abs().max().item() <= tol
+        assert int(ws[:65536].view(torch.int32).ne(0).sum()) == 0

@@ -88,6 +88,7 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--only", default="", help="NxK: time just this shape")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-ws", action="store_true", help="no split-K workspace: the mma.sync kernel instead of the tcgen05 one")
     ap.add_argument("--no-lut", action="store_true", help="no prebuilt table image: the kernel builds its table per launch")
     ap.add_argument("--next", action="store_true", help="hint the next matrix of the pool for L2 prefetch")
     ap.add_argument("--streams", type=int, default=1, help="parallel capture branches (independent launches)")
@@ -129,9 +130,11 @@ def main():
         ptrs = [m.data_ptr() for m in mats]
 
         lut = None if (a.no_lut or dt == torch.float32) else st0.lut(dt)
+        ws = torch.zeros(_lib.Q4_GEMV_WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
         fused = [_lib.GemvFused(x.data_ptr(), None, None, 0.0, ptrs[i], ctypes.pointer(stats), None, None, 1, st0.code.data_ptr(), None,
                                 outs2[i % NSTREAMS].data_ptr(), N, K, 64, dcode, a.flags, ptrs[(i + 1) % nmat] if a.next else None,
-                                per if a.next else 0, None if lut is None else lut.data_ptr()) for i in range(nmat)]
+                                per if a.next else 0, None if lut is None else lut.data_ptr(),
+                                None if a.no_ws else ws.data_ptr(), 0 if a.no_ws else ws.numel()) for i in range(nmat)]
 
         def ours(i):
             if dt == torch.float32:

@@ -17,12 +17,14 @@ mats = [packed.clone() for _ in range(8)]
 x = torch.randn(1, 1, K, device=dev, dtype=torch.bfloat16)
 out = torch.empty(1, 1, N, device=dev, dtype=torch.bfloat16)
 NL = 6
-traces = [torch.zeros(148 * 8, dtype=torch.int64, device=dev) for _ in range(NL)]
+traces = [torch.zeros(148 * 8 + 64, dtype=torch.int64, device=dev) for _ in range(NL)]
 stream = torch.cuda.current_stream().cuda_stream
 lut = None if os.environ.get("NO_LUT") else st.lut(torch.bfloat16)
 stats = st.native_stats()
+ws = torch.zeros(_lib.Q4_GEMV_WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
 fused = [_lib.GemvFused(x.data_ptr(), None, None, 0.0, m.data_ptr(), ctypes.pointer(stats), None, None, 1, st.code.data_ptr(), None,
-                        out.data_ptr(), N, K, 64, 2, flags, None, 0, None if lut is None else lut.data_ptr()) for m in mats]
+                        out.data_ptr(), N, K, 64, 2, flags, None, 0, None if lut is None else lut.data_ptr(),
+                        None if os.environ.get("NO_WS") else ws.data_ptr(), 0 if os.environ.get("NO_WS") else ws.numel()) for m in mats]
 def launch(i, tr):
     L.q4_debug_set_gemv_trace(tr.data_ptr() if tr is not None else None)
     L.q4_gemv_4bit_fused(ctypes.byref(fused[i % 8]), stream)
@@ -45,7 +47,8 @@ L.q4_debug_set_gemv_trace(None)
 names = ["start", "issued", "waited", "x staged", "loop done", "end", "table ok"]
 t0 = None
 for i, tr in enumerate(traces):
-    t = tr.cpu().view(148, 8)
+    print("   extra:", tr.cpu()[148 * 8:148 * 8 + 60].view(10, 6).tolist()) if i == NL - 1 else None
+    t = tr.cpu()[:148 * 8].view(148, 8)
     t = t[t[:, 0] > 0]
     if t0 is None:
         t0 = int(t[:, 0].min())
