@@ -175,10 +175,15 @@ def run_ours(args, rank, world, device):
     for m in units:
         outs.setdefault((m.name_, m.out_features), torch.empty(1, 1, m.out_features, device=device, dtype=dtype))
     comm = None
+    fused_ar = None
     if world > 1:
         import torch.distributed as dist
 
         comm = dist
+        if not args.nccl_allreduce:  # the product path: all-reduce inside the row-parallel GEMV's epilogue over NVLink peer memory
+            from quantizations_b200 import tp as tpmod
+
+            fused_ar = tpmod.FusedAllReduce(cfg["hidden"], device=device)
 
     pdl = _lib.Q4_GEMV_PDL if args.pdl else 0
     # A decoder layer's Linear4bit calls form a small DAG: q/k/v share their input and are independent of each other, so do
@@ -232,14 +237,15 @@ def run_ours(args, rank, world, device):
                                    _lib.Q4_BF16, flags, npt, nby, m.lut(dtype).data_ptr(), ws_ptr, ws_bytes)
             else:
                 st = m.weight.quant_state
+                ar = ctypes.pointer(fused_ar.struct) if (fused_ar is not None and m.parallel == "row") else None
                 f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.weight.data_ptr(), ctypes.pointer(st.native_stats()), None,
                                    None, 1, st.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, st.blocksize,
-                                   _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr(), ws_ptr, ws_bytes)
+                                   _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr(), ws_ptr, ws_bytes, ar)
             fused_args[key] = f
         rc = L.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream().cuda_stream)
         if rc:
             _lib.check(rc, "q4_gemv_4bit_fused")
-        if comm is not None and m.parallel == "row":
+        if comm is not None and fused_ar is None and m.parallel == "row":
             comm.all_reduce(outs[(m.name_, m.out_features)])
 
     def step_cabi():
@@ -296,9 +302,12 @@ def run_ours(args, rank, world, device):
     def launch_api(i, m, flags):
         m.gemv_flags = flags
         m.prefetch_next = packed_of(units[(i + 1) % len(units)]) if args.prefetch else None
-        y = m.forward_fused(x_static[m.in_features]) if isinstance(m, q.Linear4bitGroup) else m(x_static[m.in_features])
-        if comm is not None and m.parallel == "row":
-            comm.all_reduce(y)
+        if fused_ar is not None and m.parallel == "row":
+            y = q.gemv_4bit_fused(x_static[m.in_features], m.weight.data, m.weight.quant_state, flags=flags, allreduce=fused_ar)
+        else:
+            y = m.forward_fused(x_static[m.in_features]) if isinstance(m, q.Linear4bitGroup) else m(x_static[m.in_features])
+            if comm is not None and m.parallel == "row":
+                comm.all_reduce(y)
         y_static[(m.name_, m.out_features)] = y
 
     def step_api():
@@ -347,7 +356,7 @@ def run_ours(args, rank, world, device):
         "config": {
             "workload": f"{args.model} Linear4bit stack, NF4 + double-quant, blocksize 64, bs=1 decode: {layers} layers x "
                         f"(q,k,v,o,gate,up,down) = {len(mods)} GEMVs/step per GPU"
-                        + (f" in {len(units)} launches (q/k/v and gate/up grouped: they share their input)" if args.group else "") + (f", tensor-parallel tp{world} (NCCL all-reduce after o_proj/down_proj)" if world > 1 else ""),
+                        + (f" in {len(units)} launches (q/k/v and gate/up grouped: they share their input)" if args.group else "") + (f", tensor-parallel tp{world} (" + ("NCCL all-reduce after" if fused_ar is None else "all-reduce fused into the epilogue of") + " o_proj/down_proj)" if world > 1 else ""),
             "shapes": sorted({f"{m.out_features}x{m.in_features}" for m in mods}),
             "packed_weight_bytes_per_gpu": packed_bytes, "algorithmic_bytes_per_step": step_bytes,
             "l2_policy": "inputs larger than L2: every layer has its own weights (3.5 GB/step >> 126 MB L2), no flush needed",
@@ -541,6 +550,8 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="decoder layers in the stack (0 = the model's own count)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="tensor-parallel runs: NCCL all-reduce after the row-parallel GEMVs (the baseline) instead of the fused epilogue exchange")
     ap.add_argument("--prefetch", action="store_true",
                     help="pass the next layer's packed weight as the L2 prefetch hint (measured neutral on one stream; off by default so "
                          "that every launch's DRAM traffic is exactly its own matrix)")

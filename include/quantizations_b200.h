@@ -124,6 +124,23 @@ int q4_gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* sta
                          const int* row_end, int nmat, const float* code, const void* bias, void* out, int64_t rows, int64_t K,
                          int blocksize, int dtype, int flags, const void* prefetch, int64_t prefetch_bytes, void* stream);
 
+/* Tensor-parallel row-parallel layers (o_proj, down_proj): every rank holds a partial [rows] vector that must be summed
+ * over the ranks (one all-reduce of a hidden-sized vector per layer).  With this descriptor the decode GEMV does
+ * that exchange itself, in its epilogue, over NVLink peer memory: each CTA stores the fp32 partial sums of ITS rows, tagged with
+ * a launch epoch (one 8-byte store per value), into every peer's exchange area, polls its own area until the same rows of every
+ * peer carry the epoch, and adds the partials in rank order (deterministic, bit-identical on every rank) before bias / residual
+ * and the store -- a one-shot all-reduce with no extra launch, no flag, no fence and no grid-wide barrier.
+ * peer_bases: DEVICE array [world] of the ranks' exchange areas (one symmetric allocation of Q4_AR_BYTES(max_rows) per rank,
+ * zeroed once, e.g. torch.distributed._symmetric_memory: buffer_ptrs_dev); all ranks must issue the same sequence of calls. */
+typedef struct q4_allreduce_t {
+    void* const* peer_bases;
+    int world, rank; /* world <= 8 */
+    int max_rows;    /* rows of the row-parallel layers sharing this exchange area (the hidden size): every call must have rows == max_rows */
+} q4_allreduce_t;
+#define Q4_AR_MAX_CTAS 1024
+#define Q4_AR_DATA_OFFSET 65536
+#define Q4_AR_BYTES(max_rows) (Q4_AR_DATA_OFFSET + 2 * 8 * (int64_t)(max_rows) * 8)
+
 /* Decode GEMV with the surrounding elementwise glue of a transformer block fused in (everything optional, NULL = off):
  *   rms_weight : the activation is RMS-normalised first, x * rsqrt(mean(x^2) + rms_eps) * rms_weight  (fp32, rounded to dtype)
  *   x_gate     : the activation is silu(x_gate[k]) * x[k]  (SwiGLU: x = up-projection output, x_gate = gate output)
@@ -153,6 +170,7 @@ typedef struct q4_gemv_fused_t {
                       * With lut and workspace the tcgen05 kernel runs (row tiles split along K across CTAs, partial sums combined
                       * through the workspace in a fixed order; it leaves the workspace zeroed); without, the mma.sync kernel. */
     int64_t workspace_bytes;
+    const q4_allreduce_t* allreduce; /* optional: sum the output over tensor-parallel ranks in the epilogue (see q4_allreduce_t) */
 } q4_gemv_fused_t;
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
 

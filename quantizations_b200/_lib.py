@@ -35,6 +35,20 @@ class AbsmaxStats(ctypes.Structure):
     ]
 
 
+class AllReduce(ctypes.Structure):
+    """q4_allreduce_t"""
+
+    _fields_ = [("peer_bases", ctypes.c_void_p), ("world", ctypes.c_int), ("rank", ctypes.c_int), ("max_rows", ctypes.c_int)]
+
+
+Q4_AR_MAX_CTAS = 1024
+Q4_AR_DATA_OFFSET = 65536
+
+
+def ar_bytes(max_rows: int) -> int:
+    return Q4_AR_DATA_OFFSET + 2 * 8 * max_rows * 8
+
+
 class GemvFused(ctypes.Structure):
     """q4_gemv_fused_t"""
 
@@ -45,6 +59,7 @@ class GemvFused(ctypes.Structure):
         ("out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("K", ctypes.c_int64), ("blocksize", ctypes.c_int),
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("prefetch", ctypes.c_void_p), ("prefetch_bytes", ctypes.c_int64),
         ("lut", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+        ("allreduce", ctypes.POINTER(AllReduce)),
     ]  # fmt: skip
 
 

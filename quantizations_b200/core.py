@@ -650,6 +650,7 @@ def gemv_4bit_fused(
     out: Optional[Tensor] = None,
     flags: int = _lib.Q4_GEMV_PDL,
     prefetch: Optional[Tensor] = None,
+    allreduce=None,
 ) -> Tensor:
     """Decode GEMV with a transformer block's elementwise glue fused in (include/quantizations_b200.h: q4_gemv_4bit_fused):
 
@@ -658,7 +659,9 @@ def gemv_4bit_fused(
               = silu(gate) * A                      (gate given: A is the up-projection output)
         out   = x_eff @ dequant(B)^T  (+ residual)  (residual may be `out` itself: in-place residual stream)
 
-    `group` (a Linear4bitGroup) runs the grouped launch over its members instead of a single (B, state)."""
+    `group` (a Linear4bitGroup) runs the grouped launch over its members instead of a single (B, state).
+    `allreduce` (a tp.FusedAllReduce) sums the output over the tensor-parallel ranks inside the kernel's epilogue, before the
+    residual is added: the row-parallel layers' all-reduce without a collective call."""
     if A.numel() != A.shape[-1]:
         raise ValueError("gemv_4bit_fused needs a single activation vector")
     if A.dtype not in (torch.float16, torch.bfloat16):
@@ -689,7 +692,7 @@ def gemv_4bit_fused(
         packed.data_ptr(), ctypes.pointer(stats), offsets, row_end, nmat, code.data_ptr(),
         None if residual is None else residual.data_ptr(), out.data_ptr(), rows, K, blocksize, _DTYPE_CODE[A.dtype], flags,
         None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
-        lut.data_ptr(), *_ws_args(A.device),
+        lut.data_ptr(), *_ws_args(A.device), None if allreduce is None else ctypes.pointer(allreduce.struct),
     )
     rc = _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
     if rc:

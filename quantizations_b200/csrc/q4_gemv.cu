@@ -99,6 +99,7 @@ struct GemvPrologue {  // optional fused input transforms (16-bit activations on
     const void* lut = nullptr;  // prebuilt table image (q4_gemv_lut_build) for this code / code2 / dtype
     void* workspace = nullptr;  // split-K workspace of the tcgen05 kernel (zeroed once by the caller)
     int64_t workspace_bytes = 0;
+    const q4_allreduce_t* ar = nullptr;  // fused all-reduce over tensor-parallel ranks
 };
 
 template <typename K, typename... Args>
@@ -154,7 +155,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         }
         static const int env_impl = getenv("Q4_GEMV_IMPL") ? atoi(getenv("Q4_GEMV_IMPL")) : 0;  // 1: force the mma.sync kernel
         // tcgen05 kernel (q4_gemv_tc.cuh): needs the prebuilt table image and the split-K workspace
-        if (fast && env_impl != 1 && pro && pro->lut && pro->workspace && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&
+        if (fast && env_impl != 1 && pro && pro->lut && pro->workspace && !pro->ar && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&
             (reinterpret_cast<uintptr_t>(pro->workspace) & 15) == 0) {
             const int bpr = (int)(K / 64);
             const int rt_total = (int)((N + kTcRows - 1) / kTcRows);
@@ -255,6 +256,17 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             }
             a.next = (reinterpret_cast<uintptr_t>(next) & 15) == 0 ? (const uint8_t*)next : nullptr;
             a.next_bytes = a.next ? next_bytes : 0;
+            if (pro && pro->ar && pro->ar->world > 1) {
+                const q4_allreduce_t* ar = pro->ar;
+                if (!ar->peer_bases) return Q4_ERR_NULL;
+                // one row count per exchange area: the CTA -> rows mapping (and with it the double-buffer argument) must be identical in
+                // every launch that shares it
+                if (ar->world > kArMaxWorld || ar->rank < 0 || ar->rank >= ar->world || N != ar->max_rows) return Q4_ERR_SHAPE;
+                a.ar_peer_bases = ar->peer_bases;
+                a.ar_world = ar->world;
+                a.ar_rank = ar->rank;
+                a.ar_max_rows = ar->max_rows;
+            }
             a.rows = (int)N;
             a.K = (int)K;
             a.rt_total = (int)((N + 7) / 8);
@@ -268,7 +280,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             // two CTAs per SM for matrices that keep an SM busy for several microseconds (the loop is bound by the legacy tensor
             // pipe and wants all 16 warps); one for small ones (the next launch's prologue shares the SM instead)
             static const int env_mult_raw = getenv("Q4_GEMV_GRID_MULT") ? atoi(getenv("Q4_GEMV_GRID_MULT")) : 0;
-            const int env_mult = env_mult_raw > 0 ? env_mult_raw : ((N * K / 2) / sms > 100 * 1024 ? 2 : 1);
+            const int env_mult = a.ar_world > 1 ? 1 : (env_mult_raw > 0 ? env_mult_raw : ((N * K / 2) / sms > 100 * 1024 ? 2 : 1));
             // grid: one half-SM CTA per SM (the other half is for the next launch's prologue, see the kernel), or more when
             // the per-CTA partial-sum buffer would not fit
             const size_t tail = (size_t)a.kt * 1024 + 128 + 16;
@@ -280,6 +292,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                 grid += sms;
             }
             if (grid > a.rt_total) grid = a.rt_total;
+            if (a.ar_world > 1 && grid > kArMaxCtas) return Q4_ERR_SHAPE;
             const size_t rest = tail + (size_t)((a.rt_total + grid - 1) / grid) * a.kt * 32;
             const bool compact = dyn_base == kDynBase && !env_aligned && kLutBytes + rest <= 220 * 1024;
             const size_t smem = (compact ? 1 : 2) * (size_t)kLutBytes + rest;
@@ -298,7 +311,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, pdl, a);
         }
     }
-    if (nmat > 1 || (pro && (pro->x_gate || pro->rms_weight))) return Q4_ERR_SHAPE;  // only the fast path groups / fuses
+    if (nmat > 1 || (pro && (pro->x_gate || pro->rms_weight || (pro->ar && pro->ar->world > 1)))) return Q4_ERR_SHAPE;  // only the fast path groups / fuses
     // generic: x as fp32 in shared memory
     const size_t smem = 128 + sizeof(float) * (size_t)K;
     if (smem > 200 * 1024) return Q4_ERR_SHAPE;
@@ -335,6 +348,7 @@ int gemv_4bit_fused(const q4_gemv_fused_t* f, cudaStream_t stream)
     pro.lut = f->lut;
     pro.workspace = f->workspace;
     pro.workspace_bytes = f->workspace_bytes;
+    pro.ar = f->allreduce;
     const int flags = f->flags & ~Q4_GEMV_EXACT_F32;
     switch (f->dtype) {
         case Q4_F16:

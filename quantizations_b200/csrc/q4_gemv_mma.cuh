@@ -62,7 +62,14 @@ struct MmaGemvArgs {
     int x_iters;   // ceil(kt * 64 / blockDim): 16-byte activation chunks per thread
     unsigned long long* trace;
     int debug;  // developer experiments (env Q4_GEMV_DEBUG)
+    // fused one-shot all-reduce over tensor-parallel ranks (q4_allreduce_t), ar_world <= 1: off
+    void* const* ar_peer_bases;
+    int ar_world, ar_rank, ar_max_rows;
 };
+
+constexpr int kArMaxCtas = 1024;       // Q4_AR_MAX_CTAS
+constexpr int kArDataOffset = 65536;   // Q4_AR_DATA_OFFSET
+constexpr int kArMaxWorld = 8;
 
 template <typename T> struct Hmma;
 template <> struct Hmma<__half> {
@@ -434,16 +441,66 @@ gemv_mma_kernel(const MmaGemvArgs a)
     mma_trace(a, 4);
     __syncthreads();
 
-    // ---- fixed-order sum over the k tiles, bias / residual, store
-    for (int i = tid; i < row_hi - row_lo; i += nthr) {
+    // ---- fixed-order sum over the k tiles, [all-reduce over tensor-parallel ranks,] bias / residual, store
+    auto row_total = [&](int i) {
         const float* p = s_part + (i >> 3) * KT * 8 + (i & 7);
         float total = 0.0f;
         for (int kt = 0; kt < KT; kt++) total += p[kt * 8];
+        return total;
+    };
+    auto finish = [&](int i, float total) {
         const int r = row_lo + i;
         T y = Elem<T>::from_f32(total);
         const T* bias = reinterpret_cast<const T*>(a.bias);
         if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + Elem<T>::to_f32(bias[r]));  // torch `out += bias`
         reinterpret_cast<T*>(a.out)[r] = y;
+    };
+    const int nrows = row_hi - row_lo;
+    if (a.ar_world > 1) {
+        // One-shot all-reduce in the epilogue (include/quantizations_b200.h: q4_allreduce_t), "low latency" style: every partial
+        // travels as ONE 8-byte store {value, epoch} into every peer's exchange area, and the owner of a row polls the W slots of
+        // that row until they carry the current epoch -- no flag, no fence, no barrier: one NVLink hop.  Exchange area of a rank:
+        //   [epochs u32 [kArMaxCtas]] ... [slots {f32, u32} [2][world][max_rows]] at kArDataOffset
+        // The same CTA index owns the same rows on every rank (identical launch), so the exchange is CTA-local; launches are
+        // counted per CTA on the device, so replayed CUDA graphs stay in step across ranks; slots are double-buffered by epoch
+        // parity because a fast peer may start its NEXT exchange while this rank still reads the current one.
+        const int W = a.ar_world, me = a.ar_rank;
+        uint8_t* mine = reinterpret_cast<uint8_t*>(a.ar_peer_bases[me]);
+        uint32_t* s_epoch = reinterpret_cast<uint32_t*>(s_red);
+        if (tid == 0) {
+            uint32_t* ep = reinterpret_cast<uint32_t*>(mine) + blockIdx.x;
+            const uint32_t e = *ep + 1;
+            *ep = e;
+            *s_epoch = e;
+        }
+        __syncthreads();
+        const uint32_t epoch = *s_epoch;
+        const size_t half = (size_t)(epoch & 1) * W * a.ar_max_rows;
+        for (int i = tid; i < nrows; i += nthr) {
+            const float total = row_total(i);
+            for (int p = 0; p < W; p++) {
+                uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.ar_peer_bases[p]) + kArDataOffset) + half +
+                             (size_t)me * a.ar_max_rows + row_lo + i;
+                asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(total)), "r"(epoch) : "memory");
+            }
+        }
+        const uint2* slots = reinterpret_cast<const uint2*>(mine + kArDataOffset) + half;
+        for (int i = tid; i < nrows; i += nthr) {
+            float total = 0.0f;
+            for (int p = 0; p < W; p++) {  // rank order: every rank computes the same sum
+                const uint2* src = slots + (size_t)p * a.ar_max_rows + row_lo + i;
+                uint32_t v, e;
+                for (long long spin = 0;; spin++) {
+                    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
+                    if (e == epoch) break;
+                    if (spin > (1ll << 26)) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
+                }
+                total += __uint_as_float(v);
+            }
+            finish(i, total);
+        }
+    } else {
+        for (int i = tid; i < nrows; i += nthr) finish(i, row_total(i));
     }
     mma_trace(a, 5);
 }

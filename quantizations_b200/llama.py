@@ -73,6 +73,7 @@ class Llama(nn.Module):
         super().__init__()
         self.cfg, self.tp, self.group, self.dtype = cfg, tp, group, dtype
         self.fuse_glue = True  # fold RMSNorm / SwiGLU / residual adds into the decode GEMV launches (Linear4bit layers only)
+        self.fused_ar = None   # tp.FusedAllReduce: the row-parallel all-reduce inside the GEMV epilogue instead of NCCL
         g = torch.Generator(device=device).manual_seed(1234)
         self.embed = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
         self.lm_head = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
@@ -125,13 +126,14 @@ class Llama(nn.Module):
             a = F.scaled_dot_product_attention(q.transpose(0, 1).unsqueeze(0), self.k_cache[li].unsqueeze(0),
                                                self.v_cache[li].unsqueeze(0), attn_mask=mask, enable_gqa=True)  # [1, nh, T, hd]
             a = a.squeeze(0).transpose(0, 1).reshape(1, T, L.nh * L.hd)
-            if fused and self.tp == 1:
+            if fused and (self.tp == 1 or self.fused_ar is not None):
                 # o_proj adds the residual stream in its epilogue; norm folded into gate/up; SwiGLU folded into down_proj's
                 # activation staging, residual again in its epilogue: four launches for the layer's seven Linears + glue
                 qs = L.o_proj.weight.quant_state
-                x = gemv_4bit_fused(a, L.o_proj.weight.data, qs, residual=x)
+                x = gemv_4bit_fused(a, L.o_proj.weight.data, qs, residual=x, allreduce=self.fused_ar)
                 g, u = gemv_4bit_fused(x, None, group=L.gate_up, rms_weight=L.ln2, rms_eps=cfg.eps).split(L.gate_up.splits, dim=-1)
-                x = gemv_4bit_fused(u, L.down_proj.weight.data, L.down_proj.weight.quant_state, gate=g, residual=x)
+                x = gemv_4bit_fused(u, L.down_proj.weight.data, L.down_proj.weight.quant_state, gate=g, residual=x,
+                                    allreduce=self.fused_ar)
                 continue
             x = x + self._allreduce(L.o_proj(a))
             h = F.rms_norm(x, (cfg.hidden,), L.ln2, cfg.eps)

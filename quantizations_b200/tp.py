@@ -56,3 +56,31 @@ def combine_output(y: torch.Tensor, kind: str, group=None) -> torch.Tensor:
     if kind == "row":
         torch.distributed.all_reduce(y, group=group)
     return y
+
+
+class FusedAllReduce:
+    """Exchange area for the all-reduce fused into the row-parallel decode GEMV (include/quantizations_b200.h: q4_allreduce_t).
+
+    One symmetric allocation per rank (torch.distributed._symmetric_memory: every rank can address every peer's copy over
+    NVLink), zeroed once; `rows` is the output size of the row-parallel layers (the hidden size).  Pass the object as
+    `allreduce=` to core.gemv_4bit_fused: the kernel then leaves the SUM over ranks (+ residual) in `out` -- no NCCL call, no
+    extra launch.  NCCL (`combine_output`) stays the reference the tests compare against."""
+
+    def __init__(self, rows: int, group=None, device=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        group = dist.group.WORLD if group is None else group
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rows, self.world, self.rank = int(rows), dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("the fused all-reduce covers one NVSwitch domain: at most 8 ranks")
+        nbytes = _lib.ar_bytes(self.rows)
+        self.area = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.area.zero_()
+        self.handle = symm_mem.rendezvous(self.area, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's area is zeroed before anyone's kernel can write into it
+        self.struct = _lib.AllReduce(self.handle.buffer_ptrs_dev, self.world, self.rank, self.rows)
