@@ -183,6 +183,14 @@ int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
 #define Q4_GEMV_WORKSPACE_BYTES (8 << 20)
 int q4_gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, void* stream);
 
+/* Decode-step glue of the end-to-end harness (not a reference entry point: the reference has no model code): RoPE (HF
+ * rotate_half convention) on the new token's q and k, KV-cache append at *pos, and grouped-query attention of that one query
+ * over cache positions [0, *pos], in one launch.  qkv = [nh*hd | nkv*hd | nkv*hd] as the grouped q/k/v GEMV leaves it;
+ * cos_tab / sin_tab [max_len, hd/2]; caches [nkv, max_len, hd]; out [nh*hd]; hd must be 128; dtype Q4_F16 / Q4_BF16;
+ * flags: Q4_GEMV_PDL.  `pos` is a DEVICE scalar so the call can sit in a replayed CUDA graph. */
+int q4_decode_attention(const void* qkv, const void* cos_tab, const void* sin_tab, void* k_cache, void* v_cache, const int64_t* pos,
+                        void* out, int nh, int nkv, int hd, int max_len, int dtype, int flags, void* stream);
+
 /* Prefill / batched path with the dequantisation fused into a tcgen05 tensor-core GEMM:
  *     out[m, r] = sum_k X[m, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r]),   m in [0, M), r in [0, N)
  * X [M, K], out [M, N], bias [N] are `dtype` (Q4_F16 or Q4_BF16), row-major contiguous; accumulation is fp32 (TMEM).

@@ -698,3 +698,26 @@ def gemv_4bit_fused(
     if rc:
         check(rc, "gemv_4bit_fused")
     return out
+
+
+def decode_attention(qkv: Tensor, cos: Tensor, sin: Tensor, k_cache: Tensor, v_cache: Tensor, pos: Tensor, nh: int, nkv: int,
+                     out: Optional[Tensor] = None, flags: int = _lib.Q4_GEMV_PDL) -> Tensor:
+    """Decode-step glue in one launch (include/quantizations_b200.h: q4_decode_attention): RoPE on the new token's q / k,
+    KV-cache append at `pos` (a device scalar), attention of the one query over positions [0, pos].
+    qkv [.., (nh + 2*nkv) * 128] as the grouped q/k/v GEMV leaves it; cos / sin [max_len, 64]; caches [nkv, max_len, 128]."""
+    hd = k_cache.shape[-1]
+    if qkv.dtype not in (torch.float16, torch.bfloat16) or qkv.numel() != (nh + 2 * nkv) * hd:
+        raise ValueError("decode_attention needs one fp16/bf16 token of q|k|v")
+    for t in (cos, sin, k_cache, v_cache):
+        if t.dtype != qkv.dtype or not t.is_contiguous():
+            raise ValueError("cos / sin / caches must be contiguous and of the activation dtype")
+    if pos.dtype != torch.int64 or pos.numel() != 1:
+        raise ValueError("pos must be a one-element int64 device tensor")
+    if out is None:
+        out = torch.empty(qkv.shape[:-1] + (nh * hd,), dtype=qkv.dtype, device=qkv.device)
+    rc = _lib.lib().q4_decode_attention(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+                                        pos.data_ptr(), out.data_ptr(), nh, nkv, hd, k_cache.shape[-2], _DTYPE_CODE[qkv.dtype], flags,
+                                        torch.cuda.current_stream(qkv.device).cuda_stream)
+    if rc:
+        check(rc, "decode_attention")
+    return out

@@ -119,6 +119,13 @@ int q4_gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* sta
 
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream) { return q4::gemv_4bit_fused(args, (cudaStream_t)stream); }
 
+int q4_decode_attention(const void* qkv, const void* cos_tab, const void* sin_tab, void* k_cache, void* v_cache, const int64_t* pos,
+                        void* out, int nh, int nkv, int hd, int max_len, int dtype, int flags, void* stream)
+{
+    return q4::decode_attention(qkv, cos_tab, sin_tab, k_cache, v_cache, (const long long*)pos, out, nh, nkv, hd, max_len, dtype, flags,
+                                (cudaStream_t)stream);
+}
+
 int q4_gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, void* stream)
 {
     return q4::gemv_lut_build(code, code2, dtype, lut, (cudaStream_t)stream);

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .core import gemv_4bit_fused
+from .core import decode_attention, gemv_4bit_fused
 
 
 @dataclass
@@ -74,6 +74,7 @@ class Llama(nn.Module):
         self.cfg, self.tp, self.group, self.dtype = cfg, tp, group, dtype
         self.fuse_glue = True  # fold RMSNorm / SwiGLU / residual adds into the decode GEMV launches (Linear4bit layers only)
         self.fused_ar = None   # tp.FusedAllReduce: the row-parallel all-reduce inside the GEMV epilogue instead of NCCL
+        self.fuse_attn = cfg.head_dim == 128  # decode: RoPE + KV append + attention as one launch (q4_decode_attention)
         g = torch.Generator(device=device).manual_seed(1234)
         self.embed = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
         self.lm_head = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
@@ -113,19 +114,23 @@ class Llama(nn.Module):
         for li, L in enumerate(self.layers):
             fused = L.qkv is not None and T == 1 and self.fuse_glue
             h = None if fused else F.rms_norm(x, (cfg.hidden,), L.ln1, cfg.eps)
-            if fused:  # RMSNorm folded into the grouped q/k/v launch: the norm kernel and its round trip disappear
+            if fused and self.fuse_attn:
+                qkv = gemv_4bit_fused(x, None, group=L.qkv, rms_weight=L.ln1, rms_eps=cfg.eps)
+                a = decode_attention(qkv, self.cos, self.sin, self.k_cache[li], self.v_cache[li], pos, L.nh, L.nkv)
+            elif fused:  # RMSNorm folded into the grouped q/k/v launch: the norm kernel and its round trip disappear
                 q, k, v = gemv_4bit_fused(x, None, group=L.qkv, rms_weight=L.ln1, rms_eps=cfg.eps).split(L.qkv.splits, dim=-1)
             elif L.qkv is not None and T == 1:
                 q, k, v = L.qkv(h)
             else:
                 q, k, v = L.q_proj(h), L.k_proj(h), L.v_proj(h)
-            q, k, v = q.reshape(T, L.nh, L.hd), k.reshape(T, L.nkv, L.hd), v.reshape(T, L.nkv, L.hd)
-            q, k = self._rope(q, cos, sin), self._rope(k, cos, sin)
-            self.k_cache[li].index_copy_(1, pos, k.transpose(0, 1))
-            self.v_cache[li].index_copy_(1, pos, v.transpose(0, 1))
-            a = F.scaled_dot_product_attention(q.transpose(0, 1).unsqueeze(0), self.k_cache[li].unsqueeze(0),
-                                               self.v_cache[li].unsqueeze(0), attn_mask=mask, enable_gqa=True)  # [1, nh, T, hd]
-            a = a.squeeze(0).transpose(0, 1).reshape(1, T, L.nh * L.hd)
+            if not (fused and self.fuse_attn):
+                q, k, v = q.reshape(T, L.nh, L.hd), k.reshape(T, L.nkv, L.hd), v.reshape(T, L.nkv, L.hd)
+                q, k = self._rope(q, cos, sin), self._rope(k, cos, sin)
+                self.k_cache[li].index_copy_(1, pos, k.transpose(0, 1))
+                self.v_cache[li].index_copy_(1, pos, v.transpose(0, 1))
+                a = F.scaled_dot_product_attention(q.transpose(0, 1).unsqueeze(0), self.k_cache[li].unsqueeze(0),
+                                                   self.v_cache[li].unsqueeze(0), attn_mask=mask, enable_gqa=True)  # [1, nh, T, hd]
+                a = a.squeeze(0).transpose(0, 1).reshape(1, T, L.nh * L.hd)
             if fused and (self.tp == 1 or self.fused_ar is not None):
                 # o_proj adds the residual stream in its epilogue; norm folded into gate/up; SwiGLU folded into down_proj's
                 # activation staging, residual again in its epilogue: four launches for the layer's seven Linears + glue

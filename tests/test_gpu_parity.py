@@ -503,3 +503,32 @@ def test_tcgen05_gemv_matches_mma_sync_gemv(q, shape, dtype):
         tol = {"bfloat16": 1e-2, "float16": 2e-3}[dtype] * outs[1].abs().max().item()
         assert (outs[0] - outs[1]).abs().max().item() <= tol
         assert int(ws[:65536].view(torch.int32).ne(0).sum()) == 0
+
+
+def test_fused_decode_attention_matches_torch_attention_path(q):
+    """q4_decode_attention (RoPE + KV append + GQA attention in one launch) against the torch ops it replaces inside the same
+    decoder (llama.py, head_dim 128): same logits within bf16 rounding, same cache contents, over several decode steps."""
+    from quantizations_b200 import llama
+
+    cfg = llama.LlamaConfig(hidden=1024, inter=2048, layers=2, heads=8, kv_heads=2, vocab=1000, max_len=64)
+    dev_ = torch.device(DEV)
+    m = llama.Llama(cfg, llama.linear4bit_factory(dev_, torch.bfloat16, "nf4"), dev_, torch.bfloat16)
+    assert m.fuse_attn
+    prompt = torch.arange(1, 12, device=dev_)
+    m.forward(prompt, torch.arange(11, device=dev_))
+    k0, v0 = m.k_cache.clone(), m.v_cache.clone()
+    tok = torch.tensor([7], device=dev_)
+    for step in range(4):
+        pos = torch.tensor([11 + step], device=dev_)
+        m.fuse_attn = False
+        ref = m.forward(tok, pos).float()
+        kr, vr = m.k_cache.clone(), m.v_cache.clone()
+        m.k_cache.copy_(k0)
+        m.v_cache.copy_(v0)
+        m.fuse_attn = True
+        got = m.forward(tok, pos).float()
+        assert (got - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+        assert (m.k_cache.float() - kr.float()).abs().max().item() <= 2e-2 * kr.float().abs().max().item()
+        assert (m.v_cache.float() - vr.float()).abs().max().item() <= 2e-2 * vr.float().abs().max().item()
+        k0, v0 = m.k_cache.clone(), m.v_cache.clone()
+        tok = got.argmax().view(1)
