@@ -273,6 +273,16 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             a.kt = (int)((K + 511) / 512);
             constexpr int threads = kMmaThreads;
             a.x_iters = (a.kt * 64 + threads - 1) / threads;
+            {
+                const int nw = threads / 32, bpr_ = (int)(K / 64);
+                const long long row_bytes = (long long)bpr_ * 32;
+                a.d_rt = nw / a.kt;
+                a.d_kt = nw % a.kt;
+                a.pw_step = (long long)a.d_rt * 8 * row_bytes + (long long)a.d_kt * 256;
+                a.pw_wrap = 8 * row_bytes - (long long)a.kt * 256;
+                a.ab_step = a.d_rt * 8 * bpr_ + a.d_kt * 8;
+                a.ab_wrap = 8 * bpr_ - a.kt * 8;
+            }
             a.trace = g_gemv_trace;
             static const int env_debug_mma = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
             a.debug = env_debug_mma;
@@ -297,16 +307,21 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             const bool compact = dyn_base == kDynBase && !env_aligned && kLutBytes + rest <= 220 * 1024;
             const size_t smem = (compact ? 1 : 2) * (size_t)kLutBytes + rest;
             if (smem > 226 * 1024) return Q4_ERR_SHAPE;
-            auto kern = compact ? (nested ? (multi ? gemv_mma_kernel<T, true, true, true> : gemv_mma_kernel<T, true, false, true>)
-                                          : gemv_mma_kernel<T, false, false, true>)
-                                : (nested ? (multi ? gemv_mma_kernel<T, true, true, false> : gemv_mma_kernel<T, true, false, false>)
-                                          : gemv_mma_kernel<T, false, false, false>);
-            static bool attr_set[2][2][2] = {};
-            if (!attr_set[compact][nested][multi]) {
+            const bool ktail = (K % 512) != 0 || (N % 8) != 0;
+            using KernT = void (*)(const MmaGemvArgs);
+            auto pick = [&](auto compact_c, auto tail_c) -> KernT {
+                constexpr bool C = decltype(compact_c)::value, TL = decltype(tail_c)::value;
+                return nested ? (multi ? (KernT)gemv_mma_kernel<T, true, true, C, TL> : (KernT)gemv_mma_kernel<T, true, false, C, TL>)
+                              : (KernT)gemv_mma_kernel<T, false, false, C, TL>;
+            };
+            KernT kern = compact ? (ktail ? pick(std::true_type{}, std::true_type{}) : pick(std::true_type{}, std::false_type{}))
+                                 : (ktail ? pick(std::false_type{}, std::true_type{}) : pick(std::false_type{}, std::false_type{}));
+            static bool attr_set[2][2][2][2] = {};
+            if (!attr_set[compact][nested][multi][ktail]) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 if (e != cudaSuccess) return (int)e;
-                attr_set[compact][nested][multi] = true;
+                attr_set[compact][nested][multi][ktail] = true;
             }
             return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, pdl, a);
         }

@@ -65,6 +65,9 @@ struct MmaGemvArgs {
     // fused one-shot all-reduce over tensor-parallel ranks (q4_allreduce_t), ar_world <= 1: off
     void* const* ar_peer_bases;
     int ar_world, ar_rank, ar_max_rows;
+    // host-computed strides of the fast path's load cursor (tile index += warps per CTA)
+    long long pw_step, pw_wrap;
+    int ab_step, ab_wrap, d_rt, d_kt;
 };
 
 constexpr int kArMaxCtas = 1024;       // Q4_AR_MAX_CTAS
@@ -190,7 +193,7 @@ constexpr int kDynBase = 1024;  // where dynamic shared memory starts in the CTA
 constexpr int kMmaThreads = 256;
 constexpr int kBuffers = 3;     // weight tiles a warp holds in registers (one being consumed, the others in flight)
 
-template <typename T, bool NESTED, bool MULTI, bool COMPACT>
+template <typename T, bool NESTED, bool MULTI, bool COMPACT, bool TAIL>
 __global__ void __launch_bounds__(kMmaThreads, 2)
 gemv_mma_kernel(const MmaGemvArgs a)
 {
@@ -250,37 +253,72 @@ gemv_mma_kernel(const MmaGemvArgs a)
     for (int m = 0; m < kMaxMats; m++) off[m] = (NESTED && (MULTI || m == 0) && a.offsets[m]) ? __ldg(a.offsets[m]) : 0.0f;
 
     // ---- tile bookkeeping: warp w takes tiles w, w + nw, ... of the CTA's (row tile, k tile) grid, k fastest
+    // TAIL = false (K % 512 == 0 and rows % 8 == 0, every Llama shape): no bounds, no zero fill, and the load addresses advance
+    // by constants (tile index += nw means kt += nw % KT, rt += nw / KT, one conditional wrap).
     struct Cursor { int t, rt, kt; };
-    auto issue = [&](TileRegs& r, const Cursor& c) {
-        const int row = (rt0 + c.rt) * 8 + g;
-        const int row_c = row < R ? row : R - 1;  // rows past the end load a valid row and are never stored
-        const int blk0 = c.kt * 8;
-        const int base = row_c * bpr + blk0;      // rows * bpr < 2^31: dispatcher
-#pragma unroll
-        for (int j = 0; j < 8; j++) r.wa.v[j] = r.wb.v[j] = 0;
-        if (blk0 + t4 < bpr) r.wa = ldg_stream_256(a.Bq + (int64_t)(base + t4) * 32);
-        if (blk0 + 4 + t4 < bpr) r.wb = ldg_stream_256(a.Bq + (int64_t)(base + 4 + t4) * 32);
-        r.q = 0;
-        r.s0 = r.s1 = 0.0f;
-        if (blk0 + 2 * t4 < bpr) {  // bpr is even: the pair is valid together
-            const int sb = base + 2 * t4;
-            if (NESTED) {
-                r.q = __ldg(reinterpret_cast<const unsigned short*>(a.s.qabsmax + sb));
-                r.s0 = __ldg(a.s.absmax2 + (sb >> a.s.shift2));
-            } else {
-                const float2 f = __ldg(reinterpret_cast<const float2*>(a.s.absmax + sb));
-                r.s0 = f.x;
-                r.s1 = f.y;
-            }
-        }
-    };
-    auto after = [&](const Cursor& c) {  // the warp's next tile: index += nw, without a division
-        Cursor n = {c.t + nw, c.rt, c.kt + nw};
-        while (n.kt >= KT) {
+    const int d_rt = a.d_rt, d_kt = a.d_kt;  // nw / KT, nw % KT
+    auto after = [&](const Cursor& c) {  // the warp's next tile
+        Cursor n = {c.t + nw, c.rt + d_rt, c.kt + d_kt};
+        if (n.kt >= KT) {
             n.kt -= KT;
             n.rt++;
         }
         return n;
+    };
+    // load cursor of the fast path: byte pointer of (row g of the row tile, block t4 of the k tile) and the block index of the
+    // lane's absmax pair
+    const int64_t row_bytes = (int64_t)bpr * 32;
+    const uint8_t* pw = a.Bq + ((int64_t)(rt0 + warp / KT) * 8 + g) * row_bytes + (int64_t)(warp % KT) * 256 + t4 * 32;
+    int ab = ((rt0 + warp / KT) * 8 + g) * bpr + (warp % KT) * 8 + 2 * t4;  // rows * bpr < 2^31: dispatcher
+    int kt_ld = warp % KT;
+    auto issue = [&](TileRegs& r, const Cursor& c) {
+        if (TAIL) {
+            const int row = (rt0 + c.rt) * 8 + g;
+            const int row_c = row < R ? row : R - 1;  // rows past the end load a valid row and are never stored
+            const int blk0 = c.kt * 8;
+            const int base = row_c * bpr + blk0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) r.wa.v[j] = r.wb.v[j] = 0;
+            if (blk0 + t4 < bpr) r.wa = ldg_stream_256(a.Bq + (int64_t)(base + t4) * 32);
+            if (blk0 + 4 + t4 < bpr) r.wb = ldg_stream_256(a.Bq + (int64_t)(base + 4 + t4) * 32);
+            r.q = 0;
+            r.s0 = r.s1 = 0.0f;
+            if (blk0 + 2 * t4 < bpr) {  // bpr is even: the pair is valid together
+                const int sb = base + 2 * t4;
+                if (NESTED) {
+                    r.q = __ldg(reinterpret_cast<const unsigned short*>(a.s.qabsmax + sb));
+                    r.s0 = __ldg(a.s.absmax2 + (sb >> a.s.shift2));
+                } else {
+                    const float2 f = __ldg(reinterpret_cast<const float2*>(a.s.absmax + sb));
+                    r.s0 = f.x;
+                    r.s1 = f.y;
+                }
+            }
+        } else {
+#ifdef Q4_GEMV_EXPERIMENT_NOLOAD  // developer experiment (wrong results): only the first tiles are loaded -> pure SM-side rate
+            if (c.t < 3 * nw)
+#endif
+            {
+                r.wa = ldg_stream_256(pw);
+                r.wb = ldg_stream_256(pw + 128);
+            }
+            if (NESTED) {
+                r.q = __ldg(reinterpret_cast<const unsigned short*>(a.s.qabsmax + ab));
+                r.s0 = __ldg(a.s.absmax2 + (ab >> a.s.shift2));
+            } else {
+                const float2 f = __ldg(reinterpret_cast<const float2*>(a.s.absmax + ab));
+                r.s0 = f.x;
+                r.s1 = f.y;
+            }
+            pw += a.pw_step;
+            ab += a.ab_step;
+            kt_ld += d_kt;
+            if (kt_ld >= KT) {
+                kt_ld -= KT;
+                pw += a.pw_wrap;
+                ab += a.ab_wrap;
+            }
+        }
     };
 
     if (!a.lut) {  // fallback: build the table here (callers without a prebuilt image)
@@ -348,6 +386,7 @@ gemv_mma_kernel(const MmaGemvArgs a)
     // ---- main loop
     const uint32_t lane_base = lut_saddr | (uint32_t)(lane * 4);
     const bool xrole = t4 == (g & 3);  // this lane feeds column g of the B operand: x of the tile's block g
+    const uint32_t x_saddr = (uint32_t)__cvta_generic_to_shared(s_x), xswz = (uint32_t)(g * 16);
     uint32_t xr[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) xr[i] = 0;
@@ -356,10 +395,12 @@ gemv_mma_kernel(const MmaGemvArgs a)
     auto compute = [&](const TileRegs& r, const Cursor& c) {
         if (c.kt != kt_loaded) {  // warp-uniform
             if (xrole) {
-                const uint4* src = s_x + (c.kt * 8 + g) * 8;
+                // chunk i of block kt*8+g sits at piece i ^ g: byte offset (kt*1024 + g*128 + i*16) ^ (g*16)
+                const uint32_t base = x_saddr + (uint32_t)(c.kt * 1024 + g * 128);
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const uint4 v = src[i ^ g];
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((base | (uint32_t)(i * 16)) ^ xswz));
                     xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
                 }
             }
@@ -421,7 +462,7 @@ gemv_mma_kernel(const MmaGemvArgs a)
         float part = fmaf(u0, am0, u1 * am1);
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
-        if (t4 == 0) s_part[(c.rt * KT + c.kt) * 8 + g] = part;
+        if (t4 == 0) s_part[c.t * 8 + g] = part;  // tile index = rt * KT + kt
     };
 
     for (;;) {  // three register buffers in rotation: compute the oldest, refill it with the tile after the newest
