@@ -3,7 +3,7 @@
 Drop-in for the hot path of kkbwilldo/quantizations: `core` mirrors the reference's core.py, `modules` its modules.py;
 both call hand-written CUDA through the C ABI declared in include/quantizations_b200.h.  No CPU fallback.
 """
-from . import core, modules  # noqa: F401
+from . import _lib, core, modules  # noqa: F401
 from .core import (  # noqa: F401
     Params4bit,
     QuantState,

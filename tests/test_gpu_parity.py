@@ -532,3 +532,17 @@ def test_fused_decode_attention_matches_torch_attention_path(q):
         assert (m.v_cache.float() - vr.float()).abs().max().item() <= 2e-2 * vr.float().abs().max().item()
         k0, v0 = m.k_cache.clone(), m.v_cache.clone()
         tok = got.argmax().view(1)
+
+
+@pytest.mark.parametrize("M", [2, 4])
+def test_small_batch_runs_one_decode_gemv_per_token(q, M):
+    """2..4 tokens go through the decode GEMV row by row (modules.matmul_4bit): identical to calling the module on each token."""
+    torch.manual_seed(11)
+    lin = q.Linear4bit(1024, 768, bias=True, compute_dtype=torch.bfloat16, quant_type="nf4").to(DEV)
+    lin.bias.data = torch.randn(768, device=DEV, dtype=torch.bfloat16)
+    x = torch.randn(1, M, 1024, device=DEV, dtype=torch.bfloat16)
+    n0 = q._lib.launch_count()
+    y = lin(x)
+    assert q._lib.launch_count() - n0 == M and y.shape == (1, M, 768)
+    for m in range(M):
+        assert torch.equal(y[:, m], lin(x[:, m:m + 1])[:, 0])
