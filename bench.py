@@ -349,6 +349,15 @@ def run_ours(args, rank, world, device):
         return None
     peak, peak_src = measured_peak()
     per_launch_us = ms_per_step * 1e3 / launches_per_step
+    # DRAM traffic per launch from the committed ncu capture (profiles/gemv_traffic.json), averaged over a layer's launches;
+    # only meaningful for the configuration it was captured on
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "gemv_traffic.json")))
+        if world == 1 and args.group and args.model == "llama3-8b":
+            traffic = int(sum(tj["per_launch_bytes"].values()) / len(tj["per_launch_bytes"]))
+    except Exception:
+        traffic = None
     res = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -375,7 +384,7 @@ def run_ours(args, rank, world, device):
         "roofline": {"bound": "hbm", "kernel": "q4::gemv_mma_kernel<bf16, nested>", "achieved": round(value / world, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(value / world / peak, 4), "peak_source": peak_src,
                      "avg_launch_us": round(per_launch_us, 3), "algorithmic_bytes_per_launch": step_bytes_local // launches_per_step,
-                     "traffic": None, "timed_blocks_ms": [round(t, 3) for t in times[:5]]},
+                     "traffic": traffic, "timed_blocks_ms": [round(t, 3) for t in times[:5]]},
     }
     if world == 1 and not args.no_cpu:
         res["cpu_baseline"] = cpu_baseline(mods[:7], x_in, budget_s=args.cpu_seconds)
