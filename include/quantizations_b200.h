@@ -174,6 +174,15 @@ typedef struct q4_gemv_fused_t {
 } q4_gemv_fused_t;
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
 
+/* `n` (<= 4) DEPENDENT decode GEMVs in one persistent launch: stage i+1 may consume what stage i produced (x / x_gate / bias of a
+ * later stage pointing at the `out` of an earlier one), e.g. o_proj -> gate/up -> down_proj -> the next layer's q/k/v.  Between
+ * stages the grid synchronises on a counter in `barrier_ws` (4 bytes of device memory, zero before the first call, left zero;
+ * owned by one stream at a time) instead of ending the kernel: the table image is fetched once, the cold start is paid once, and
+ * the first weight tiles of the next stage are already in registers while the barrier is pending.  Same results as n calls of
+ * q4_gemv_4bit_fused -- which is also what runs when a stage is not eligible (no table image, ragged shape, mixed types).
+ * flags of stage 0 apply to the launch. */
+int q4_gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, void* stream);
+
 /* The decode GEMV decodes one packed BYTE per shared-memory lookup through a 64-KB table derived from the 16-entry 4-bit code
  * and the 256-entry absmax code (reference: `T quant_map[16]` in kernels.cu:1115-1121 and `code[q]` in kernels.cu:552).  The
  * table depends only on (code, code2, dtype), i.e. it is the same for every Linear4bit of a model: build it once into

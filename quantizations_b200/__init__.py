@@ -12,6 +12,7 @@ from .core import (  # noqa: F401
     dequantize_blockwise,
     gemm_4bit,
     gemv_4bit_fused,
+    gemv_4bit_chain,
     decode_attention,
     gemv_4bit,
     get_4bit_type,

@@ -651,6 +651,7 @@ def gemv_4bit_fused(
     flags: int = _lib.Q4_GEMV_PDL,
     prefetch: Optional[Tensor] = None,
     allreduce=None,
+    _defer=None,
 ) -> Tensor:
     """Decode GEMV with a transformer block's elementwise glue fused in (include/quantizations_b200.h: q4_gemv_4bit_fused):
 
@@ -694,10 +695,63 @@ def gemv_4bit_fused(
         None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
         lut.data_ptr(), *_ws_args(A.device), None if allreduce is None else ctypes.pointer(allreduce.struct),
     )
+    if _defer is not None:  # gemv_4bit_chain collects the stage instead of launching it
+        _defer.append((f, (A, gate, rms_weight, residual, out, lut, stats)))
+        return out
     rc = _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
     if rc:
         check(rc, "gemv_4bit_fused")
     return out
+
+
+_chain_barriers = {}
+
+
+class gemv_4bit_chain:
+    """Up to four DEPENDENT decode GEMVs in one persistent launch (include/quantizations_b200.h: q4_gemv_4bit_chain):
+
+        with gemv_4bit_chain() as ch:
+            h = ch.add(a, W_o, st_o, residual=h, out=h)                            # every add() takes gemv_4bit_fused's arguments
+            gu = ch.add(h, None, group=gate_up, rms_weight=ln2)                    # and returns the (not yet written) output
+            h = ch.add(gu[..., I:], W_d, st_d, gate=gu[..., :I], residual=h, out=h)
+        # leaving the block launches the chain
+
+    Results equal those of the same gemv_4bit_fused calls issued one after the other."""
+
+    def __init__(self, flags: int = _lib.Q4_GEMV_PDL):
+        self.flags, self.stages = flags, []
+
+    def __enter__(self):
+        return self
+
+    def add(self, A, B, state=None, **kw) -> Tensor:
+        kw.setdefault("flags", self.flags)
+        return gemv_4bit_fused(A, B, state, _defer=self.stages, **kw)
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.launch()
+        return False
+
+    def launch(self):
+        import ctypes
+
+        if not self.stages:
+            return
+        dev = self.stages[0][1][0].device
+        stream = torch.cuda.current_stream(dev)
+        key = (dev.index, stream.cuda_stream)
+        bar = _chain_barriers.get(key)
+        if bar is None:
+            bar = _chain_barriers[key] = torch.zeros(64, dtype=torch.int32, device=dev)
+        lib = _lib.lib()
+        for i in range(0, len(self.stages), 4):
+            part = self.stages[i:i + 4]
+            arr = (_lib.GemvFused * len(part))(*[f for f, _ in part])
+            rc = lib.q4_gemv_4bit_chain(arr, len(part), bar.data_ptr(), stream.cuda_stream)
+            if rc:
+                check(rc, "gemv_4bit_chain")
+        self.stages = []
 
 
 def decode_attention(qkv: Tensor, cos: Tensor, sin: Tensor, k_cache: Tensor, v_cache: Tensor, pos: Tensor, nh: int, nkv: int,

@@ -119,6 +119,11 @@ int q4_gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* sta
 
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream) { return q4::gemv_4bit_fused(args, (cudaStream_t)stream); }
 
+int q4_gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, void* stream)
+{
+    return q4::gemv_4bit_chain(stages, n, barrier_ws, (cudaStream_t)stream);
+}
+
 int q4_decode_attention(const void* qkv, const void* cos_tab, const void* sin_tab, void* k_cache, void* v_cache, const int64_t* pos,
                         void* out, int nh, int nkv, int hd, int max_len, int dtype, int flags, void* stream)
 {

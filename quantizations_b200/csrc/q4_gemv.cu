@@ -120,11 +120,45 @@ static int launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t
     return finish_launch();
 }
 
+// A prepared (not yet launched) stage of the mma.sync kernel: what q4_gemv_4bit_chain collects before its single launch.
+struct MmaStage {
+    MmaGemvArgs a;
+    bool nested, ktail;
+};
+constexpr int kStagePrepared = 1, kStageNotChainable = 2;  // positive returns of gemv_dispatch(..., stage_out)
+
+template <typename T, bool NESTED>
+static void* mma_kernel_ptr(bool compact, bool ktail)
+{
+    using KernT = void (*)(const MmaChainArgs);
+    KernT k = compact ? (ktail ? (KernT)gemv_mma_kernel<T, NESTED, true, true> : (KernT)gemv_mma_kernel<T, NESTED, true, false>)
+                      : (ktail ? (KernT)gemv_mma_kernel<T, NESTED, false, true> : (KernT)gemv_mma_kernel<T, NESTED, false, false>);
+    return (void*)k;
+}
+
+// one launch of the mma.sync kernel over `n` prepared stages (n == 1: the plain GEMV)
+template <typename T>
+static int launch_mma(const MmaChainArgs& c, bool nested, bool compact, bool ktail, int grid, size_t smem, bool pdl, cudaStream_t stream)
+{
+    using KernT = void (*)(const MmaChainArgs);
+    KernT kern = (KernT)(nested ? mma_kernel_ptr<T, true>(compact, ktail) : mma_kernel_ptr<T, false>(compact, ktail));
+    static bool attr_set[2][2][2] = {};
+    if (!attr_set[nested][compact][ktail]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        attr_set[nested][compact][ktail] = true;
+    }
+    return launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, c);
+}
+
+static int g_dyn_base = -1;  // where dynamic shared memory starts in a CTA's window (probed once, see gemv_dispatch)
+
 template <typename T>
 static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, const float* code, const T* bias, T* out,
                          int64_t N, int64_t K, int blocksize, int flags, const void* next, int64_t next_bytes, cudaStream_t stream,
                          int nmat = 1, const float* const* offsets = nullptr, const int* row_end = nullptr,
-                         const GemvPrologue* pro = nullptr)
+                         const GemvPrologue* pro = nullptr, MmaStage* stage_out = nullptr)
 {
     const AbsmaxView v = make_view(st);
     const bool nested = st->qabsmax != nullptr;
@@ -152,10 +186,11 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                     dyn_base = (int)h;
                 cudaFree(d);
             }
+            g_dyn_base = dyn_base;
         }
         static const int env_impl = getenv("Q4_GEMV_IMPL") ? atoi(getenv("Q4_GEMV_IMPL")) : 0;  // 1: force the mma.sync kernel
         // tcgen05 kernel (q4_gemv_tc.cuh): needs the prebuilt table image and the split-K workspace
-        if (fast && env_impl != 1 && pro && pro->lut && pro->workspace && !pro->ar && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&
+        if (fast && env_impl != 1 && !stage_out && pro && pro->lut && pro->workspace && !pro->ar && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&
             (reinterpret_cast<uintptr_t>(pro->workspace) & 15) == 0) {
             const int bpr = (int)(K / 64);
             const int rt_total = (int)((N + kTcRows - 1) / kTcRows);
@@ -286,6 +321,13 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             a.trace = g_gemv_trace;
             static const int env_debug_mma = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
             a.debug = env_debug_mma;
+            a.multi = multi ? 1 : 0;
+            if (stage_out) {  // q4_gemv_4bit_chain: hand the prepared stage back instead of launching it
+                stage_out->a = a;
+                stage_out->nested = nested;
+                stage_out->ktail = (K % 512) != 0 || (N % 8) != 0;
+                return kStagePrepared;
+            }
             static const int env_aligned = getenv("Q4_GEMV_ALIGNED") ? atoi(getenv("Q4_GEMV_ALIGNED")) : 0;
             // two CTAs per SM for matrices that keep an SM busy for several microseconds (the loop is bound by the legacy tensor
             // pipe and wants all 16 warps); one for small ones (the next launch's prologue shares the SM instead)
@@ -308,24 +350,14 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             const size_t smem = (compact ? 1 : 2) * (size_t)kLutBytes + rest;
             if (smem > 226 * 1024) return Q4_ERR_SHAPE;
             const bool ktail = (K % 512) != 0 || (N % 8) != 0;
-            using KernT = void (*)(const MmaGemvArgs);
-            auto pick = [&](auto compact_c, auto tail_c) -> KernT {
-                constexpr bool C = decltype(compact_c)::value, TL = decltype(tail_c)::value;
-                return nested ? (multi ? (KernT)gemv_mma_kernel<T, true, true, C, TL> : (KernT)gemv_mma_kernel<T, true, false, C, TL>)
-                              : (KernT)gemv_mma_kernel<T, false, false, C, TL>;
-            };
-            KernT kern = compact ? (ktail ? pick(std::true_type{}, std::true_type{}) : pick(std::true_type{}, std::false_type{}))
-                                 : (ktail ? pick(std::false_type{}, std::true_type{}) : pick(std::false_type{}, std::false_type{}));
-            static bool attr_set[2][2][2][2] = {};
-            if (!attr_set[compact][nested][multi][ktail]) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                if (e != cudaSuccess) return (int)e;
-                attr_set[compact][nested][multi][ktail] = true;
-            }
-            return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, pdl, a);
+            MmaChainArgs c = {};
+            c.st[0] = a;
+            c.n = 1;
+            c.x_bytes = a.kt * 1024;
+            return launch_mma<T>(c, nested, compact, ktail, grid, smem, pdl, stream);
         }
     }
+    if (stage_out) return kStageNotChainable;
     if (nmat > 1 || (pro && (pro->x_gate || pro->rms_weight || (pro->ar && pro->ar->world > 1)))) return Q4_ERR_SHAPE;  // only the fast path groups / fuses
     // generic: x as fp32 in shared memory
     const size_t smem = 128 + sizeof(float) * (size_t)K;
@@ -339,7 +371,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
     return launch_pdl(kern, dim3(grid), dim3(256), smem, stream, pdl, x, B, v, code, bias, out, N, K, ilog2(blocksize));
 }
 
-int gemv_4bit_fused(const q4_gemv_fused_t* f, cudaStream_t stream)
+static int gemv_4bit_fused_impl(const q4_gemv_fused_t* f, cudaStream_t stream, MmaStage* stage_out)
 {
     if (!f) return Q4_ERR_NULL;
     if (!valid_blocksize(f->blocksize)) return Q4_ERR_BLOCKSIZE;
@@ -369,13 +401,80 @@ int gemv_4bit_fused(const q4_gemv_fused_t* f, cudaStream_t stream)
         case Q4_F16:
             return gemv_dispatch<__half>((const __half*)f->x, f->B, f->stats, f->code, (const __half*)f->bias, (__half*)f->out,
                                          f->rows, f->K, f->blocksize, flags, f->prefetch, f->prefetch_bytes, stream, nmat, offsets,
-                                         row_end, &pro);
+                                         row_end, &pro, stage_out);
         case Q4_BF16:
             return gemv_dispatch<__nv_bfloat16>((const __nv_bfloat16*)f->x, f->B, f->stats, f->code, (const __nv_bfloat16*)f->bias,
                                                 (__nv_bfloat16*)f->out, f->rows, f->K, f->blocksize, flags, f->prefetch,
-                                                f->prefetch_bytes, stream, nmat, offsets, row_end, &pro);
+                                                f->prefetch_bytes, stream, nmat, offsets, row_end, &pro, stage_out);
         default: return Q4_ERR_DTYPE;
     }
+}
+
+int gemv_4bit_fused(const q4_gemv_fused_t* f, cudaStream_t stream) { return gemv_4bit_fused_impl(f, stream, nullptr); }
+
+// `n` dependent decode GEMVs (stage i+1 may read what stage i wrote) in ONE persistent launch: see MmaChainArgs.  Falls back to n
+// ordinary launches whenever a stage cannot run on the chained kernel, so the result never depends on the path taken.
+int gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, cudaStream_t stream)
+{
+    if (n < 1) return 0;
+    if (!stages) return Q4_ERR_NULL;
+    static const int env_nochain = getenv("Q4_GEMV_NO_CHAIN") ? atoi(getenv("Q4_GEMV_NO_CHAIN")) : 0;
+    bool chain = n > 1 && n <= kMaxChain && barrier_ws && !env_nochain && (reinterpret_cast<uintptr_t>(barrier_ws) & 3) == 0;
+    MmaStage st[kMaxChain];
+    for (int i = 0; chain && i < n; i++) {
+        if (stages[i].rows == 0) chain = false;
+        else {
+            const int rc = gemv_4bit_fused_impl(&stages[i], stream, &st[i]);
+            if (rc < 0 || rc > kStageNotChainable) return rc;  // argument error (or a CUDA error from the one-time probe)
+            if (rc != kStagePrepared) chain = false;
+        }
+    }
+    for (int i = 0; chain && i < n; i++) {
+        // one kernel instance for the whole chain: same element type, nesting, no ragged shapes, the same table image; tensor-
+        // parallel stages keep their fixed CTA -> rows mapping only at the plain grid, so they are not chained with wider grids
+        if (stages[i].dtype != stages[0].dtype || st[i].nested != st[0].nested || st[i].ktail || !st[i].a.lut || st[i].a.lut != st[0].a.lut)
+            chain = false;
+    }
+    if (chain && g_dyn_base != kDynBase) chain = false;
+    if (chain) {
+        MmaChainArgs c = {};
+        c.n = n;
+        c.barrier = reinterpret_cast<unsigned*>(barrier_ws);
+        const int sms = sm_count();
+        bool any_ar = false;
+        for (int i = 0; i < n; i++) {
+            c.st[i] = st[i].a;
+            if (c.st[i].kt * 1024 > c.x_bytes) c.x_bytes = c.st[i].kt * 1024;
+            any_ar = any_ar || st[i].a.ar_world > 1;
+        }
+        // grid: every CTA must be resident at once (grid barrier).  Two half-SM CTAs per SM when the shared-memory plan allows it
+        // (all 16 warps per SM work on the chain), else one; tensor-parallel stages need the plain one-per-SM mapping.
+        int grid = 0;
+        size_t smem = 0;
+        for (int per_sm = any_ar ? 1 : 2; per_sm >= 1; per_sm--) {
+            grid = sms * per_sm;
+            size_t part = 0;
+            for (int i = 0; i < n; i++) {
+                const size_t p = (size_t)((c.st[i].rt_total + grid - 1) / grid) * c.st[i].kt * 32;
+                if (p > part) part = p;
+            }
+            smem = (size_t)kLutBytes + c.x_bytes + 128 + 16 + part;
+            if (smem <= (per_sm == 2 ? 112 * 1024 : 226 * 1024)) break;
+            if (per_sm == 1) chain = false;
+        }
+        if (chain && any_ar && grid > kArMaxCtas) chain = false;
+        if (chain) {
+            const bool pdl = stages[0].flags & Q4_GEMV_PDL;
+            switch (stages[0].dtype) {
+                case Q4_F16: return launch_mma<__half>(c, st[0].nested, true, false, grid, smem, pdl, stream);
+                case Q4_BF16: return launch_mma<__nv_bfloat16>(c, st[0].nested, true, false, grid, smem, pdl, stream);
+                default: return Q4_ERR_DTYPE;
+            }
+        }
+    }
+    for (int i = 0; i < n; i++)
+        if (int rc = gemv_4bit_fused_impl(&stages[i], stream, nullptr)) return rc;
+    return 0;
 }
 
 int gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, cudaStream_t stream)

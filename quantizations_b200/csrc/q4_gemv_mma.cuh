@@ -68,7 +68,36 @@ struct MmaGemvArgs {
     // host-computed strides of the fast path's load cursor (tile index += warps per CTA)
     long long pw_step, pw_wrap;
     int ab_step, ab_wrap, d_rt, d_kt;
+    int multi;  // grouped launch with per-matrix offsets (nested statistics)
 };
+
+// A launch runs `n` dependent GEMVs back to back ("chain": e.g. o_proj -> gate/up -> down_proj -> next layer's q/k/v): one
+// persistent grid, the table copied once, a grid-wide barrier instead of a launch boundary between stages, and the first weight
+// tiles of stage s+1 already in registers while the barrier is pending.  n == 1 is the plain single-GEMV launch.
+constexpr int kMaxChain = 4;
+struct MmaChainArgs {
+    MmaGemvArgs st[kMaxChain];
+    int n;
+    int x_bytes;          // shared-memory bytes reserved for the activation vector: max over the stages of kt * 1024
+    unsigned* barrier;    // n > 1: grid-barrier counter in global memory (zero between launches; the kernel leaves it zero)
+};
+
+// Grid-wide barrier of a persistent launch whose CTAs are all co-resident (the dispatcher sizes the grid accordingly).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        for (long long spin = 0;; spin++) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            if (spin > (1ll << 27)) __trap();  // a CTA never arrived (grid not co-resident?): fail loudly
+        }
+    }
+    __syncthreads();
+}
 
 constexpr int kArMaxCtas = 1024;       // Q4_AR_MAX_CTAS
 constexpr int kArDataOffset = 65536;   // Q4_AR_DATA_OFFSET
@@ -145,10 +174,10 @@ __device__ __noinline__ void stage_x_fused(const void* x, const void* x_gate, co
     for (int c = tid; c < npad; c += nthr) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (c < nchunk) {
-            v = __ldg(reinterpret_cast<const uint4*>(a.x) + c);
+            v = __ldcg(reinterpret_cast<const uint4*>(a.x) + c);
             uint32_t uw[4] = {v.x, v.y, v.z, v.w};
             if (a.x_gate) {
-                const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(a.x_gate) + c);
+                const uint4 g4 = __ldcg(reinterpret_cast<const uint4*>(a.x_gate) + c);
                 const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
                 for (int q2 = 0; q2 < 4; q2++) {
@@ -193,13 +222,11 @@ constexpr int kDynBase = 1024;  // where dynamic shared memory starts in the CTA
 constexpr int kMmaThreads = 256;
 constexpr int kBuffers = 3;     // weight tiles a warp holds in registers (one being consumed, the others in flight)
 
-template <typename T, bool NESTED, bool MULTI, bool COMPACT, bool TAIL>
+template <typename T, bool NESTED, bool COMPACT, bool TAIL>
 __global__ void __launch_bounds__(kMmaThreads, 2)
-gemv_mma_kernel(const MmaGemvArgs a)
+gemv_mma_kernel(const __grid_constant__ MmaChainArgs c)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int K = a.K, R = a.rows, KT = a.kt;
-    const int bpr = K >> 6;  // 64-wide blocks per row
     // Shared-memory plan.  The PRMT splice needs the table at (64-KB aligned window address) + (compile-time immediate).
     //   COMPACT: the table is the first thing in dynamic shared memory, which starts kDynBase into the window -> ~75-100 KB per
     //            CTA, two CTAs per SM: in a decode chain the NEXT launch's CTA is co-resident and runs its whole x-independent
@@ -210,8 +237,8 @@ gemv_mma_kernel(const MmaGemvArgs a)
     const uint32_t lut_saddr = COMPACT ? (smem_saddr - kDynBase) : ((smem_saddr + 0xFFFFu) & 0xFFFF0000u);
     if (COMPACT && lut_saddr != 0) __trap();  // the host probe and the kernel disagree about the window layout
     uint8_t* lut = COMPACT ? smem : smem + (lut_saddr - smem_saddr);
-    uint4* s_x = reinterpret_cast<uint4*>(lut + kLutBytes);                   // KT*64 chunks of 8 activations, swizzled
-    float* s_red = reinterpret_cast<float*>(lut + kLutBytes + KT * 1024);     // 32 floats
+    uint4* s_x = reinterpret_cast<uint4*>(lut + kLutBytes);                   // kt*64 chunks of 8 activations, swizzled
+    float* s_red = reinterpret_cast<float*>(lut + kLutBytes + c.x_bytes);     // 32 floats
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 32);                // mbarrier (+ pad)
     float* s_part = reinterpret_cast<float*>(s_bar + 2);                      // [row tile][k tile][8 rows]
 
@@ -219,18 +246,12 @@ gemv_mma_kernel(const MmaGemvArgs a)
     const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
     const int g = lane >> 2, t4 = lane & 3;
 
-    // this CTA's row tiles: a contiguous byte range of the packed weight and of the statistics
-    const int rt0 = (int)(((int64_t)blockIdx.x * a.rt_total) / gridDim.x);
-    const int rt1 = (int)(((int64_t)(blockIdx.x + 1) * a.rt_total) / gridDim.x);
-    const int ntiles = (rt1 - rt0) * KT;
-    const int row_lo = rt0 * 8, row_hi = rt1 * 8 < R ? rt1 * 8 : R;
-
     pdl_launch_dependents();
-    mma_trace(a, 0);
+    mma_trace(c.st[0], 0);
 
     // ---- table: one TMA bulk copy of the prebuilt image (no thread touches it), completion on an mbarrier
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
-    if (a.lut && tid == 0) {
+    if (c.st[0].lut && tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kLutBytes) : "memory");
@@ -238,16 +259,27 @@ gemv_mma_kernel(const MmaGemvArgs a)
         for (int i = 0; i < 4; i++)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              lut_saddr + kImm + i * (kLutBytes / 4)),
-                         "l"(reinterpret_cast<const uint8_t*>(a.lut) + i * (kLutBytes / 4)), "r"(kLutBytes / 4), "r"(bar)
+                         "l"(reinterpret_cast<const uint8_t*>(c.st[0].lut) + i * (kLutBytes / 4)), "r"(kLutBytes / 4), "r"(bar)
                          : "memory");
     }
     // ---- optional hint: this CTA's share of what the NEXT launch will stream, HBM -> L2 (TMA bulk prefetch, fire and forget)
-    if (warp == nw - 1 && a.next_bytes > 0) {
-        const int64_t share = ((a.next_bytes / gridDim.x) + 15) & ~(int64_t)15;
+    if (warp == nw - 1 && c.st[0].next_bytes > 0) {
+        const int64_t share = ((c.st[0].next_bytes / gridDim.x) + 15) & ~(int64_t)15;
         const int64_t lo = share * blockIdx.x;
-        const int64_t n = lo + share <= a.next_bytes ? share : a.next_bytes - lo;
-        if (n > 0) bulk_prefetch_l2_range(a.next + lo, n, lane);
+        const int64_t n = lo + share <= c.st[0].next_bytes ? share : c.st[0].next_bytes - lo;
+        if (n > 0) bulk_prefetch_l2_range(c.st[0].next + lo, n, lane);
     }
+
+  for (int stage = 0; stage < c.n; stage++) {  // (body indented as the single-stage kernel it grew from)
+    const MmaGemvArgs& a = c.st[stage];
+    const int K = a.K, R = a.rows, KT = a.kt;
+    const int bpr = K >> 6;  // 64-wide blocks per row
+    // this CTA's row tiles: a contiguous byte range of the packed weight and of the statistics
+    const int rt0 = (int)(((int64_t)blockIdx.x * a.rt_total) / gridDim.x);
+    const int rt1 = (int)(((int64_t)(blockIdx.x + 1) * a.rt_total) / gridDim.x);
+    const int ntiles = (rt1 - rt0) * KT;
+    const int row_lo = rt0 * 8, row_hi = rt1 * 8 < R ? rt1 * 8 : R;
+    const bool MULTI = a.multi != 0;
     float off[kMaxMats];
 #pragma unroll
     for (int m = 0; m < kMaxMats; m++) off[m] = (NESTED && (MULTI || m == 0) && a.offsets[m]) ? __ldg(a.offsets[m]) : 0.0f;
@@ -321,7 +353,7 @@ gemv_mma_kernel(const MmaGemvArgs a)
         }
     };
 
-    if (!a.lut) {  // fallback: build the table here (callers without a prebuilt image)
+    if (stage == 0 && !a.lut) {  // fallback: build the table here (callers without a prebuilt image)
         for (int c = tid; c < kLutBytes / 16; c += nthr) {
             const int seg = c >> 3, b = seg >> 1;
             uint32_t word;
@@ -340,8 +372,9 @@ gemv_mma_kernel(const MmaGemvArgs a)
     if (c2.t < ntiles) issue(r2, c2);
     mma_trace(a, 1);
 
-    // ---- everything below may read the previous kernel's output
-    pdl_wait();
+    // ---- everything below may read the previous kernel's (stage 0) or the previous stage's output
+    if (stage == 0) pdl_wait();
+    else grid_barrier(c.barrier, (unsigned)stage * gridDim.x);
     mma_trace(a, 2);
     {
         const int nchunk = K >> 3;  // 16-byte chunks of x
@@ -357,7 +390,7 @@ gemv_mma_kernel(const MmaGemvArgs a)
                 for (int j = 0; j < 4; j++) {
                     const int c = cb + j * nthr;
                     v[j] = make_uint4(0, 0, 0, 0);
-                    if (c < nchunk) v[j] = __ldg(reinterpret_cast<const uint4*>(a.x) + c);
+                    if (c < nchunk) v[j] = __ldcg(reinterpret_cast<const uint4*>(a.x) + c);  // coherent: may be a previous stage's output
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -369,7 +402,7 @@ gemv_mma_kernel(const MmaGemvArgs a)
     }
     mma_trace(a, 3);
     __syncthreads();
-    if (a.lut) {  // table landed?
+    if (stage == 0 && a.lut) {  // table landed?
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -410,7 +443,11 @@ gemv_mma_kernel(const MmaGemvArgs a)
         // the tensor pipe (software pipeline, everything unrolled): a warp then has 4*kAhead shared-memory loads in flight
         // instead of stalling on each group of four.
         float ce[4] = {0.0f, 0.0f, 0.0f, 0.0f}, co[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#ifdef Q4_KAHEAD
+        constexpr int kAhead = Q4_KAHEAD;
+#else
         constexpr int kAhead = 3;
+#endif
         uint32_t f[kAhead + 1][4];
         auto fetch = [&](uint32_t (&d)[4], int j) {
             const uint32_t wa = r.wa.v[j >> 1], wb = r.wb.v[j >> 1];
@@ -493,7 +530,7 @@ gemv_mma_kernel(const MmaGemvArgs a)
         const int r = row_lo + i;
         T y = Elem<T>::from_f32(total);
         const T* bias = reinterpret_cast<const T*>(a.bias);
-        if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + Elem<T>::to_f32(bias[r]));  // torch `out += bias`
+        if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + Elem<T>::to_f32(__ldcg(bias + r)));  // torch `out += bias`
         reinterpret_cast<T*>(a.out)[r] = y;
     };
     const int nrows = row_hi - row_lo;
@@ -544,6 +581,16 @@ gemv_mma_kernel(const MmaGemvArgs a)
         for (int i = tid; i < nrows; i += nthr) finish(i, row_total(i));
     }
     mma_trace(a, 5);
+  }  // stage loop
+
+    if (c.n > 1) {  // leave the barrier counter at zero for the next launch: the last CTA to get here resets it
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned old = atomicAdd(c.barrier, 1u);
+            if (old == (unsigned)c.n * gridDim.x - 1) *c.barrier = 0;
+        }
+    }
 }
 
 __global__ void probe_dyn_smem_base_kernel(uint32_t* out)

@@ -546,3 +546,57 @@ def test_small_batch_runs_one_decode_gemv_per_token(q, M):
     assert q._lib.launch_count() - n0 == M and y.shape == (1, M, 768)
     for m in range(M):
         assert torch.equal(y[:, m], lin(x[:, m:m + 1])[:, 0])
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_chained_gemvs_equal_separate_launches(q, dtype):
+    """q4_gemv_4bit_chain: o_proj(+residual) -> norm + gate/up (grouped) -> SwiGLU + down(+residual) -> norm + next q/k/v in ONE
+    persistent launch (grid barriers between the stages) gives bit-identical results to the four separate launches, on repeated
+    calls (the barrier counter returns to zero) and under CUDA-graph replay."""
+    from quantizations_b200 import graphs
+
+    torch.manual_seed(21)
+    dt = TDT[dtype]
+    H, I = 1024, 2048
+    mk = lambda n, k: q.Linear4bit(k, n, bias=False, compute_dtype=dt, quant_type="nf4").to(DEV)
+    o, gate, up, down, qp, kp, vp = mk(H, H), mk(I, H), mk(I, H), mk(H, I), mk(H, H), mk(256, H), mk(256, H)
+    gu, qkv = q.Linear4bitGroup([gate, up]), q.Linear4bitGroup([qp, kp, vp])
+    ln2 = (1 + 0.1 * torch.randn(H, device=DEV)).to(dt)
+    ln1 = (1 + 0.1 * torch.randn(H, device=DEV)).to(dt)
+    a = torch.randn(1, 1, H, device=DEV, dtype=dt)
+    h0 = torch.randn(1, 1, H, device=DEV, dtype=dt)
+
+    def separate():
+        h = h0.clone()
+        q.gemv_4bit_fused(a, o.weight.data, o.weight.quant_state, residual=h, out=h)
+        g_u = q.gemv_4bit_fused(h, None, group=gu, rms_weight=ln2)
+        q.gemv_4bit_fused(g_u[..., I:], down.weight.data, down.weight.quant_state, gate=g_u[..., :I], residual=h, out=h)
+        return h, q.gemv_4bit_fused(h, None, group=qkv, rms_weight=ln1)
+
+    hs, qs = separate()
+    h = h0.clone()
+    g_u = torch.empty(1, 1, 2 * I, device=DEV, dtype=dt)
+    out_qkv = torch.empty(1, 1, H + 512, device=DEV, dtype=dt)
+
+    def chained():
+        with q.gemv_4bit_chain() as ch:
+            ch.add(a, o.weight.data, o.weight.quant_state, residual=h, out=h)
+            ch.add(h, None, group=gu, rms_weight=ln2, out=g_u)
+            ch.add(g_u[..., I:], down.weight.data, down.weight.quant_state, gate=g_u[..., :I], residual=h, out=h)
+            ch.add(h, None, group=qkv, rms_weight=ln1, out=out_qkv)
+
+    n0 = q._lib.launch_count()
+    chained()
+    assert q._lib.launch_count() - n0 == 1
+    assert torch.equal(h, hs) and torch.equal(out_qkv, qs)
+    for _ in range(3):
+        h.copy_(h0)
+        chained()
+        assert torch.equal(h, hs) and torch.equal(out_qkv, qs)
+    h.copy_(h0)
+    g = graphs.capture(chained)   # warm-up calls + capture advance h: reset before every replay
+    for _ in range(3):
+        h.copy_(h0)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(h, hs) and torch.equal(out_qkv, qs)
