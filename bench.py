@@ -223,8 +223,8 @@ def run_ours(args, rank, world, device):
     fused_args = {}
     ws_ptr, ws_bytes = q.core._ws_args(device)  # (None, 0) unless Q4_GEMV_TC=1: the mma.sync kernel is the default
 
-    def launch_cabi(i, m, flags):
-        """q4_gemv_4bit_fused (include/quantizations_b200.h) with the prebuilt table image; argument structs are built once"""
+    def launch_struct(i, m, flags):
+        """argument struct of unit i (q4_gemv_fused_t, include/quantizations_b200.h) with the prebuilt table image; built once"""
         key = (i, flags)
         f = fused_args.get(key)
         if f is None:
@@ -242,15 +242,55 @@ def run_ours(args, rank, world, device):
                                    None, 1, st.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, st.blocksize,
                                    _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr(), ws_ptr, ws_bytes, ar)
             fused_args[key] = f
+        return f
+
+    def launch_cabi(i, m, flags):
+        f = launch_struct(i, m, flags)
         rc = L.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream().cuda_stream)
         if rc:
             _lib.check(rc, "q4_gemv_4bit_fused")
         if comm is not None and fused_ar is None and m.parallel == "row":
             comm.all_reduce(outs[(m.name_, m.out_features)])
 
+    chain_arrays = []
+    chain_bar = torch.zeros(64, dtype=torch.int32, device=device)
+
+    def build_chains():
+        """Chained launches (q4_gemv_4bit_chain): the decode data flow is attention(L) -> [o_L -> gate/up_L -> down_L -> qkv_{L+1}]
+        -> attention(L+1), so the stack is one single launch (qkv_0) plus one persistent launch of up to four dependent GEMVs per
+        layer.  Stage argument structs are the same ones the per-launch path uses."""
+        flags = pdl
+        for i, m in enumerate(units):
+            launch_struct(i, m, flags)
+        order = [[0]]
+        per = 4
+        nl = len(units) // per
+        for l in range(nl):
+            grp = [l * per + 1, l * per + 2, l * per + 3]
+            if l + 1 < nl:
+                grp.append((l + 1) * per)
+            order.append(grp)
+        for grp in order:
+            arr = (_lib.GemvFused * len(grp))(*[fused_args[(i, flags)] for i in grp])
+            chain_arrays.append((arr, len(grp)))
+
+    def step_chained():
+        stream = torch.cuda.current_stream().cuda_stream
+        for arr, n in chain_arrays:
+            rc = L.q4_gemv_4bit_chain(arr, n, chain_bar.data_ptr(), stream)
+            if rc:
+                _lib.check(rc, "q4_gemv_4bit_chain")
+
+    use_chain = args.chain and args.group and not side and (comm is None or fused_ar is not None) and len(units) % 4 == 0
+
     def step_cabi():
         """one decode token's worth of Linear4bit GEMVs straight through the C ABI"""
-        run_stack(launch_cabi)
+        if use_chain:
+            if not chain_arrays:
+                build_chains()
+            step_chained()
+        else:
+            run_stack(launch_cabi)
 
     # ---- value: CUDA-graph replay of the step, device-timed
     n0 = _lib.launch_count()
@@ -370,6 +410,7 @@ def run_ours(args, rank, world, device):
             "packed_weight_bytes_per_gpu": packed_bytes, "algorithmic_bytes_per_step": step_bytes,
             "l2_policy": "inputs larger than L2: every layer has its own weights (3.5 GB/step >> 126 MB L2), no flush needed",
             "launch": ("CUDA graph replay" if graph is not None else "eager") + (" + programmatic dependent launch" if args.pdl else "")
+                      + (", chained: 1 + layers persistent launches per step (o -> gate/up -> down -> next q/k/v per launch)" if use_chain else "")
                       + (", q/k/v and gate/up as parallel graph branches (co-resident CTAs)" if args.branches else "")
                       + (", next-layer weight L2 prefetch hint" if args.prefetch else ""),
             "parallelism": f"tp{world}" if world > 1 else "single GPU",
@@ -559,6 +600,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="decoder layers in the stack (0 = the model's own count)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false")
+    ap.add_argument("--chain", action="store_true",
+                    help="one persistent launch per layer (q4_gemv_4bit_chain: o -> gate/up -> down -> next q/k/v) instead of one "
+                         "launch per (grouped) Linear; measured SLOWER on B200 (1.65 vs 1.47 ms/step: DESIGN.md 4.1c), hence opt-in")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="tensor-parallel runs: NCCL all-reduce after the row-parallel GEMVs (the baseline) instead of the fused epilogue exchange")
     ap.add_argument("--prefetch", action="store_true",

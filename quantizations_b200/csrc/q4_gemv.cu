@@ -128,11 +128,12 @@ struct MmaStage {
 constexpr int kStagePrepared = 1, kStageNotChainable = 2;  // positive returns of gemv_dispatch(..., stage_out)
 
 template <typename T, bool NESTED>
-static void* mma_kernel_ptr(bool compact, bool ktail)
+static void* mma_kernel_ptr(bool compact, bool ktail, bool chain)
 {
     using KernT = void (*)(const MmaChainArgs);
-    KernT k = compact ? (ktail ? (KernT)gemv_mma_kernel<T, NESTED, true, true> : (KernT)gemv_mma_kernel<T, NESTED, true, false>)
-                      : (ktail ? (KernT)gemv_mma_kernel<T, NESTED, false, true> : (KernT)gemv_mma_kernel<T, NESTED, false, false>);
+    if (chain) return (void*)(KernT)gemv_mma_kernel<T, NESTED, true, false, true>;  // chains: compact layout, no ragged shapes
+    KernT k = compact ? (ktail ? (KernT)gemv_mma_kernel<T, NESTED, true, true, false> : (KernT)gemv_mma_kernel<T, NESTED, true, false, false>)
+                      : (ktail ? (KernT)gemv_mma_kernel<T, NESTED, false, true, false> : (KernT)gemv_mma_kernel<T, NESTED, false, false, false>);
     return (void*)k;
 }
 
@@ -141,13 +142,14 @@ template <typename T>
 static int launch_mma(const MmaChainArgs& c, bool nested, bool compact, bool ktail, int grid, size_t smem, bool pdl, cudaStream_t stream)
 {
     using KernT = void (*)(const MmaChainArgs);
-    KernT kern = (KernT)(nested ? mma_kernel_ptr<T, true>(compact, ktail) : mma_kernel_ptr<T, false>(compact, ktail));
-    static bool attr_set[2][2][2] = {};
-    if (!attr_set[nested][compact][ktail]) {
+    const bool chain = c.n > 1;
+    KernT kern = (KernT)(nested ? mma_kernel_ptr<T, true>(compact, ktail, chain) : mma_kernel_ptr<T, false>(compact, ktail, chain));
+    static bool attr_set[2][2][2][2] = {};
+    if (!attr_set[nested][compact][ktail][chain]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        attr_set[nested][compact][ktail] = true;
+        attr_set[nested][compact][ktail][chain] = true;
     }
     return launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, c);
 }

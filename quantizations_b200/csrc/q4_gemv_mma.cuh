@@ -222,7 +222,7 @@ constexpr int kDynBase = 1024;  // where dynamic shared memory starts in the CTA
 constexpr int kMmaThreads = 256;
 constexpr int kBuffers = 3;     // weight tiles a warp holds in registers (one being consumed, the others in flight)
 
-template <typename T, bool NESTED, bool COMPACT, bool TAIL>
+template <typename T, bool NESTED, bool COMPACT, bool TAIL, bool CHAIN>
 __global__ void __launch_bounds__(kMmaThreads, 2)
 gemv_mma_kernel(const __grid_constant__ MmaChainArgs c)
 {
@@ -270,8 +270,10 @@ gemv_mma_kernel(const __grid_constant__ MmaChainArgs c)
         if (n > 0) bulk_prefetch_l2_range(c.st[0].next + lo, n, lane);
     }
 
-  for (int stage = 0; stage < c.n; stage++) {  // (body indented as the single-stage kernel it grew from)
-    const MmaGemvArgs& a = c.st[stage];
+  // CHAIN = false: exactly one stage, every argument a compile-time offset into the parameter bank (no indexed constant loads
+  // in the loop); CHAIN = true: c.n stages, arguments indexed by the stage.
+  for (int stage = 0; stage < (CHAIN ? c.n : 1); stage++) {  // (body indented as the single-stage kernel it grew from)
+    const MmaGemvArgs& a = CHAIN ? c.st[stage] : c.st[0];
     const int K = a.K, R = a.rows, KT = a.kt;
     const int bpr = K >> 6;  // 64-wide blocks per row
     // this CTA's row tiles: a contiguous byte range of the packed weight and of the statistics
@@ -373,7 +375,7 @@ gemv_mma_kernel(const __grid_constant__ MmaChainArgs c)
     mma_trace(a, 1);
 
     // ---- everything below may read the previous kernel's (stage 0) or the previous stage's output
-    if (stage == 0) pdl_wait();
+    if (!CHAIN || stage == 0) pdl_wait();
     else grid_barrier(c.barrier, (unsigned)stage * gridDim.x);
     mma_trace(a, 2);
     {
@@ -583,7 +585,7 @@ gemv_mma_kernel(const __grid_constant__ MmaChainArgs c)
     mma_trace(a, 5);
   }  // stage loop
 
-    if (c.n > 1) {  // leave the barrier counter at zero for the next launch: the last CTA to get here resets it
+    if (CHAIN && c.n > 1) {  // leave the barrier counter at zero for the next launch: the last CTA to get here resets it
         __syncthreads();
         if (tid == 0) {
             __threadfence();

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .core import decode_attention, gemv_4bit_fused
+from .core import decode_attention, gemv_4bit_chain, gemv_4bit_fused
 
 
 @dataclass
@@ -75,6 +75,8 @@ class Llama(nn.Module):
         self.fuse_glue = True  # fold RMSNorm / SwiGLU / residual adds into the decode GEMV launches (Linear4bit layers only)
         self.fused_ar = None   # tp.FusedAllReduce: the row-parallel all-reduce inside the GEMV epilogue instead of NCCL
         self.fuse_attn = cfg.head_dim == 128  # decode: RoPE + KV append + attention as one launch (q4_decode_attention)
+        self.chain = False     # decode: o -> gate/up -> down -> next layer's q/k/v as ONE persistent launch (q4_gemv_4bit_chain);
+                               # measured slower than separate launches under programmatic dependent launch
         g = torch.Generator(device=device).manual_seed(1234)
         self.embed = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
         self.lm_head = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
@@ -111,6 +113,9 @@ class Llama(nn.Module):
         cos, sin = self.cos.index_select(0, pos), self.sin.index_select(0, pos)
         # causal mask over the whole static cache: key j visible to query i iff j <= pos[i]
         mask = self.positions[None, :] <= pos[:, None]                      # [T, max_len]
+        if (T == 1 and self.chain and self.fuse_glue and self.fuse_attn and all(L.qkv is not None for L in self.layers)
+                and (self.tp == 1 or self.fused_ar is not None)):
+            return self._decode_chained(x, pos)
         for li, L in enumerate(self.layers):
             fused = L.qkv is not None and T == 1 and self.fuse_glue
             h = None if fused else F.rms_norm(x, (cfg.hidden,), L.ln1, cfg.eps)
@@ -149,6 +154,27 @@ class Llama(nn.Module):
             x = x + self._allreduce(L.down_proj(F.silu(g) * u))
         x = F.rms_norm(x[:, -1:], (cfg.hidden,), self.norm, cfg.eps)
         return F.linear(x, self.lm_head).view(-1)
+
+    def _decode_chained(self, x, pos):
+        """One decode step in 1 + 2 * layers launches: [norm + q/k/v of layer 0], then per layer the attention glue kernel and
+        one chained launch [o + residual -> norm + gate/up -> SwiGLU + down + residual -> norm + q/k/v of the NEXT layer]."""
+        cfg, Ls = self.cfg, self.layers
+        h = x.clone()                                               # residual stream, updated in place by the GEMV epilogues
+        I = Ls[0].gate_up.splits[0]
+        qkv = gemv_4bit_fused(h, None, group=Ls[0].qkv, rms_weight=Ls[0].ln1, rms_eps=cfg.eps)
+        gu = torch.empty(1, 1, Ls[0].gate_up.out_features, dtype=h.dtype, device=h.device)
+        for li, L in enumerate(Ls):
+            a = decode_attention(qkv, self.cos, self.sin, self.k_cache[li], self.v_cache[li], pos, L.nh, L.nkv)
+            with gemv_4bit_chain() as ch:
+                ch.add(a, L.o_proj.weight.data, L.o_proj.weight.quant_state, residual=h, out=h, allreduce=self.fused_ar)
+                ch.add(h, None, group=L.gate_up, rms_weight=L.ln2, rms_eps=cfg.eps, out=gu)
+                ch.add(gu[..., I:], L.down_proj.weight.data, L.down_proj.weight.quant_state, gate=gu[..., :I], residual=h, out=h,
+                       allreduce=self.fused_ar)
+                if li + 1 < len(Ls):
+                    N = Ls[li + 1]
+                    ch.add(h, None, group=N.qkv, rms_weight=N.ln1, rms_eps=cfg.eps, out=qkv)
+        y = F.rms_norm(h, (cfg.hidden,), self.norm, cfg.eps)
+        return F.linear(y, self.lm_head).view(-1)
 
     @torch.no_grad()
     def generate(self, prompt: torch.Tensor, new_tokens: int, use_graph: bool = True):
