@@ -130,8 +130,9 @@ constexpr int kStagePrepared = 1, kStageNotChainable = 2;  // positive returns o
 template <typename T, bool NESTED>
 static void* mma_kernel_ptr(bool compact, bool ktail, bool chain)
 {
-    using KernT = void (*)(const MmaChainArgs);
-    if (chain) return (void*)(KernT)gemv_mma_kernel<T, NESTED, true, false, true>;  // chains: compact layout, no ragged shapes
+    using ChainT = void (*)(const MmaChainArgs);
+    using KernT = void (*)(const MmaSingleArgs);
+    if (chain) return (void*)(ChainT)gemv_mma_kernel<T, NESTED, true, false, true>;  // chains: compact layout, no ragged shapes
     KernT k = compact ? (ktail ? (KernT)gemv_mma_kernel<T, NESTED, true, true, false> : (KernT)gemv_mma_kernel<T, NESTED, true, false, false>)
                       : (ktail ? (KernT)gemv_mma_kernel<T, NESTED, false, true, false> : (KernT)gemv_mma_kernel<T, NESTED, false, false, false>);
     return (void*)k;
@@ -141,9 +142,8 @@ static void* mma_kernel_ptr(bool compact, bool ktail, bool chain)
 template <typename T>
 static int launch_mma(const MmaChainArgs& c, bool nested, bool compact, bool ktail, int grid, size_t smem, bool pdl, cudaStream_t stream)
 {
-    using KernT = void (*)(const MmaChainArgs);
     const bool chain = c.n > 1;
-    KernT kern = (KernT)(nested ? mma_kernel_ptr<T, true>(compact, ktail, chain) : mma_kernel_ptr<T, false>(compact, ktail, chain));
+    void* kern = nested ? mma_kernel_ptr<T, true>(compact, ktail, chain) : mma_kernel_ptr<T, false>(compact, ktail, chain);
     static bool attr_set[2][2][2][2] = {};
     if (!attr_set[nested][compact][ktail][chain]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -151,7 +151,12 @@ static int launch_mma(const MmaChainArgs& c, bool nested, bool compact, bool kta
         if (e != cudaSuccess) return (int)e;
         attr_set[nested][compact][ktail][chain] = true;
     }
-    return launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, c);
+    if (chain) return launch_pdl((void (*)(const MmaChainArgs))kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, c);
+    MmaSingleArgs one = {};
+    one.st[0] = c.st[0];
+    one.n = 1;
+    one.x_bytes = c.x_bytes;
+    return launch_pdl((void (*)(const MmaSingleArgs))kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, one);
 }
 
 static int g_dyn_base = -1;  // where dynamic shared memory starts in a CTA's window (probed once, see gemv_dispatch)

@@ -34,6 +34,8 @@
 // are summed in a fixed order (deterministic) and stored with the bias / residual.
 #pragma once
 
+#include <type_traits>
+
 #include "q4_common.cuh"
 
 namespace q4 {
@@ -75,12 +77,14 @@ struct MmaGemvArgs {
 // persistent grid, the table copied once, a grid-wide barrier instead of a launch boundary between stages, and the first weight
 // tiles of stage s+1 already in registers while the barrier is pending.  n == 1 is the plain single-GEMV launch.
 constexpr int kMaxChain = 4;
-struct MmaChainArgs {
-    MmaGemvArgs st[kMaxChain];
+template <int NST> struct MmaStagesArgs {
+    MmaGemvArgs st[NST];
     int n;
     int x_bytes;          // shared-memory bytes reserved for the activation vector: max over the stages of kt * 1024
     unsigned* barrier;    // n > 1: grid-barrier counter in global memory (zero between launches; the kernel leaves it zero)
 };
+using MmaChainArgs = MmaStagesArgs<kMaxChain>;
+using MmaSingleArgs = MmaStagesArgs<1>;  // the plain launch: a quarter of the parameter bytes
 
 // Grid-wide barrier of a persistent launch whose CTAs are all co-resident (the dispatcher sizes the grid accordingly).
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
@@ -224,7 +228,7 @@ constexpr int kBuffers = 3;     // weight tiles a warp holds in registers (one b
 
 template <typename T, bool NESTED, bool COMPACT, bool TAIL, bool CHAIN>
 __global__ void __launch_bounds__(kMmaThreads, 2)
-gemv_mma_kernel(const __grid_constant__ MmaChainArgs c)
+gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChainArgs, MmaSingleArgs>::type c)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     // Shared-memory plan.  The PRMT splice needs the table at (64-KB aligned window address) + (compile-time immediate).
