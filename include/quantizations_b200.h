@@ -174,6 +174,15 @@ typedef struct q4_gemv_fused_t {
 } q4_gemv_fused_t;
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
 
+/* Small batch (2 <= tokens <= 16: speculative / multi-sequence decode) in ONE pass over the packed weight:
+ *     out[t, r] = sum_k x[t, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r])
+ * x [tokens, K], out [tokens, N] row-major contiguous, bias [N].  Runs the tcgen05 decode kernel with the N columns of the MMA as
+ * the tokens, so the cost is that of one GEMV pass whatever `tokens` is; needs the table image (`lut`) and the split-K workspace
+ * (see q4_gemv_fused_t), blocksize 64 and K % 256 == 0; Q4_ERR_SHAPE otherwise (callers then use q4_gemm_4bit). */
+int q4_gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
+                       int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
 /* `n` (<= 4) DEPENDENT decode GEMVs in one persistent launch: stage i+1 may consume what stage i produced (x / x_gate / bias of a
  * later stage pointing at the `out` of an earlier one), e.g. o_proj -> gate/up -> down_proj -> the next layer's q/k/v.  Between
  * stages the grid synchronises on a counter in `barrier_ws` (4 bytes of device memory, zero before the first call, left zero;

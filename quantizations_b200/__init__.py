@@ -13,6 +13,7 @@ from .core import (  # noqa: F401
     gemm_4bit,
     gemv_4bit_fused,
     gemv_4bit_chain,
+    gemv_4bit_batch,
     decode_attention,
     gemv_4bit,
     get_4bit_type,

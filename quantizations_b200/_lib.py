@@ -81,6 +81,7 @@ _SIGNATURES = {
     "q4_gemv_4bit_fused": [ctypes.POINTER(GemvFused), _vp],
     "q4_gemv_lut_build": [_vp, _vp, _i, _vp, _vp],
     "q4_gemv_4bit_chain": [ctypes.POINTER(GemvFused), _i, _vp, _vp],
+    "q4_gemv_4bit_batch": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _i64, _vp],
     "q4_decode_attention": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "q4_gemm_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
     "q4_gemv_4bit": [_vp, _vp, ctypes.POINTER(AbsmaxStats), _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],

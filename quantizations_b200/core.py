@@ -704,6 +704,29 @@ def gemv_4bit_fused(
     return out
 
 
+def gemv_4bit_batch(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                    flags: int = _lib.Q4_GEMV_DEFAULT) -> Tensor:
+    """2..16 tokens in ONE pass over the packed weight (include/quantizations_b200.h: q4_gemv_4bit_batch): out[.., t, n] =
+    sum_k A[.., t, k] * dequant(B)[n, k] (+ bias[n]).  Raises Q4Error when the shape is not supported by that kernel."""
+    N, K = state.shape[0], state.shape[1]
+    M = A.numel() // A.shape[-1]
+    if A.shape[-1] != K or not 1 <= M <= 16 or A.dtype not in (torch.float16, torch.bfloat16):
+        raise ValueError("gemv_4bit_batch needs 1..16 fp16/bf16 tokens of the weight's in_features")
+    A2 = A.reshape(M, K)
+    if not A2.is_contiguous():
+        A2 = A2.contiguous()
+    if out is None:
+        out = torch.empty(A.shape[:-1] + (N,), dtype=A.dtype, device=A.device)
+    ws = gemv_workspace(A.device)
+    rc = _lib.lib().q4_gemv_4bit_batch(A2.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
+                                       None if bias is None else bias.data_ptr(), out.data_ptr(), M, N, K, state.blocksize,
+                                       _DTYPE_CODE[A.dtype], flags, state.lut(A.dtype).data_ptr(), ws.data_ptr(), ws.numel(),
+                                       torch.cuda.current_stream(A.device).cuda_stream)
+    if rc:
+        check(rc, "gemv_4bit_batch")
+    return out
+
+
 _chain_barriers = {}
 
 

@@ -100,6 +100,7 @@ struct GemvPrologue {  // optional fused input transforms (16-bit activations on
     void* workspace = nullptr;  // split-K workspace of the tcgen05 kernel (zeroed once by the caller)
     int64_t workspace_bytes = 0;
     const q4_allreduce_t* ar = nullptr;  // fused all-reduce over tensor-parallel ranks
+    int tokens = 1;                      // > 1: small-batch call (x [tokens, K], out [tokens, N]): tcgen05 kernel only
 };
 
 template <typename K, typename... Args>
@@ -203,7 +204,10 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             const int rt_total = (int)((N + kTcRows - 1) / kTcRows);
             const int64_t U = (int64_t)rt_total * bpr;
             int grid = (int)(U / kTcGroups < sms ? U / kTcGroups : sms);
-            const size_t smem = (size_t)kLutBytes + (size_t)K * 2 + kTcXPad + 128 + (1 + 6 * kTcGroups) * 8 + 128;
+            const int tokens = pro->tokens;
+            const int mt = tokens > 1 ? 16 : 1;
+            const size_t smem = (size_t)kLutBytes + (mt == 1 ? (size_t)K * 2 + kTcXPad : (size_t)kTcGroups * kTcA * 2048) + 128 +
+                                (1 + 6 * kTcGroups) * 8 + 128;
             if (grid >= 1 && smem <= 226 * 1024) {
                 const int G2 = kTcGroups * grid;
                 auto run_of = [&](int64_t u) { return (int)(((u + 1) * G2 - 1) / U); };
@@ -215,7 +219,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                 // counters live in a FIXED region at the start (they must stay zero between launches of any shape), partials after it
                 const size_t cnt_bytes = 64 * 1024;
                 if ((size_t)rt_total * 4 > cnt_bytes) return Q4_ERR_SHAPE;
-                const size_t need = cnt_bytes + (size_t)rt_total * max_seg * kTcRows * 4;
+                const size_t need = cnt_bytes + (size_t)rt_total * max_seg * mt * kTcRows * 4;
                 if ((int64_t)need <= pro->workspace_bytes) {
                     const bool multi = nmat > 1 && nested;
                     TcGemvArgs a = {};
@@ -254,18 +258,23 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                     a.trace = g_gemv_trace;
                     static const int env_debug = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
                     a.debug = env_debug;
-                    auto kern = nested ? (multi ? gemv_tc_kernel<T, true, true> : gemv_tc_kernel<T, true, false>) : gemv_tc_kernel<T, false, false>;
-                    static bool attr_set[2][2] = {};
-                    if (!attr_set[nested][multi]) {
+                    a.tokens = tokens;
+                    if (mt > 1 && (multi || a.x_gate || a.rms_weight)) return Q4_ERR_SHAPE;
+                    auto kern = mt > 1 ? (nested ? gemv_tc_kernel<T, true, false, 16> : gemv_tc_kernel<T, false, false, 16>)
+                                       : (nested ? (multi ? gemv_tc_kernel<T, true, true, 1> : gemv_tc_kernel<T, true, false, 1>)
+                                                 : gemv_tc_kernel<T, false, false, 1>);
+                    static bool attr_set[2][2][2] = {};
+                    if (!attr_set[nested][multi][mt > 1]) {
                         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
                         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                         if (e != cudaSuccess) return (int)e;
-                        attr_set[nested][multi] = true;
+                        attr_set[nested][multi][mt > 1] = true;
                     }
                     return launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, stream, pdl, a);
                 }
             }
         }
+        if (pro && pro->tokens > 1) return Q4_ERR_SHAPE;  // small batches exist only on the tcgen05 kernel
         if (mma_ok) {
             const bool multi = nmat > 1 && nested;
             MmaGemvArgs a = {};
@@ -482,6 +491,33 @@ int gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, cuda
     for (int i = 0; i < n; i++)
         if (int rc = gemv_4bit_fused_impl(&stages[i], stream, nullptr)) return rc;
     return 0;
+}
+
+// 2..16 tokens in one pass over the packed weight (tcgen05 kernel, N columns of the MMA = tokens): x [tokens, K], out [tokens, N]
+int gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
+                    int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t stream)
+{
+    if (!valid_blocksize(blocksize)) return Q4_ERR_BLOCKSIZE;
+    if (N < 0 || K < 0 || (K & 1) || tokens < 1 || tokens > 16) return Q4_ERR_SHAPE;
+    if (N == 0) return 0;
+    if (!x || !B || !code || !out || !lut || !workspace) return Q4_ERR_NULL;
+    if (int e = check_stats(stats)) return e;
+    GemvPrologue pro;
+    pro.lut = lut;
+    pro.workspace = workspace;
+    pro.workspace_bytes = workspace_bytes;
+    pro.tokens = tokens;
+    flags &= ~Q4_GEMV_EXACT_F32;
+    switch (dtype) {
+        case Q4_F16:
+            return gemv_dispatch<__half>((const __half*)x, B, stats, code, (const __half*)bias, (__half*)out, N, K, blocksize, flags, nullptr,
+                                         0, stream, 1, nullptr, nullptr, &pro);
+        case Q4_BF16:
+            return gemv_dispatch<__nv_bfloat16>((const __nv_bfloat16*)x, B, stats, code, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, N, K,
+                                                blocksize, flags, nullptr, 0, stream, 1, nullptr, nullptr, &pro);
+        default: return Q4_ERR_DTYPE;
+    }
 }
 
 int gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, cudaStream_t stream)

@@ -62,6 +62,7 @@ struct TcGemvArgs {
     int* ws_count;   // workspace: [row tile] arrival counters (zero between launches)
     int max_seg;
     int rows, K;
+    int tokens;      // rows of x / out: 1 (decode GEMV) .. 16 (small batch: the N columns of the MMA are the tokens)
     int rt_total;    // ceil(rows / 128)
     unsigned long long* trace;
     int debug;       // developer experiments (env Q4_GEMV_DEBUG)
@@ -100,7 +101,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 
-template <typename T, bool NESTED, bool MULTI>
+// MT = 1: one activation vector, read in place through the overlapping descriptor (above).  MT = 16: up to 16 tokens -- x [tokens, K],
+// out [tokens, rows]; every warpgroup stages the 64 k of its current block for all tokens into a 2-KB shared-memory slot laid out
+// as the canonical K-major B tile ([8-element k chunk][token][16 B]: core-matrix rows = tokens), so column n of D is token n and one
+// pass over the packed weight serves the whole batch.
+template <typename T, bool NESTED, bool MULTI, int MT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemv_tc_kernel(const TcGemvArgs a)
 {
@@ -114,7 +119,7 @@ gemv_tc_kernel(const TcGemvArgs a)
     const uint32_t lut_saddr = 0;
     uint8_t* s_xb = smem + kLutBytes;
     uint4* s_x = reinterpret_cast<uint4*>(s_xb);
-    const int xbytes = K * 2 + kTcXPad;
+    const int xbytes = MT == 1 ? K * 2 + kTcXPad : kTcGroups * kTcA * 2048;  // MT > 1: per-warpgroup ring of B tiles
     float* s_red = reinterpret_cast<float*>(s_xb + xbytes);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 32);  // [0] table, [1 + wg*6 + s] full, [1 + wg*6 + 3 + s] done
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1 + 6 * kTcGroups);
@@ -216,7 +221,7 @@ gemv_tc_kernel(const TcGemvArgs a)
     // ---- everything below may read the previous kernel's output
     pdl_wait();
     tc_trace(a, 2);
-    {
+    if (MT == 1) {
         const int nchunk = K >> 3, npad = nchunk + kTcXPad / 16;
         if (a.x_gate || a.rms_weight) {
             stage_x_fused<T, false>(a.x, a.x_gate, a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, npad);
@@ -250,7 +255,8 @@ gemv_tc_kernel(const TcGemvArgs a)
     // instruction descriptor: D fp32, A/B fp16|bf16, K-major, N = 16, M = 128
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
     // B descriptor: K-major, no swizzle, leading (k-half) offset 16 B, stride (8-row group) offset 128 B, version 1
-    const uint64_t bdesc0 = ((uint64_t)1 << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    // (MT > 1: the real tile -- k-chunk stride 256 B, 8-token group stride 128 B)
+    const uint64_t bdesc0 = ((uint64_t)((MT == 1 ? 16 : 256) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint32_t x_saddr = (uint32_t)__cvta_generic_to_shared(s_xb);
     const uint32_t lane_base = lut_saddr | (uint32_t)(lane * 4);
     const uint32_t t_col = tmem_base + (uint32_t)(wg * 128);              // this warpgroup's columns, lane 0
@@ -258,7 +264,9 @@ gemv_tc_kernel(const TcGemvArgs a)
     int rt_st = u_lo / bpr, b_st = u_lo - rt_st * bpr;  // stage cursor
     int rt_acc = rt_st;                                 // row tile the accumulator belongs to
     int rt_epi = rt_st, b_epi = b_st;                   // epilogue cursor
-    float acc = 0.0f;
+    float acc[MT];
+#pragma unroll
+    for (int n = 0; n < MT; n++) acc[n] = 0.0f;
     float am_pend[3];
     // second-level absmax: one value per 256 consecutive blocks of the flattened weight, i.e. it changes at most once per
     // ~256 units of this thread's row -- fetched when the index moves, not per unit
@@ -270,11 +278,11 @@ gemv_tc_kernel(const TcGemvArgs a)
         const int nseg = run_of(rt * bpr + bpr - 1) - first + 1;
         const int row = rt * kTcRows + t;
         bool fin = true;
-        float total = acc;
+        float* part = a.ws_part + ((int64_t)rt * a.max_seg) * (MT * kTcRows);  // [segment][token][128 rows]
         if (nseg > 1) {
             const int seg = j_run - first;
-            float* part = a.ws_part + ((int64_t)rt * a.max_seg) * kTcRows;
-            __stcg(part + seg * kTcRows + t, acc);
+#pragma unroll
+            for (int n = 0; n < MT; n++) __stcg(part + (seg * MT + n) * kTcRows + t, acc[n]);
             __threadfence();
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
             if (t == 0) s_flag[wg] = atomicAdd(a.ws_count + rt, 1);
@@ -282,17 +290,27 @@ gemv_tc_kernel(const TcGemvArgs a)
             fin = s_flag[wg] == nseg - 1;
             if (fin) {  // last arriver: fixed-order sum of every run's partial
                 __threadfence();
-                total = 0.0f;
-                for (int s = 0; s < nseg; s++) total += __ldcg(part + s * kTcRows + t);
+#pragma unroll
+                for (int n = 0; n < MT; n++) {
+                    float total = 0.0f;
+                    for (int s = 0; s < nseg; s++) total += __ldcg(part + (s * MT + n) * kTcRows + t);
+                    acc[n] = total;
+                }
                 if (t == 0) a.ws_count[rt] = 0;
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");  // s_flag reusable
         }
         if (fin && row < R) {
-            T y = Elem<T>::from_f32(total);
             const T* bias = reinterpret_cast<const T*>(a.bias);
-            if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + Elem<T>::to_f32(bias[row]));  // torch `out += bias`
-            reinterpret_cast<T*>(a.out)[row] = y;
+            const float bv = bias ? Elem<T>::to_f32(bias[row]) : 0.0f;
+#pragma unroll
+            for (int n = 0; n < MT; n++) {
+                if (n < a.tokens) {
+                    T y = Elem<T>::from_f32(acc[n]);
+                    if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + bv);  // torch `out += bias`
+                    reinterpret_cast<T*>(a.out)[(size_t)n * R + row] = y;
+                }
+            }
         }
     };
 
@@ -305,14 +323,13 @@ gemv_tc_kernel(const TcGemvArgs a)
     // Nothing in a step waits for work issued in the same step.  Buffer reuse is safe by program order: every warp completed
     // the D read of unit i-2 (1.) before its arrival for unit i, and MMAs complete in issue order, so A(i-3) and D(i-2) are
     // free when the stores / MMAs of unit i start.
-    uint32_t d_pend = 0;
+    uint32_t d_pend[MT];
+#pragma unroll
+    for (int n = 0; n < MT; n++) d_pend[n] = 0;
     for (int base = 0; base <= n_units + 1; base += kTcUnroll) {  // two extra steps drain the pipeline
 #pragma unroll
         for (int k = 0; k < kTcUnroll; k++) {
             const int i = base + k;
-            const bool prof = (a.debug & 8) && a.trace && blockIdx.x == 0 && tid == (a.debug >> 8) && i < 10;
-            long long pm[7] = {0, 0, 0, 0, 0, 0, 0};
-            if (prof) pm[0] = clock64();
             if (i < n_units) {
                 // absmax of this unit (kept until its D column has been read, two steps later)
                 float am;
@@ -331,7 +348,12 @@ gemv_tc_kernel(const TcGemvArgs a)
                     am = __uint_as_float(aq[k % kTcU]);
                 }
                 am_pend[k % 3] = am;
-                if (prof) pm[1] = clock64();
+                uint4 xpiece = make_uint4(0, 0, 0, 0);
+                if (MT > 1) {  // this thread's 16 bytes of the block's B tile: k chunk t / 16 of token t % 16
+                    const int n = t & 15;
+                    if (n < a.tokens)
+                        xpiece = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.x) + (size_t)n * K + b_st * 64 + (t >> 4) * 8));
+                }
                 // 2. decode: 32 lookups -> 32 TMEM columns of this thread's lane (A buffer k % 3)
                 const uint32_t a_t = t_lane + (uint32_t)((k % kTcA) * 32);
 #pragma unroll
@@ -347,19 +369,24 @@ gemv_tc_kernel(const TcGemvArgs a)
                     }
                     tmem_st16(a_t + (uint32_t)(16 * h), v);
                 }
-                if (prof) pm[2] = clock64();
                 if (i >= 2 && i <= n_units + 1) {  // 1. unit i-2
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (rt_epi != rt_acc) {  // the run moved on to the next row tile
                         flush(rt_acc);
-                        acc = 0.0f;
+#pragma unroll
+                        for (int n = 0; n < MT; n++) acc[n] = 0.0f;
                         rt_acc = rt_epi;
                     }
-                    acc = fmaf(__uint_as_float(d_pend), am_pend[(k + kTcUnroll - 2) % kTcUnroll % 3], acc);
+#pragma unroll
+                    for (int n = 0; n < MT; n++) acc[n] = fmaf(__uint_as_float(d_pend[n]), am_pend[(k + kTcUnroll - 2) % kTcUnroll % 3], acc[n]);
                     if (++b_epi == bpr) {
                         b_epi = 0;
                         rt_epi++;
                     }
+                }
+                if (MT > 1) {
+                    *reinterpret_cast<uint4*>(s_xb + (wg * kTcA + (k % kTcA)) * 2048 + t * 16) = xpiece;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy store -> visible to the tensor core
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -377,7 +404,9 @@ gemv_tc_kernel(const TcGemvArgs a)
                         const uint32_t a_m = t_col + (uint32_t)((k % kTcA) * 32);
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            const uint64_t bdesc = bdesc0 | (uint64_t)(((x_saddr + (uint32_t)(b_st * 64 + q * 16) * 2u) & 0x3FFFFu) >> 4);
+                            const uint32_t b_saddr = MT == 1 ? x_saddr + (uint32_t)(b_st * 64 + q * 16) * 2u
+                                                             : x_saddr + (uint32_t)((wg * kTcA + (k % kTcA)) * 2048 + q * 512);
+                            const uint64_t bdesc = bdesc0 | (uint64_t)((b_saddr & 0x3FFFFu) >> 4);
                             asm volatile(
                                 "{\n"
                                 ".reg .pred p;\n"
@@ -392,11 +421,9 @@ gemv_tc_kernel(const TcGemvArgs a)
                     }
                 }
                 __syncwarp();
-                if (prof) pm[3] = clock64();
                 // 3.
                 if (i + kTcU < n_units) load_unit(k % kTcU);
                 if ((b_st & 3) == 0 && left_pf > 0) prefetch_line();
-                if (prof) pm[4] = clock64();
                 if (++b_st == bpr) {
                     b_st = 0;
                     rt_st++;
@@ -407,26 +434,34 @@ gemv_tc_kernel(const TcGemvArgs a)
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (rt_epi != rt_acc) {  // the run moved on to the next row tile
                         flush(rt_acc);
-                        acc = 0.0f;
+#pragma unroll
+                        for (int n = 0; n < MT; n++) acc[n] = 0.0f;
                         rt_acc = rt_epi;
                     }
-                    acc = fmaf(__uint_as_float(d_pend), am_pend[(k + kTcUnroll - 2) % kTcUnroll % 3], acc);
+#pragma unroll
+                    for (int n = 0; n < MT; n++) acc[n] = fmaf(__uint_as_float(d_pend[n]), am_pend[(k + kTcUnroll - 2) % kTcUnroll % 3], acc[n]);
                     if (++b_epi == bpr) {
                         b_epi = 0;
                         rt_epi++;
                     }
                 }
             }
-            if (prof) pm[5] = clock64();
             if (i >= 1 && i <= n_units) {  // 5. unit i-1
                 const int kp = (k + kTcUnroll - 1) % kTcUnroll;
                 tc_mbar_wait(bar_done0 + 8u * (kp % kTcA), (uint32_t)(((i - 1) / kTcA) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(d_pend) : "r"(t_lane + (uint32_t)(kTcA * 32 + (kp % kTcD) * 16)) : "memory");
-            }
-            if (prof) {
-                pm[6] = clock64();
-                for (int z = 0; z < 6; z++) a.trace[148 * 8 + i * 6 + z] = (unsigned long long)(pm[z + 1] - pm[z]);
+                const uint32_t d_addr = t_lane + (uint32_t)(kTcA * 32 + (kp % kTcD) * 16);
+                if constexpr (MT == 1) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(d_pend[0]) : "r"(d_addr) : "memory");
+                } else {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(d_pend[0]), "=r"(d_pend[1]), "=r"(d_pend[2]), "=r"(d_pend[3]), "=r"(d_pend[4]), "=r"(d_pend[5]), "=r"(d_pend[6]),
+                          "=r"(d_pend[7]), "=r"(d_pend[8]), "=r"(d_pend[9]), "=r"(d_pend[10]), "=r"(d_pend[11]), "=r"(d_pend[12]),
+                          "=r"(d_pend[13]), "=r"(d_pend[14]), "=r"(d_pend[15])
+                        : "r"(d_addr)
+                        : "memory");
+                }
             }
         }
     }

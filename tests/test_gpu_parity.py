@@ -600,3 +600,20 @@ def test_chained_gemvs_equal_separate_launches(q, dtype):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(h, hs) and torch.equal(out_qkv, qs)
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (1000, 512)])
+@pytest.mark.parametrize("M", [2, 7, 16])
+def test_small_batch_tcgen05_gemv_matches_per_token_gemv(q, shape, M):
+    """q4_gemv_4bit_batch (the tcgen05 decode kernel with the MMA's N columns as tokens): one pass over the packed weight for
+    2..16 tokens gives what the per-token decode GEMV gives, bias included, ragged last row tile included."""
+    N, K = shape
+    torch.manual_seed(17)
+    W = (torch.randn(N, K, device=DEV) * 0.02).to(torch.bfloat16)
+    packed, st = q.quantize_4bit(W, quant_type="nf4")
+    bias = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    x = torch.randn(1, M, K, device=DEV, dtype=torch.bfloat16)
+    y = q.gemv_4bit_batch(x, packed, st, bias=bias)
+    ref = torch.cat([q.gemv_4bit(x[:, m:m + 1], packed, state=st, bias=bias) for m in range(M)], dim=1)
+    assert y.shape == (1, M, N)
+    assert (y.float() - ref.float()).abs().max().item() <= 1e-2 * ref.float().abs().max().item()
