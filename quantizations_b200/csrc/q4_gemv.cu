@@ -367,6 +367,8 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             const size_t smem = (compact ? 1 : 2) * (size_t)kLutBytes + rest;
             if (smem > 226 * 1024) return Q4_ERR_SHAPE;
             const bool ktail = (K % 512) != 0 || (N % 8) != 0;
+            a.rt_q = a.rt_total / grid;
+            a.rt_r = a.rt_total % grid;
             MmaChainArgs c = {};
             c.st[0] = a;
             c.n = 1;
@@ -482,6 +484,10 @@ int gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, cuda
         }
         if (chain && any_ar && grid > kArMaxCtas) chain = false;
         if (chain) {
+            for (int i = 0; i < n; i++) {
+                c.st[i].rt_q = c.st[i].rt_total / grid;
+                c.st[i].rt_r = c.st[i].rt_total % grid;
+            }
             const bool pdl = stages[0].flags & Q4_GEMV_PDL;
             switch (stages[0].dtype) {
                 case Q4_F16: return launch_mma<__half>(c, st[0].nested, true, false, grid, smem, pdl, stream);

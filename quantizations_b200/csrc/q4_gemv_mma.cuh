@@ -71,6 +71,7 @@ struct MmaGemvArgs {
     long long pw_step, pw_wrap;
     int ab_step, ab_wrap, d_rt, d_kt;
     int multi;  // grouped launch with per-matrix offsets (nested statistics)
+    int rt_q, rt_r;  // rt_total / grid, rt_total % grid: CTA b owns row tiles [b*rt_q + min(b, rt_r), ...) -- no division on the device
 };
 
 // A launch runs `n` dependent GEMVs back to back ("chain": e.g. o_proj -> gate/up -> down_proj -> next layer's q/k/v): one
@@ -223,11 +224,15 @@ __device__ __noinline__ void stage_x_fused(const void* x, const void* x_gate, co
 }
 
 constexpr int kDynBase = 1024;  // where dynamic shared memory starts in the CTA's shared window on sm_100 (probed on the host)
+#ifdef Q4_MMA_THREADS
+constexpr int kMmaThreads = Q4_MMA_THREADS;
+#else
 constexpr int kMmaThreads = 256;
+#endif
 constexpr int kBuffers = 3;     // weight tiles a warp holds in registers (one being consumed, the others in flight)
 
 template <typename T, bool NESTED, bool COMPACT, bool TAIL, bool CHAIN>
-__global__ void __launch_bounds__(kMmaThreads, 2)
+__global__ void __launch_bounds__(kMmaThreads, 512 / kMmaThreads)
 gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChainArgs, MmaSingleArgs>::type c)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -266,6 +271,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
                          "l"(reinterpret_cast<const uint8_t*>(c.st[0].lut) + i * (kLutBytes / 4)), "r"(kLutBytes / 4), "r"(bar)
                          : "memory");
     }
+    mma_trace(c.st[0], 7);
     // ---- optional hint: this CTA's share of what the NEXT launch will stream, HBM -> L2 (TMA bulk prefetch, fire and forget)
     if (warp == nw - 1 && c.st[0].next_bytes > 0) {
         const int64_t share = ((c.st[0].next_bytes / gridDim.x) + 15) & ~(int64_t)15;
@@ -281,8 +287,9 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     const int K = a.K, R = a.rows, KT = a.kt;
     const int bpr = K >> 6;  // 64-wide blocks per row
     // this CTA's row tiles: a contiguous byte range of the packed weight and of the statistics
-    const int rt0 = (int)(((int64_t)blockIdx.x * a.rt_total) / gridDim.x);
-    const int rt1 = (int)(((int64_t)(blockIdx.x + 1) * a.rt_total) / gridDim.x);
+    const int bx = blockIdx.x;
+    const int rt0 = bx * a.rt_q + (bx < a.rt_r ? bx : a.rt_r);
+    const int rt1 = rt0 + a.rt_q + (bx < a.rt_r ? 1 : 0);
     const int ntiles = (rt1 - rt0) * KT;
     const int row_lo = rt0 * 8, row_hi = rt1 * 8 < R ? rt1 * 8 : R;
     const bool MULTI = a.multi != 0;
@@ -306,9 +313,14 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     // load cursor of the fast path: byte pointer of (row g of the row tile, block t4 of the k tile) and the block index of the
     // lane's absmax pair
     const int64_t row_bytes = (int64_t)bpr * 32;
-    const uint8_t* pw = a.Bq + ((int64_t)(rt0 + warp / KT) * 8 + g) * row_bytes + (int64_t)(warp % KT) * 256 + t4 * 32;
-    int ab = ((rt0 + warp / KT) * 8 + g) * bpr + (warp % KT) * 8 + 2 * t4;  // rows * bpr < 2^31: dispatcher
-    int kt_ld = warp % KT;
+    int w_rt = 0, w_kt = warp;  // warp / KT, warp % KT (warp < 8: a short subtraction loop instead of a division)
+    while (w_kt >= KT) {
+        w_kt -= KT;
+        w_rt++;
+    }
+    const uint8_t* pw = a.Bq + ((int64_t)(rt0 + w_rt) * 8 + g) * row_bytes + (int64_t)w_kt * 256 + t4 * 32;
+    int ab = ((rt0 + w_rt) * 8 + g) * bpr + w_kt * 8 + 2 * t4;  // rows * bpr < 2^31: dispatcher
+    int kt_ld = w_kt;
     auto issue = [&](TileRegs& r, const Cursor& c) {
         if (TAIL) {
             const int row = (rt0 + c.rt) * 8 + g;
@@ -371,7 +383,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     // ---- the first kBuffers tiles go into registers now: under programmatic dependent launch this happens while the previous
     //      kernel is still computing (weights do not depend on it), so a small matrix is entirely on chip before x exists
     TileRegs r0, r1, r2;
-    Cursor c0 = {warp, warp / KT, warp % KT};
+    Cursor c0 = {warp, w_rt, w_kt};
     Cursor c1 = after(c0), c2 = after(c1);
     if (c0.t < ntiles) issue(r0, c0);
     if (c1.t < ntiles) issue(r1, c1);

@@ -44,7 +44,7 @@ g.replay(); torch.cuda.synchronize()
 junk.fill_(2); torch.cuda.synchronize()
 g.replay(); torch.cuda.synchronize()
 L.q4_debug_set_gemv_trace(None)
-names = ["start", "issued", "waited", "x staged", "loop done", "end", "table ok"]
+names = ["start", "issued", "waited", "x staged", "loop done", "end", "table ok", "tma sent"]
 t0 = None
 for i, tr in enumerate(traces):
     print("   extra:", tr.cpu()[148 * 8:148 * 8 + 60].view(10, 6).tolist()) if i == NL - 1 else None
