@@ -158,6 +158,16 @@ __device__ __forceinline__ void mma_trace(const MmaGemvArgs& a, int slot)
     }
 }
 
+// developer trace, CTA 0 only: extra marks after the per-CTA slots (tools/gemv_trace.py prints them relative to mark 0)
+__device__ __forceinline__ void mma_trace_x(const MmaGemvArgs& a, int k)
+{
+    if (a.trace && threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[1024 * 8 + k] = t;  // the trace buffer holds 1024 CTAs x 8 slots, then the extras
+    }
+}
+
 struct TileRegs {
     u32x8 wa, wb;  // 32 packed bytes of (row g, block t) and of (row g, block 4 + t)
     uint32_t q;    // nested: two 8-bit absmax codes (blocks 2t, 2t+1 of the tile)
@@ -296,6 +306,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     float off[kMaxMats];
 #pragma unroll
     for (int m = 0; m < kMaxMats; m++) off[m] = (NESTED && (MULTI || m == 0) && a.offsets[m]) ? __ldg(a.offsets[m]) : 0.0f;
+    mma_trace_x(a, 0);
 
     // ---- tile bookkeeping: warp w takes tiles w, w + nw, ... of the CTA's (row tile, k tile) grid, k fastest
     // TAIL = false (K % 512 == 0 and rows % 8 == 0, every Llama shape): no bounds, no zero fill, and the load addresses advance
@@ -385,9 +396,12 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     TileRegs r0, r1, r2;
     Cursor c0 = {warp, w_rt, w_kt};
     Cursor c1 = after(c0), c2 = after(c1);
+    mma_trace_x(a, 1);
     if (c0.t < ntiles) issue(r0, c0);
+    mma_trace_x(a, 2);
     if (c1.t < ntiles) issue(r1, c1);
     if (c2.t < ntiles) issue(r2, c2);
+    mma_trace_x(a, 3);
     mma_trace(a, 1);
 
     // ---- everything below may read the previous kernel's (stage 0) or the previous stage's output

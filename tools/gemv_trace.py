@@ -17,7 +17,7 @@ mats = [packed.clone() for _ in range(8)]
 x = torch.randn(1, 1, K, device=dev, dtype=torch.bfloat16)
 out = torch.empty(1, 1, N, device=dev, dtype=torch.bfloat16)
 NL = 6
-traces = [torch.zeros(148 * 8 + 64, dtype=torch.int64, device=dev) for _ in range(NL)]
+traces = [torch.zeros(1024 * 8 + 64, dtype=torch.int64, device=dev) for _ in range(NL)]  # kernels write blockIdx * 8 + slot, extras after
 stream = torch.cuda.current_stream().cuda_stream
 lut = None if os.environ.get("NO_LUT") else st.lut(torch.bfloat16)
 stats = st.native_stats()
@@ -47,8 +47,11 @@ L.q4_debug_set_gemv_trace(None)
 names = ["start", "issued", "waited", "x staged", "loop done", "end", "table ok", "tma sent"]
 t0 = None
 for i, tr in enumerate(traces):
-    print("   extra:", tr.cpu()[148 * 8:148 * 8 + 60].view(10, 6).tolist()) if i == NL - 1 else None
-    t = tr.cpu()[:148 * 8].view(148, 8)
+    if i == NL - 1:
+        ex = tr.cpu()
+        print("   CTA 0 extra marks, us after its start:", [round((int(v) - int(ex[0])) / 1e3, 2) for v in ex[1024 * 8:1024 * 8 + 4]],
+              " tma sent", round((int(ex[7]) - int(ex[0])) / 1e3, 2), " issued", round((int(ex[1]) - int(ex[0])) / 1e3, 2))
+    t = tr.cpu()[:1024 * 8].view(1024, 8)
     t = t[t[:, 0] > 0]
     if t0 is None:
         t0 = int(t[:, 0].min())
