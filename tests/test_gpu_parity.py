@@ -617,3 +617,60 @@ def test_small_batch_tcgen05_gemv_matches_per_token_gemv(q, shape, M):
     ref = torch.cat([q.gemv_4bit(x[:, m:m + 1], packed, state=st, bias=bias) for m in range(M)], dim=1)
     assert y.shape == (1, M, N)
     assert (y.float() - ref.float()).abs().max().item() <= 1e-2 * ref.float().abs().max().item()
+
+
+def test_decode_kernels_do_not_write_outside_their_outputs(q):
+    """Guard bands around every output of the decode kernels (mma.sync GEMV incl. ragged shapes and grouped launch, tcgen05 GEMV
+    single / multi-token, chained launch, decode attention) must keep their sentinel after the calls."""
+    dt = torch.bfloat16
+    G = 256
+
+    def guarded(n):
+        buf = torch.full((n + 2 * G,), 7.75, device=DEV, dtype=dt)
+        return buf, buf[G:G + n]
+
+    def intact(buf, n):
+        return bool((buf[:G] == 7.75).all()) and bool((buf[G + n:] == 7.75).all())
+
+    torch.manual_seed(4)
+    for N, K in ((512, 1024), (1000, 640), (264, 256)):
+        lin = q.Linear4bit(K, N, bias=False, compute_dtype=dt, quant_type="nf4").to(DEV)
+        st = lin.weight.quant_state
+        x = torch.randn(1, 1, K, device=DEV, dtype=dt)
+        buf, out = guarded(N)
+        q.gemv_4bit(x, lin.weight.data, out=out.view(1, 1, N), state=st)
+        assert intact(buf, N) and torch.isfinite(out.float()).all()
+        if K % 256 == 0:
+            M = 5
+            buf, out = guarded(M * N)
+            q.gemv_4bit_batch(torch.randn(1, M, K, device=DEV, dtype=dt), lin.weight.data, st, out=out.view(1, M, N))
+            assert intact(buf, M * N) and torch.isfinite(out.float()).all()
+    H, I = 512, 1024
+    mk = lambda n, k: q.Linear4bit(k, n, bias=False, compute_dtype=dt, quant_type="nf4").to(DEV)
+    o, gate, up, down = mk(H, H), mk(I, H), mk(I, H), mk(H, I)
+    gu = q.Linear4bitGroup([gate, up])
+    ln = torch.ones(H, device=DEV, dtype=dt)
+    a = torch.randn(1, 1, H, device=DEV, dtype=dt)
+    bh, h = guarded(H)
+    bg, g_u = guarded(2 * I)
+    h.copy_(torch.randn(H, device=DEV, dtype=dt))
+    with q.gemv_4bit_chain() as ch:
+        ch.add(a, o.weight.data, o.weight.quant_state, residual=h.view(1, 1, H), out=h.view(1, 1, H))
+        ch.add(h.view(1, 1, H), None, group=gu, rms_weight=ln, out=g_u.view(1, 1, 2 * I))
+        ch.add(g_u.view(1, 1, 2 * I)[..., I:], down.weight.data, down.weight.quant_state, gate=g_u.view(1, 1, 2 * I)[..., :I],
+               residual=h.view(1, 1, H), out=h.view(1, 1, H))
+    torch.cuda.synchronize()
+    assert intact(bh, H) and intact(bg, 2 * I)
+    nh, nkv, hd, L = 4, 2, 128, 16
+    qkv_t = torch.randn(1, 1, (nh + 2 * nkv) * hd, device=DEV, dtype=dt)
+    cos, sin = torch.randn(L, hd // 2, device=DEV, dtype=dt), torch.randn(L, hd // 2, device=DEV, dtype=dt)
+    bk, kc = guarded(nkv * L * hd)
+    bv, vc = guarded(nkv * L * hd)
+    kc.zero_()
+    vc.zero_()
+    bo, ao = guarded(nh * hd)
+    for p in (0, 7, L - 1):
+        q.decode_attention(qkv_t, cos, sin, kc.view(nkv, L, hd), vc.view(nkv, L, hd), torch.tensor([p], device=DEV), nh, nkv,
+                           out=ao.view(1, 1, nh * hd))
+    torch.cuda.synchronize()
+    assert intact(bk, nkv * L * hd) and intact(bv, nkv * L * hd) and intact(bo, nh * hd)
