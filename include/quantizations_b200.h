@@ -104,8 +104,8 @@ int q4_dequantize_blockwise_4bit(const uint8_t* A, const q4_absmax_t* stats, voi
  * flags: Q4_GEMV_EXACT_F32 forces the fp32-multiply path (reference arithmetic for T=float) for any dtype;
  *        Q4_GEMV_PDL launches with programmatic stream serialization (the kernel's prologue -- table build, first
  *        weight loads, L2 prefetch -- overlaps the previous kernel's tail; x is read only after it has completed);
- *        Q4_GEMV_SHARE_SM sizes the CTAs to half an SM because an independent launch runs concurrently on another
- *        stream (q/k/v or gate/up of one layer): the two launches are then co-resident on every SM.
+ *        Q4_GEMV_SHARE_SM launches one half-SM CTA per SM instead of two, leaving half of every SM to an independent launch
+ *        running concurrently on another stream (or to the next launch's prologue).
  * prefetch / prefetch_bytes (optional, NULL / 0): a byte range that the NEXT call will stream (typically the packed
  * weight of the following Linear4bit).  It is pulled into the 126 MB L2 with TMA bulk prefetches while this call
  * computes, so HBM never idles between dependent launches.  Purely a hint: results do not depend on it. */

@@ -323,7 +323,6 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             a.rt_total = (int)((N + 7) / 8);
             a.kt = (int)((K + 511) / 512);
             constexpr int threads = kMmaThreads;
-            a.x_iters = (a.kt * 64 + threads - 1) / threads;
             {
                 const int nw = threads / 32, bpr_ = (int)(K / 64);
                 const long long row_bytes = (long long)bpr_ * 32;
@@ -349,7 +348,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             // leaving half of every SM to the next launch's prologue (1.37 vs 1.46 ms/step) -- the loop wants all 16 warps.  The rule
             // depends on the row count only, so tensor-parallel launches that share an exchange area keep one CTA -> rows mapping.
             static const int env_mult_raw = getenv("Q4_GEMV_GRID_MULT") ? atoi(getenv("Q4_GEMV_GRID_MULT")) : 0;
-            const int env_mult = env_mult_raw > 0 ? env_mult_raw : (a.rt_total >= 2 * sms ? 2 : 1);
+            const int env_mult = env_mult_raw > 0 ? env_mult_raw : ((flags & Q4_GEMV_SHARE_SM) ? 1 : (a.rt_total >= 2 * sms ? 2 : 1));
             // grid: one half-SM CTA per SM (the other half is for the next launch's prologue, see the kernel), or more when
             // the per-CTA partial-sum buffer would not fit
             const size_t tail = (size_t)a.kt * 1024 + 128 + 16;

@@ -61,7 +61,6 @@ struct MmaGemvArgs {
     int rows, K;
     int rt_total;  // ceil(rows / 8)
     int kt;        // ceil(K / 512): k tiles per row tile
-    int x_iters;   // ceil(kt * 64 / blockDim): 16-byte activation chunks per thread
     unsigned long long* trace;
     int debug;  // developer experiments (env Q4_GEMV_DEBUG)
     // fused one-shot all-reduce over tensor-parallel ranks (q4_allreduce_t), ar_world <= 1: off

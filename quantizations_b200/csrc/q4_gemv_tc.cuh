@@ -121,7 +121,7 @@ gemv_tc_kernel(const TcGemvArgs a)
     uint4* s_x = reinterpret_cast<uint4*>(s_xb);
     const int xbytes = MT == 1 ? K * 2 + kTcXPad : kTcGroups * kTcA * 2048;  // MT > 1: per-warpgroup ring of B tiles
     float* s_red = reinterpret_cast<float*>(s_xb + xbytes);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 32);  // [0] table, [1 + wg*6 + s] full, [1 + wg*6 + 3 + s] done
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 32);  // [0] table, [1 + wg*6 + 3 + s] done (the slots before are unused)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1 + 6 * kTcGroups);
     int* s_flag = reinterpret_cast<int*>(s_tmem + 1);            // [kTcGroups]
     int* s_cnt = s_flag + kTcGroups;                             // [kTcGroups][kTcA] arrival counters of the A buffers
@@ -130,7 +130,7 @@ gemv_tc_kernel(const TcGemvArgs a)
     const int wg = warp >> 2, wq4 = warp & 3;  // warpgroup, warp inside it (= TMEM lane quarter)
     const int t = tid & 127;                   // row inside the tile
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
-    const uint32_t bar_full0 = bar0 + 8u * (1 + wg * 6), bar_done0 = bar_full0 + 24u;
+    const uint32_t bar_done0 = bar0 + 8u * (1 + wg * 6 + 3);  // [1 + wg*6 + 3 + s]: MMA(unit) done, s = A buffer
 
     // unit runs: unit u = (row tile u / bpr, block u % bpr); run j = [j*U/G, (j+1)*U/G), j = 4*CTA + warpgroup
     const int64_t U = (int64_t)a.rt_total * bpr;
@@ -152,7 +152,6 @@ gemv_tc_kernel(const TcGemvArgs a)
             for (int g = 0; g < kTcGroups; g++)
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
-                    asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(bar0 + 8u * (1 + g * 6 + i)));      // full: one arrive per warp
                     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * (1 + g * 6 + 3 + i)));  // done: tcgen05.commit
                 }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
