@@ -57,6 +57,10 @@ for i, tr in enumerate(traces):
         t0 = int(t[:, 0].min())
     rel = (t - t0).float() / 1e3
     print(f"launch {i}: CTAs {t.shape[0]}")
+    if i == NL - 1 and t.shape[0] > 148:
+        lo, hi = rel[:148], rel[148:]
+        print(f"   first 148 CTAs: start {lo[:, 0].median():.2f} x-staged {lo[:, 3].median():.2f} end {lo[:, 5].median():.2f} (max {lo[:, 5].max():.2f})"
+              f" | rest: start {hi[:, 0].median():.2f} x-staged {hi[:, 3].median():.2f} end {hi[:, 5].median():.2f} (max {hi[:, 5].max():.2f})")
     for j, n in enumerate(names):
         col = rel[:, j]
         print(f"   {n:8s} min {col.min():8.2f}  median {col.median():8.2f}  max {col.max():8.2f} us")
