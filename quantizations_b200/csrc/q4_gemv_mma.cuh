@@ -167,6 +167,27 @@ __device__ __forceinline__ void mma_trace_x(const MmaGemvArgs& a, int k)
     }
 }
 
+__device__ __noinline__ void prefetch_next_share(const uint8_t* next, int64_t next_bytes, int lane)
+{
+    const int64_t share = ((next_bytes / gridDim.x) + 15) & ~(int64_t)15;
+    const int64_t lo = share * blockIdx.x;
+    const int64_t n = lo + share <= next_bytes ? share : next_bytes - lo;
+    if (n > 0) bulk_prefetch_l2_range(next + lo, n, lane);
+}
+
+// table built in the kernel (callers without a prebuilt image): out of line for the same reason
+template <typename T, bool NESTED>
+__device__ __noinline__ void build_lut_in_kernel(uint8_t* lut, const float* code, const float* code2)
+{
+    for (int c = threadIdx.x; c < kLutBytes / 16; c += blockDim.x) {
+        const int seg = c >> 3, b = seg >> 1;
+        uint32_t word;
+        if (seg & 1) word = NESTED ? __float_as_uint(__ldg(code2 + b)) : 0u;
+        else word = pack2<T>(__ldg(code + (b >> 4)), __ldg(code + (b & 15)));
+        *reinterpret_cast<uint4*>(lut + c * 16) = make_uint4(word, word, word, word);
+    }
+}
+
 struct TileRegs {
     u32x8 wa, wb;  // 32 packed bytes of (row g, block t) and of (row g, block 4 + t)
     uint32_t q;    // nested: two 8-bit absmax codes (blocks 2t, 2t+1 of the tile)
@@ -281,13 +302,9 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
                          : "memory");
     }
     mma_trace(c.st[0], 7);
-    // ---- optional hint: this CTA's share of what the NEXT launch will stream, HBM -> L2 (TMA bulk prefetch, fire and forget)
-    if (warp == nw - 1 && c.st[0].next_bytes > 0) {
-        const int64_t share = ((c.st[0].next_bytes / gridDim.x) + 15) & ~(int64_t)15;
-        const int64_t lo = share * blockIdx.x;
-        const int64_t n = lo + share <= c.st[0].next_bytes ? share : c.st[0].next_bytes - lo;
-        if (n > 0) bulk_prefetch_l2_range(c.st[0].next + lo, n, lane);
-    }
+    // ---- optional hint: this CTA's share of what the NEXT launch will stream, HBM -> L2 (out of line: rarely used, and the cold
+    //      start of a CTA is on the critical path of a launch chain -- the straight-line prologue should be short)
+    if (warp == nw - 1 && c.st[0].next_bytes > 0) prefetch_next_share(c.st[0].next, c.st[0].next_bytes, lane);
 
   // CHAIN = false: exactly one stage, every argument a compile-time offset into the parameter bank (no indexed constant loads
   // in the loop); CHAIN = true: c.n stages, arguments indexed by the stage.
@@ -381,15 +398,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
         }
     };
 
-    if (stage == 0 && !a.lut) {  // fallback: build the table here (callers without a prebuilt image)
-        for (int c = tid; c < kLutBytes / 16; c += nthr) {
-            const int seg = c >> 3, b = seg >> 1;
-            uint32_t word;
-            if (seg & 1) word = NESTED ? __float_as_uint(__ldg(a.s.code2 + b)) : 0u;
-            else word = pack2<T>(__ldg(a.code + (b >> 4)), __ldg(a.code + (b & 15)));
-            *reinterpret_cast<uint4*>(lut + c * 16) = make_uint4(word, word, word, word);
-        }
-    }
+    if (stage == 0 && !a.lut) build_lut_in_kernel<T, NESTED>(lut, a.code, a.s.code2);  // callers without a prebuilt image
     // ---- the first kBuffers tiles go into registers now: under programmatic dependent launch this happens while the previous
     //      kernel is still computing (weights do not depend on it), so a small matrix is entirely on chip before x exists
     TileRegs r0, r1, r2;
