@@ -217,7 +217,9 @@ __device__ __noinline__ void stage_x_fused(const void* x, const void* x_gate, co
 #pragma unroll
                 for (int q2 = 0; q2 < 4; q2++) {
                     const float2 gg = unpack2<T>(gw[q2]), u = unpack2<T>(uw[q2]);
-                    const float2 sg = unpack2<T>(pack2<T>(gg.x / (1.0f + expf(-gg.x)), gg.y / (1.0f + expf(-gg.y))));
+                    // every CTA recomputes the whole vector: the fast exp / divide (~1e-6 relative, far below the rounding to T)
+                    // instead of the IEEE ones take this from ~5 us to ~1.5 us per launch on a 14336-wide input
+                    const float2 sg = unpack2<T>(pack2<T>(__fdividef(gg.x, 1.0f + __expf(-gg.x)), __fdividef(gg.y, 1.0f + __expf(-gg.y))));
                     uw[q2] = pack2<T>(sg.x * u.x, sg.y * u.y);
                 }
                 v = make_uint4(uw[0], uw[1], uw[2], uw[3]);

@@ -110,11 +110,13 @@ class Llama(nn.Module):
         T == 1 is the decode step (static shapes: capturable in a CUDA graph with device-resident `tokens` / `pos`)."""
         cfg, T = self.cfg, tokens.shape[0]
         x = self.embed.index_select(0, tokens).unsqueeze(0)                 # [1, T, h]
-        cos, sin = self.cos.index_select(0, pos), self.sin.index_select(0, pos)
-        # causal mask over the whole static cache: key j visible to query i iff j <= pos[i]
-        mask = self.positions[None, :] <= pos[:, None]                      # [T, max_len]
-        if (T == 1 and self.chain and self.fuse_glue and self.fuse_attn and all(L.qkv is not None for L in self.layers)
-                and (self.tp == 1 or self.fused_ar is not None)):
+        all_fused = (T == 1 and self.fuse_glue and self.fuse_attn and all(L.qkv is not None for L in self.layers)
+                     and (self.tp == 1 or self.fused_ar is not None))
+        if not all_fused:  # the fused decode step reads cos / sin / cache positions inside q4_decode_attention
+            cos, sin = self.cos.index_select(0, pos), self.sin.index_select(0, pos)
+            # causal mask over the whole static cache: key j visible to query i iff j <= pos[i]
+            mask = self.positions[None, :] <= pos[:, None]                  # [T, max_len]
+        if all_fused and self.chain:
             return self._decode_chained(x, pos)
         for li, L in enumerate(self.layers):
             fused = L.qkv is not None and T == 1 and self.fuse_glue
