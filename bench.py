@@ -231,16 +231,17 @@ def run_ours(args, rank, world, device):
             out = outs[(m.name_, m.out_features)]
             nxt = packed_of(units[(i + 1) % len(units)]) if args.prefetch else None  # the following launch's packed weight
             npt, nby = (None, 0) if nxt is None else (nxt.data_ptr(), nxt.numel())
+            nk = units[(i + 1) % len(units)].in_features if args.prefetch else 0  # exact hint: the next launch's in_features
             if isinstance(m, q.Linear4bitGroup):
                 f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.packed.data_ptr(), ctypes.pointer(m._stats), m._offsets,
                                    m._row_end, len(m.splits), m.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, 64,
-                                   _lib.Q4_BF16, flags, npt, nby, m.lut(dtype).data_ptr(), ws_ptr, ws_bytes)
+                                   _lib.Q4_BF16, flags, npt, nby, m.lut(dtype).data_ptr(), ws_ptr, ws_bytes, prefetch_K=nk)
             else:
                 st = m.weight.quant_state
                 ar = ctypes.pointer(fused_ar.struct) if (fused_ar is not None and m.parallel == "row") else None
                 f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.weight.data_ptr(), ctypes.pointer(st.native_stats()), None,
                                    None, 1, st.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, st.blocksize,
-                                   _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr(), ws_ptr, ws_bytes, ar)
+                                   _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr(), ws_ptr, ws_bytes, ar, nk)
             fused_args[key] = f
         return f
 
@@ -341,7 +342,7 @@ def run_ours(args, rank, world, device):
 
     def launch_api(i, m, flags):
         m.gemv_flags = flags
-        m.prefetch_next = packed_of(units[(i + 1) % len(units)]) if args.prefetch else None
+        m.prefetch_next = (packed_of(units[(i + 1) % len(units)]), units[(i + 1) % len(units)].in_features) if args.prefetch else None
         if fused_ar is not None and m.parallel == "row":
             y = q.gemv_4bit_fused(x_static[m.in_features], m.weight.data, m.weight.quant_state, flags=flags, allreduce=fused_ar)
         else:

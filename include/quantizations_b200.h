@@ -171,6 +171,9 @@ typedef struct q4_gemv_fused_t {
                       * through the workspace in a fixed order; it leaves the workspace zeroed); without, the mma.sync kernel. */
     int64_t workspace_bytes;
     const q4_allreduce_t* allreduce; /* optional: sum the output over tensor-parallel ranks in the epilogue (see q4_allreduce_t) */
+    int64_t prefetch_K; /* optional (0 = unknown): in_features of the weight behind `prefetch`.  With it the hint becomes exact: only
+                         * the first tiles every CTA of the NEXT launch will ask for (what it keeps in registers before its
+                         * activation exists, ~14 MB over the grid) are pulled into L2 instead of the whole range. */
 } q4_gemv_fused_t;
 int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
 

@@ -190,7 +190,11 @@ unsigned char q4o_quantize_8bit(const float* code, float x)
 static float block_absmax(const float* a, long valid, int blocksize)
 {
     float m = -FLT_MAX;
-    for (long j = 0; j < valid; j++) m = fmaxf(m, fabsf(a[j]));
+    /* the device's fmaxf returns the other operand for ANY NaN; glibc's propagates signalling NaNs, so spell it out */
+    for (long j = 0; j < valid; j++) {
+        const float v = fabsf(a[j]);
+        if (v == v) m = fmaxf(m, v);
+    }
     if (valid < blocksize) m = fmaxf(m, 0.0f);
     return m;
 }

@@ -59,7 +59,7 @@ class GemvFused(ctypes.Structure):
         ("out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("K", ctypes.c_int64), ("blocksize", ctypes.c_int),
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("prefetch", ctypes.c_void_p), ("prefetch_bytes", ctypes.c_int64),
         ("lut", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
-        ("allreduce", ctypes.POINTER(AllReduce)),
+        ("allreduce", ctypes.POINTER(AllReduce)), ("prefetch_K", ctypes.c_int64),
     ]  # fmt: skip
 
 

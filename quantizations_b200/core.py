@@ -477,6 +477,9 @@ def gemv_4bit(
     `prefetch` (optional) is a tensor the next call will stream -- usually the packed weight of the following layer; it is
     pulled into L2 while this call computes (a hint only, see include/quantizations_b200.h).
     """
+    prefetch_k = 0
+    if isinstance(prefetch, tuple):  # (packed weight of the next call, its in_features): the exact form of the hint
+        prefetch, prefetch_k = prefetch
     if state is None:
         raise ValueError("state cannot None. gem_4bit( ) requires the state from quantize_4bit( )")
     if A.numel() != A.shape[-1]:
@@ -504,7 +507,7 @@ def gemv_4bit(
             A.data_ptr(), None, None, 0.0, B.data_ptr(), ctypes.pointer(state.native_stats()), None, None, 1, state.code.data_ptr(),
             None if bias is None else bias.data_ptr(), out.data_ptr(), bout, k, state.blocksize, _DTYPE_CODE[A.dtype], flags,
             None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
-            state.lut(A.dtype).data_ptr(), *_ws_args(A.device),
+            state.lut(A.dtype).data_ptr(), *_ws_args(A.device), None, int(prefetch_k),
         )
         rc = lib.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
         if rc != 0:
@@ -663,6 +666,9 @@ def gemv_4bit_fused(
     `group` (a Linear4bitGroup) runs the grouped launch over its members instead of a single (B, state).
     `allreduce` (a tp.FusedAllReduce) sums the output over the tensor-parallel ranks inside the kernel's epilogue, before the
     residual is added: the row-parallel layers' all-reduce without a collective call."""
+    prefetch_k = 0
+    if isinstance(prefetch, tuple):  # (packed weight of the next launch, its in_features): the exact form of the hint
+        prefetch, prefetch_k = prefetch
     if A.numel() != A.shape[-1]:
         raise ValueError("gemv_4bit_fused needs a single activation vector")
     if A.dtype not in (torch.float16, torch.bfloat16):
@@ -693,7 +699,7 @@ def gemv_4bit_fused(
         packed.data_ptr(), ctypes.pointer(stats), offsets, row_end, nmat, code.data_ptr(),
         None if residual is None else residual.data_ptr(), out.data_ptr(), rows, K, blocksize, _DTYPE_CODE[A.dtype], flags,
         None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
-        lut.data_ptr(), *_ws_args(A.device), None if allreduce is None else ctypes.pointer(allreduce.struct),
+        lut.data_ptr(), *_ws_args(A.device), None if allreduce is None else ctypes.pointer(allreduce.struct), int(prefetch_k),
     )
     if _defer is not None:  # gemv_4bit_chain collects the stage instead of launching it
         _defer.append((f, (A, gate, rms_weight, residual, out, lut, stats)))

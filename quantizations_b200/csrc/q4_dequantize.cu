@@ -7,8 +7,8 @@
 // 1/2 + 1/bs bytes and writes sizeof(T).
 //
 // Design: a thread owns 8 consecutive outputs = one 32-bit packed word, so a warp reads 128 contiguous bytes and
-// writes 512 (16-bit) or 1024 (fp32) contiguous bytes per step with 128-bit stores; four independent steps are in
-// flight per thread.  The 16-entry decode table is staged in shared memory (one word per bank: conflict-free).
+// writes 512 (16-bit) or 1024 (fp32) contiguous bytes per step with 128-bit stores; eight independent steps are in
+// flight per thread.  The 16-entry decode table and the 8-bit absmax map are staged in shared memory.
 #include "q4_common.cuh"
 #include "q4_launch.h"
 
@@ -37,46 +37,74 @@ template <typename T, int QT, bool NESTED>
 __global__ void __launch_bounds__(256)
 dequantize_4bit_kernel(const uint8_t* __restrict__ A, AbsmaxView s, T* __restrict__ out, int bs_shift, int64_t n)
 {
-    constexpr int STEPS = 4;
+    constexpr int STEPS = 8;  // independent 128-byte reads / 512-byte (16-bit) writes per warp in flight
     __shared__ float s_table[16];
+    __shared__ float s_code2[NESTED ? 256 : 1];
     if (threadIdx.x < 16) s_table[threadIdx.x] = QT == Q4_NF4 ? kNf4Decode[threadIdx.x] : kFp4Decode[threadIdx.x];
-    __syncthreads();
-    const float offset = NESTED ? __ldg(s.offset) : 0.0f;
+    if (NESTED) s_code2[threadIdx.x] = __ldg(s.code2 + threadIdx.x);  // 8-bit absmax map: a lookup that depends on a loaded byte
+    const float offset = NESTED ? __ldg(s.offset) : 0.0f;              // should not be a second trip to L2
     const int64_t ngroups = (n + 7) >> 3;  // 8-element groups
     const int64_t g0 = (int64_t)blockIdx.x * (256 * STEPS) + threadIdx.x;
+    const bool whole = ((int64_t)(blockIdx.x + 1) * (256 * STEPS)) * 8 <= n;  // CTA-uniform: no bounds, no ragged group
 
     uint32_t word[STEPS];
-    float am[STEPS];
+    float am[STEPS];   // nested: second-level absmax until decoded
+    uint32_t q[STEPS];
+    if (whole) {
 #pragma unroll
-    for (int i = 0; i < STEPS; i++) {
-        const int64_t g = g0 + i * 256;
-        word[i] = 0;
-        am[i] = 0.0f;
-        if (g < ngroups) {
-            const int64_t e0 = g << 3;
-            if (e0 + 8 <= n) {
-                word[i] = ldg_stream_32(A + (e0 >> 1));
-            } else {  // ragged tail: (n+1)/2 bytes exist
-                const int64_t nbytes = (n + 1) >> 1;
-                for (int j = 0; j < 4; j++)
-                    if ((e0 >> 1) + j < nbytes) word[i] |= (uint32_t)A[(e0 >> 1) + j] << (8 * j);
+        for (int i = 0; i < STEPS; i++) {
+            const int64_t e0 = (g0 + i * 256) << 3;
+            word[i] = ldg_stream_32(A + (e0 >> 1));
+            const int64_t b = e0 >> bs_shift;
+            if (NESTED) {
+                q[i] = __ldg(s.qabsmax + b);
+                am[i] = __ldg(s.absmax2 + (b >> s.shift2));
+            } else {
+                am[i] = __ldg(s.absmax + b);
             }
-            am[i] = load_absmax<NESTED>(s, e0 >> bs_shift, offset);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < STEPS; i++) {
+            const int64_t g = g0 + i * 256;
+            word[i] = 0;
+            am[i] = 0.0f;
+            q[i] = 0;
+            if (g < ngroups) {
+                const int64_t e0 = g << 3;
+                if (e0 + 8 <= n) {
+                    word[i] = ldg_stream_32(A + (e0 >> 1));
+                } else {  // ragged tail: (n+1)/2 bytes exist
+                    const int64_t nbytes = (n + 1) >> 1;
+                    for (int j = 0; j < 4; j++)
+                        if ((e0 >> 1) + j < nbytes) word[i] |= (uint32_t)A[(e0 >> 1) + j] << (8 * j);
+                }
+                const int64_t b = e0 >> bs_shift;
+                if (NESTED) {
+                    q[i] = __ldg(s.qabsmax + b);
+                    am[i] = __ldg(s.absmax2 + (b >> s.shift2));
+                } else {
+                    am[i] = __ldg(s.absmax + b);
+                }
+            }
         }
     }
+    __syncthreads();  // tables staged (the loads above are already in flight)
 #pragma unroll
     for (int i = 0; i < STEPS; i++) {
         const int64_t g = g0 + i * 256;
-        if (g >= ngroups) continue;
+        if (!whole && g >= ngroups) continue;
         const int64_t e0 = g << 3;
+        // nested: one fp32 multiply (kernels.cu:552) then one fp32 add (core.py:615), never an FMA
+        const float a = NESTED ? __fadd_rn(__fmul_rn(s_code2[q[i]], am[i]), offset) : am[i];
         float v[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t byte = (word[i] >> (8 * j)) & 0xFFu;
-            v[2 * j] = decode_nibble(s_table, byte >> 4, am[i]);
-            v[2 * j + 1] = decode_nibble(s_table, byte & 0xFu, am[i]);
+            v[2 * j] = decode_nibble(s_table, byte >> 4, a);
+            v[2 * j + 1] = decode_nibble(s_table, byte & 0xFu, a);
         }
-        if (e0 + 8 <= n) {
+        if (whole || e0 + 8 <= n) {
             store8<T>(out + e0, v);
         } else {
             for (int j = 0; j < 8; j++)
@@ -115,7 +143,7 @@ static int launch_dequantize_4bit(const uint8_t* A, const q4_absmax_t* st, T* ou
     const AbsmaxView v = make_view(st);
     const int shift = ilog2(blocksize);
     const int64_t ngroups = (n + 7) / 8;
-    const unsigned grid = (unsigned)((ngroups + 1023) / 1024);
+    const unsigned grid = (unsigned)((ngroups + 2047) / 2048);
     const bool nested = st->qabsmax != nullptr;
     if (quant_type == Q4_FP4) {
         if (nested) dequantize_4bit_kernel<T, Q4_FP4, true><<<grid, 256, 0, stream>>>(A, v, out, shift, n);

@@ -28,6 +28,7 @@ namespace q4 {
 // ------------------------------------------------------------------------------------------------ fast path
 
 unsigned long long* g_gemv_trace = nullptr;  // set by q4_debug_set_gemv_trace (developer tool, not part of the ABI)
+constexpr int kDefaultGridRule = 0;          // default of Q4_GEMV_GRID (see gemv_dispatch)
 
 // ------------------------------------------------------------------------------------------------ generic path
 
@@ -101,6 +102,7 @@ struct GemvPrologue {  // optional fused input transforms (16-bit activations on
     int64_t workspace_bytes = 0;
     const q4_allreduce_t* ar = nullptr;  // fused all-reduce over tensor-parallel ranks
     int tokens = 1;                      // > 1: small-batch call (x [tokens, K], out [tokens, N]): tcgen05 kernel only
+    int64_t next_K = 0;                  // in_features of the weight behind the prefetch hint (0: unknown)
 };
 
 template <typename K, typename... Args>
@@ -348,18 +350,50 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             // leaving half of every SM to the next launch's prologue (1.37 vs 1.46 ms/step) -- the loop wants all 16 warps.  The rule
             // depends on the row count only, so tensor-parallel launches that share an exchange area keep one CTA -> rows mapping.
             static const int env_mult_raw = getenv("Q4_GEMV_GRID_MULT") ? atoi(getenv("Q4_GEMV_GRID_MULT")) : 0;
-            const int env_mult = env_mult_raw > 0 ? env_mult_raw : ((flags & Q4_GEMV_SHARE_SM) ? 1 : (a.rt_total >= 2 * sms ? 2 : 1));
-            // grid: one half-SM CTA per SM (the other half is for the next launch's prologue, see the kernel), or more when
-            // the per-CTA partial-sum buffer would not fit
+            // Balanced grid (Q4_GEMV_GRID=1): the SMALLEST grid with the same ceil(rt_total / grid) leaves CTA slots to the next
+            // launch of a decode chain.  Measured SLOWER than filling every slot (1.35 vs 1.30 ms/step: the loop wants all 16 warps of
+            // every SM), so the plain rule stays the default.  Q4_GEMV_GRID: 0 = plain rule, 1 = balanced, n > 1 = exactly n CTAs.
+            static const int env_grid = getenv("Q4_GEMV_GRID") ? atoi(getenv("Q4_GEMV_GRID")) : kDefaultGridRule;
+            // The rule depends on the shape only (tensor parallel: one CTA -> rows mapping per exchange area; the prefetch hint: this
+            // launch must know how the NEXT one will split its rows).
+            auto plan_grid = [&](int rt_total, int kt) {
+                const int mult = env_mult_raw > 0 ? env_mult_raw : ((flags & Q4_GEMV_SHARE_SM) ? 1 : (rt_total >= 2 * sms ? 2 : 1));
+                // grid: two half-SM CTAs per SM (or one, leaving the other half to the next launch's prologue, see the kernel), or more
+                // when the per-CTA partial-sum buffer would not fit
+                const size_t tail = (size_t)kt * 1024 + 128 + 16;
+                const int cap_ctas = sms * mult;
+                int grid = rt_total < cap_ctas ? rt_total : cap_ctas;
+                for (;;) {
+                    const size_t part = (size_t)((rt_total + grid - 1) / grid) * kt * 32;
+                    if (kLutBytes + tail + part <= 100 * 1024 || 2 * (size_t)kLutBytes + tail + part <= 200 * 1024 || grid >= rt_total) break;
+                    grid += sms;
+                }
+                if (grid > rt_total) grid = rt_total;
+                if (env_grid == 1) {
+                    const int per = (rt_total + grid - 1) / grid;
+                    grid = (rt_total + per - 1) / per;
+                } else if (env_grid > 1 && env_grid <= grid) {
+                    const size_t part = (size_t)((rt_total + env_grid - 1) / env_grid) * kt * 32;
+                    if (kLutBytes + tail + part <= 100 * 1024) grid = env_grid;
+                }
+                return grid;
+            };
             const size_t tail = (size_t)a.kt * 1024 + 128 + 16;
-            const int cap_ctas = sms * (env_mult > 0 ? env_mult : 1);
-            int grid = a.rt_total < cap_ctas ? a.rt_total : cap_ctas;
-            for (;;) {
-                const size_t part = (size_t)((a.rt_total + grid - 1) / grid) * a.kt * 32;
-                if (kLutBytes + tail + part <= 100 * 1024 || 2 * (size_t)kLutBytes + tail + part <= 200 * 1024 || grid >= a.rt_total) break;
-                grid += sms;
+            const int grid = plan_grid(a.rt_total, a.kt);
+            // exact prefetch hint: how the next launch will split ITS rows, and how many row tiles each of its CTAs loads before its
+            // activation exists (kBuffers tiles per warp, k fastest: ceil(kBuffers * warps / kt) row tiles)
+            if (a.next && pro && pro->next_K >= 512 && (pro->next_K % 512) == 0 && a.next_bytes % (pro->next_K * 4) == 0) {
+                const int64_t nK = pro->next_K, nrows = a.next_bytes * 2 / nK;
+                const int nkt = (int)(nK / 512), nrt = (int)(nrows / 8);
+                if (nrt > 0 && nK <= 32768) {
+                    const int ngrid = plan_grid(nrt, nkt);
+                    a.nx_grid = ngrid;
+                    a.nx_rt_q = nrt / ngrid;
+                    a.nx_rt_r = nrt % ngrid;
+                    a.nx_head = (kBuffers * (kMmaThreads / 32) + nkt - 1) / nkt;
+                    a.nx_tile_bytes = 4 * nK;  // 8 rows x K/2 bytes
+                }
             }
-            if (grid > a.rt_total) grid = a.rt_total;
             if (a.ar_world > 1 && grid > kArMaxCtas) return Q4_ERR_SHAPE;
             const size_t rest = tail + (size_t)((a.rt_total + grid - 1) / grid) * a.kt * 32;
             const bool compact = dyn_base == kDynBase && !env_aligned && kLutBytes + rest <= 220 * 1024;
@@ -414,6 +448,7 @@ static int gemv_4bit_fused_impl(const q4_gemv_fused_t* f, cudaStream_t stream, M
     pro.workspace = f->workspace;
     pro.workspace_bytes = f->workspace_bytes;
     pro.ar = f->allreduce;
+    pro.next_K = f->prefetch_K;
     const int flags = f->flags & ~Q4_GEMV_EXACT_F32;
     switch (f->dtype) {
         case Q4_F16:

@@ -71,6 +71,10 @@ struct MmaGemvArgs {
     int ab_step, ab_wrap, d_rt, d_kt;
     int multi;  // grouped launch with per-matrix offsets (nested statistics)
     int rt_q, rt_r;  // rt_total / grid, rt_total % grid: CTA b owns row tiles [b*rt_q + min(b, rt_r), ...) -- no division on the device
+    // exact prefetch hint (nx_grid > 0): the NEXT launch runs nx_grid CTAs over `next`, CTA j owning row tiles
+    // [j*nx_rt_q + min(j, nx_rt_r), ...) of nx_tile_bytes each and loading the first nx_head of them before its activation exists
+    int nx_grid, nx_rt_q, nx_rt_r, nx_head;
+    long long nx_tile_bytes;
 };
 
 // A launch runs `n` dependent GEMVs back to back ("chain": e.g. o_proj -> gate/up -> down_proj -> next layer's q/k/v): one
@@ -173,6 +177,20 @@ __device__ __noinline__ void prefetch_next_share(const uint8_t* next, int64_t ne
     const int64_t lo = share * blockIdx.x;
     const int64_t n = lo + share <= next_bytes ? share : next_bytes - lo;
     if (n > 0) bulk_prefetch_l2_range(next + lo, n, lane);
+}
+
+// Exact form of the hint: only the head of every next-launch CTA's share -- the tiles it will load into registers during its cold
+// start, ~14 MB over the grid -- goes HBM -> L2.  Measured on the Llama-3-8B stack (1.305 ms/step without a hint): issued in the
+// CTA's first instructions 1.287 ms, after its loop 1.312 ms, right after griddepcontrol.wait 1.357 ms.
+__device__ __noinline__ void prefetch_next_heads(const uint8_t* next, int nx_grid, int nx_rt_q, int nx_rt_r, int nx_head,
+                                                 long long nx_tile_bytes, int lane)
+{
+    for (int j = blockIdx.x; j < nx_grid; j += gridDim.x) {
+        const int rt0 = j * nx_rt_q + (j < nx_rt_r ? j : nx_rt_r);
+        const int nrt = nx_rt_q + (j < nx_rt_r ? 1 : 0);
+        const int head = nrt < nx_head ? nrt : nx_head;
+        bulk_prefetch_l2_range(next + (int64_t)rt0 * nx_tile_bytes, (int64_t)head * nx_tile_bytes, lane);
+    }
 }
 
 // table built in the kernel (callers without a prebuilt image): out of line for the same reason
@@ -306,7 +324,10 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     mma_trace(c.st[0], 7);
     // ---- optional hint: this CTA's share of what the NEXT launch will stream, HBM -> L2 (out of line: rarely used, and the cold
     //      start of a CTA is on the critical path of a launch chain -- the straight-line prologue should be short)
-    if (warp == nw - 1 && c.st[0].next_bytes > 0) prefetch_next_share(c.st[0].next, c.st[0].next_bytes, lane);
+    if (warp == nw - 1 && c.st[0].next_bytes > 0) {
+        if (c.st[0].nx_grid == 0) prefetch_next_share(c.st[0].next, c.st[0].next_bytes, lane);
+        else prefetch_next_heads(c.st[0].next, c.st[0].nx_grid, c.st[0].nx_rt_q, c.st[0].nx_rt_r, c.st[0].nx_head, c.st[0].nx_tile_bytes, lane);
+    }
 
   // CHAIN = false: exactly one stage, every argument a compile-time offset into the parameter bank (no indexed constant loads
   // in the loop); CHAIN = true: c.n stages, arguments indexed by the stage.
@@ -418,6 +439,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     if (!CHAIN || stage == 0) pdl_wait();
     else grid_barrier(c.barrier, (unsigned)stage * gridDim.x);
     mma_trace(a, 2);
+
     {
         const int nchunk = K >> 3;  // 16-byte chunks of x
         const int npad = KT * 64;   // staged chunks (zero tail up to whole tiles)

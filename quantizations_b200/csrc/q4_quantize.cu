@@ -11,6 +11,7 @@
 // 8 codes as one 64-bit store (8-bit), so loads and stores are fully coalesced.  max() is exact under any
 // association, so the different reduction shape cannot change a bit.
 #include "q4_common.cuh"
+#include "q4_encode_lut.h"
 #include "q4_launch.h"
 
 namespace q4 {
@@ -121,12 +122,130 @@ quantize_blockwise_kernel(const float* __restrict__ code, const T* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- 4-bit fast path
+//
+// The kernel above spends ~50 instructions per element on the compare trees; at HBM rate the SM has ~11 (16-bit input).  This
+// one encodes through the binned table of q4_encode_lut.h: one fused multiply-add (exact bin), one 8-byte shared-memory lookup
+// {threshold inside the bin, code below it}, one compare.  The table is replicated 16 times (entry stride 128 B, replica =
+// lane % 16), so the half-warp phases of a 64-bit lookup never conflict whatever the data; persistent CTAs (4 per SM) build
+// it once and stream whole 2048-element chunks, four 128-bit loads in flight per thread.  Blocks whose absmax is not a
+// normal finite number (all-zero, denormal, inf / NaN inputs) take the compare trees, so every special value encodes exactly
+// as before.  Used for blocksize <= 256 (absmax by shuffles only) and n % 8 == 0.
+constexpr int kEncReplicas = 16;
+constexpr int kEncLutBytes = Q4_ENC_BINS * kEncReplicas * 8;
+
+template <int QT> __device__ __forceinline__ uint32_t encode_lut(uint32_t lut_lane, float x)
+{
+    if (QT == Q4_NF4) {
+        const float xc = fmaxf(x, -1.0f);  // NaN -> -1 -> code 0, like fifteen false compares
+        const uint32_t bits = __float_as_uint(__fmaf_rn(xc, 128.0f, 8388736.0f));
+        uint32_t thr, base;
+        // (bits << 7) = 0x80000000 + bin * 128: the constant is folded into lut_lane (32-bit wrap-around)
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(thr), "=r"(base) : "r"(bits * 128u + lut_lane));
+        return base + (xc > __uint_as_float(thr) ? 1u : 0u);
+    } else {
+        const float a = fmaxf(fabsf(x), 0.0f);  // NaN -> 0 -> rank 0
+        const uint32_t bits = __float_as_uint(__fmaf_rn(a, 256.0f, 8388608.0f));
+        uint32_t thr, codes;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(thr), "=r"(codes) : "r"(bits * 128u + lut_lane));
+        const uint32_t c = a > __uint_as_float(thr) ? (codes >> 4) : (codes & 0xFu);
+        return c + (x < 0.0f ? 8u : 0u);
+    }
+}
+
+template <typename T, int BS, int QT>
+__global__ void __launch_bounds__(256, 4)
+quantize_4bit_lut_kernel(const T* __restrict__ A, float* __restrict__ absmax, uint8_t* __restrict__ out, int64_t ngroups)
+{
+    constexpr int TPB = BS / 8;  // lanes that share one quantization block (<= 32)
+    constexpr int UNROLL = sizeof(T) == 2 ? 4 : 2;
+    extern __shared__ __align__(16) uint8_t enc_smem[];
+    for (int b = threadIdx.x; b < Q4_ENC_BINS; b += 256) {  // replica 0 of every bin ...
+        float thr;
+        uint32_t word;
+        q4_enc_entry(QT == Q4_NF4, b, &thr, &word);
+        *reinterpret_cast<uint2*>(enc_smem + (size_t)b * kEncReplicas * 8) = make_uint2(__float_as_uint(thr), word);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Q4_ENC_BINS * kEncReplicas; i += 256)  // ... copied to the other fifteen
+        if (i % kEncReplicas) *reinterpret_cast<uint2*>(enc_smem + (size_t)i * 8) = *reinterpret_cast<const uint2*>(enc_smem + (size_t)(i - i % kEncReplicas) * 8);
+    __syncthreads();
+    const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(enc_smem) + (threadIdx.x & 15) * 8 - 0x80000000u;
+
+    const int64_t nchunks = (ngroups + 255) / 256;
+    for (int64_t c0 = (int64_t)blockIdx.x * UNROLL; c0 < nchunks; c0 += (int64_t)gridDim.x * UNROLL) {
+        float v[UNROLL][8];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t g = (c0 + u) * 256 + threadIdx.x;
+            if (g < ngroups) {
+                load8<T>(A, g * 8, g * 8 + 8, v[u]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[u][j] = 0.0f;  // out-of-range slots read as 0 (kernels.cu:410)
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t g = (c0 + u) * 256 + threadIdx.x;
+            float m = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 8; j++) m = fmaxf(m, fabsf(v[u][j]));
+#pragma unroll
+            for (int o = TPB / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (g >= ngroups) continue;
+            if ((threadIdx.x & (TPB - 1)) == 0) absmax[g / TPB] = m;
+            const float inv = __fdiv_rn(1.0f, m);  // IEEE divide, kernels.cu:438
+            uint32_t word = 0;
+            if (m >= FLT_MIN && m <= FLT_MAX) {  // |v * inv| <= 1 + 2^-23 (or v is NaN): the binned encoder's domain
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    word |= encode_lut<QT>(lut_lane, __fmul_rn(v[u][j], inv)) << (8 * (j >> 1) + ((j & 1) ? 0 : 4));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float xn = __fmul_rn(v[u][j], inv);
+                    word |= (QT == Q4_NF4 ? encode_nf4(xn) : encode_fp4(xn)) << (8 * (j >> 1) + ((j & 1) ? 0 : 4));
+                }
+            }
+            *reinterpret_cast<uint32_t*>(out + g * 4) = word;
+        }
+    }
+}
+
 template <typename T, int QT>
 static int launch_quantize(const float* code, const T* A, float* absmax, uint8_t* out, int blocksize, int64_t n,
                            cudaStream_t stream)
 {
     if (n <= 0) return 0;
     const int64_t nblocks = (n + blocksize - 1) / blocksize;
+    if constexpr (QT != Q4_GENERAL8BIT) {
+        if ((n & 7) == 0 && blocksize <= 256) {
+            const int64_t ngroups = n / 8;
+            constexpr int UNROLL = sizeof(T) == 2 ? 4 : 2;
+            const int64_t want = (ngroups + 256 * UNROLL - 1) / (256 * UNROLL);
+            const int64_t cap = (int64_t)sm_count() * 4;
+            const unsigned grid = (unsigned)(want < cap ? want : cap);
+#define Q4_LUT_CASE(BS)                                                                                                   \
+    case BS: {                                                                                                            \
+        static bool attr = false;                                                                                         \
+        if (!attr) {                                                                                                      \
+            cudaError_t e = cudaFuncSetAttribute(quantize_4bit_lut_kernel<T, BS, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncLutBytes); \
+            if (e != cudaSuccess) return (int)e;                                                                          \
+            attr = true;                                                                                                  \
+        }                                                                                                                 \
+        quantize_4bit_lut_kernel<T, BS, QT><<<grid, 256, kEncLutBytes, stream>>>(A, absmax, out, ngroups);               \
+        return finish_launch();                                                                                           \
+    }
+            switch (blocksize) {
+                Q4_LUT_CASE(64)
+                Q4_LUT_CASE(128)
+                Q4_LUT_CASE(256)
+                default: break;
+            }
+#undef Q4_LUT_CASE
+        }
+    }
 #define Q4_CASE(BS)                                                                                              \
     case BS: {                                                                                                   \
         constexpr int CTA = (BS / 8 > 256) ? BS / 8 : 256;                                                       \

@@ -101,6 +101,67 @@ def test_quantize_4bit_nested_bit_exact_vs_oracle(q, oracle, quant_type):
     assert tuple(state.shape) == (N, K) and state.dtype == torch.bfloat16
 
 
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16", "float32"])
+@pytest.mark.parametrize("quant_type", ["fp4", "nf4"])
+def test_quantize_4bit_binned_encoder_edge_cases(q, oracle, dtype, quant_type):
+    """The fast quantize kernel (n % 8 == 0, blocksize <= 256) encodes through a binned table instead of the reference's
+    compare tree (csrc/q4_encode_lut.h; the method is swept over all 2^32 floats on the CPU by tests/test_host.py).  Here
+    the kernel itself: every 16-bit pattern (or 2^20 random fp32 patterns) as an element, blocks with absmax exactly 1 so that
+    the normalised value IS the element, values within a few ulp of every threshold under several absmax scalings, and blocks
+    whose absmax is zero / denormal / inf / NaN-polluted (the kernel's compare-tree branch)."""
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, quant_type)).encode()))
+    tdt = TDT[dtype]
+    if dtype == "float32":
+        pat = rng.integers(0, 2**32, 1 << 20, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    else:
+        pat = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(tdt).float().numpy()
+    chunks = []
+    unit = pat[np.isnan(pat) | (np.abs(pat) <= 1.0)]
+    for i in range(0, len(unit), 63):                      # 63 patterns + a 1.0: absmax == 1, x == element
+        blk = np.ones(64, np.float32)
+        blk[: len(unit[i:i + 63])] = unit[i:i + 63]
+        chunks.append(blk)
+    chunks.append(np.resize(pat, (len(pat) + 63) // 64 * 64))  # raw patterns: inf / NaN / huge blocks too
+    if quant_type == "nf4":  # the 15 midpoints of the table (kernels.cu:851)
+        t64 = oracle.nf4_table().astype(np.float64)
+        thr = ((t64[:-1] + t64[1:]) / 2).astype(np.float32)
+    else:                    # kernels.cu:141-159
+        thr = np.array([0.00260417, 0.0859375, 0.20833333, 0.29166667, 0.4166667, 0.583333, 0.8333333], np.float32)
+    near = []
+    for scale in (1.0, 0.02, 3.0, 1e-3, 7.7):
+        for t in np.concatenate([thr, -thr]):
+            c = np.float32(t) * np.float32(scale)
+            v = c
+            for _ in range(4):
+                v = np.nextafter(v, np.float32(-np.inf), dtype=np.float32)
+            for _ in range(9):
+                near.append(v)
+                v = np.nextafter(v, np.float32(np.inf), dtype=np.float32)
+    near = np.array(near, np.float32)
+    for scale, grp in zip((1.0, 0.02, 3.0, 1e-3, 7.7), np.split(near, 5)):
+        for i in range(0, len(grp), 63):
+            blk = np.full(64, scale, np.float32)
+            blk[: len(grp[i:i + 63])] = grp[i:i + 63]
+            chunks.append(blk)
+    special = np.zeros((6, 64), np.float32)
+    special[1, 3] = 1e-41                                   # denormal absmax: 1 / absmax overflows
+    special[2, :] = 1e-39
+    special[3, 5], special[3, 6] = np.inf, 1.0
+    special[4, 7], special[4, 8] = np.nan, -0.5
+    special[5, :] = -0.0
+    chunks.append(special.ravel())
+    a = np.concatenate(chunks).astype(np.float32)
+    A = dev(a, tdt)
+    a = f32(A)
+    assert a.size % 8 == 0
+    for blocksize in (64, 256):
+        n = a.size // blocksize * blocksize
+        packed, state = q.quantize_4bit(A[:n], blocksize=blocksize, quant_type=quant_type, compress_statistics=False)
+        o_packed, o_absmax = oracle.quantize_blockwise_4bit(a[:n], blocksize, quant_type)
+        assert_bits_equal(state.absmax.cpu().numpy(), o_absmax, f"absmax bs{blocksize}")
+        assert_bits_equal(packed.cpu().numpy().ravel(), o_packed, f"packed bs{blocksize}")
+
+
 def test_quantize_fp4_matches_reference_golden(q, golden):
     g = golden("quantize_fp4")
     for k, (dtype, blocksize, n, kind) in iter_cases(g):

@@ -96,3 +96,16 @@ def test_native_stats_validation():
     assert st.native_stats() is s  # cached until the tensors move
     st.to("cpu")
     assert st._stats is None
+
+
+def test_binned_4bit_encoder_equals_compare_tree_on_every_float(tmp_path):
+    """csrc/q4_encode_lut.h (what the fast quantize kernel encodes with) against the reference's compare trees
+    (kernels.cu:113-163; the 15 NF4 midpoints) on ALL 2^32 float bit patterns of its domain -- plain C on the host."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "encode_lut_check")
+    subprocess.check_call(["gcc", "-O2", "-fopenmp", os.path.join(root, "tests", "encode_lut_check.c"), "-lm", "-o", exe])
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
