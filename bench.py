@@ -413,7 +413,7 @@ def run_ours(args, rank, world, device):
             "launch": ("CUDA graph replay" if graph is not None else "eager") + (" + programmatic dependent launch" if args.pdl else "")
                       + (", chained: 1 + layers persistent launches per step (o -> gate/up -> down -> next q/k/v per launch)" if use_chain else "")
                       + (", q/k/v and gate/up as parallel graph branches (co-resident CTAs)" if args.branches else "")
-                      + (", next-layer weight L2 prefetch hint" if args.prefetch else ""),
+                      + (", next launch's first tiles prefetched into L2" if args.prefetch else ""),
             "parallelism": f"tp{world}" if world > 1 else "single GPU",
         },
         "pct_of_8TBs": round(value / world / 8000 * 100, 2),
@@ -428,6 +428,8 @@ def run_ours(args, rank, world, device):
                      "avg_launch_us": round(per_launch_us, 3), "algorithmic_bytes_per_launch": step_bytes_local // launches_per_step,
                      "traffic": traffic, "timed_blocks_ms": [round(t, 3) for t in times[:5]]},
     }
+    if world == 1 and not args.no_blockwise:
+        res["blockwise"] = blockwise_rates(device, peak)
     if world == 1 and not args.no_cpu:
         res["cpu_baseline"] = cpu_baseline(mods[:7], x_in, budget_s=args.cpu_seconds)
     if world == 1 and not args.no_decode:
@@ -435,6 +437,57 @@ def run_ours(args, rank, world, device):
         torch.cuda.empty_cache()
         res["decode"] = decode_tok_s(args, device, "ours")
     return res
+
+
+def blockwise_rates(device, peak, N=14336, K=4096, pool=6, iters=30):
+    """The other two HBM-bound kernels of the path: blockwise quantize (bf16 -> NF4, fp32 absmax) and dequantize
+    (NF4 + double-quant statistics -> bf16) of one 14336x4096 weight, kernel-only through the C ABI, rotating over `pool`
+    distinct matrices (inputs + outputs >> L2), CUDA events on the launching stream.  Algorithmic bytes: quantize reads 2n and
+    writes n/2 + n/16; dequantize reads n/2 + n/64 + nested statistics and writes 2n."""
+    import quantizations_b200 as q
+    from quantizations_b200 import _lib
+
+    L = _lib.lib()
+    n = N * K
+    Ws = [(torch.randn(N, K, device=device) * 0.02).to(torch.bfloat16) for _ in range(pool)]
+    packs, states = zip(*[q.quantize_4bit(W, quant_type="nf4") for W in Ws])
+    absmaxs = [torch.empty(n // 64, device=device, dtype=torch.float32) for _ in range(pool)]
+    outs = [torch.empty_like(p) for p in packs]
+    deq = [torch.empty(N, K, device=device, dtype=torch.bfloat16) for _ in range(pool)]
+    stats = [s.native_stats() for s in states]
+    stream = torch.cuda.current_stream(device).cuda_stream
+
+    def kq(i):
+        j = i % pool
+        _lib.check(L.q4_quantize_blockwise_4bit(Ws[j].data_ptr(), absmaxs[j].data_ptr(), outs[j].data_ptr(), 64, n, _lib.Q4_NF4,
+                                                  _lib.Q4_BF16, stream), "quantize")
+
+    def kd(i):
+        j = i % pool
+        _lib.check(L.q4_dequantize_blockwise_4bit(packs[j].data_ptr(), stats[j], deq[j].data_ptr(), 64, n, _lib.Q4_NF4, _lib.Q4_BF16,
+                                                    stream), "dequantize")
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) * 1e3 / iters
+
+    q_bytes = 2 * n + n // 2 + 4 * (n // 64)
+    d_bytes = n // 2 + n // 64 + 4 * -(-(n // 64) // 256) + 1092 + 2 * n
+    tq, td = timed(kq), timed(kd)
+    assert torch.equal(outs[0], packs[0])
+    return {"workload": f"{N}x{K} bf16 <-> NF4, blocksize 64, kernel-only, {pool} matrices in rotation (> L2)",
+            "quantize": {"us": round(tq, 2), "achieved": round(q_bytes / tq / 1e3, 1), "unit": "GB/s", "frac": round(q_bytes / tq / 1e3 / peak, 3),
+                         "algorithmic_bytes": q_bytes, "kernel": "q4::quantize_4bit_lut_kernel<bf16, 64, NF4>"},
+            "dequantize": {"us": round(td, 2), "achieved": round(d_bytes / td / 1e3, 1), "unit": "GB/s", "frac": round(d_bytes / td / 1e3 / peak, 3),
+                           "algorithmic_bytes": d_bytes, "kernel": "q4::dequantize_4bit_kernel<bf16, NF4, nested>"}}
 
 
 def decode_tok_s(args, device, impl):
@@ -606,14 +659,15 @@ def main():
                          "launch per (grouped) Linear; measured SLOWER on B200 (1.65 vs 1.47 ms/step: DESIGN.md 4.1c), hence opt-in")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="tensor-parallel runs: NCCL all-reduce after the row-parallel GEMVs (the baseline) instead of the fused epilogue exchange")
-    ap.add_argument("--prefetch", action="store_true",
-                    help="pass the next layer's packed weight as the L2 prefetch hint (measured neutral on one stream; off by default so "
-                         "that every launch's DRAM traffic is exactly its own matrix)")
+    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
+                    help="do not pass the next launch's packed weight + in_features as the L2 prefetch hint (q4_gemv_fused_t.prefetch_K: "
+                         "each CTA pulls the first tiles the next launch's CTAs will ask for into L2; measured 1.27 vs 1.30 ms/step)")
     ap.add_argument("--branches", action="store_true",
                     help="launch q/k/v and gate/up as parallel graph branches (measured slower than one stream + PDL: the graph's "
                          "cross-stream edges cost more than the co-residency gains on 1-5 us kernels)")
     ap.add_argument("--no-group", dest="group", action="store_false", help="one launch per Linear instead of grouped q/k/v and gate/up")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-blockwise", action="store_true", help="skip the quantize / dequantize kernel rates")
     ap.add_argument("--no-decode", action="store_true", help="skip the end-to-end Llama-3-8B decode tok/s leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

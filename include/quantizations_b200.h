@@ -109,7 +109,7 @@ int q4_dequantize_blockwise_4bit(const uint8_t* A, const q4_absmax_t* stats, voi
  * prefetch / prefetch_bytes (optional, NULL / 0): a byte range that the NEXT call will stream (typically the packed
  * weight of the following Linear4bit).  It is pulled into the 126 MB L2 with TMA bulk prefetches while this call
  * computes, so HBM never idles between dependent launches.  Purely a hint: results do not depend on it. */
-enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2, Q4_GEMV_SHARE_SM = 4 };
+enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2, Q4_GEMV_SHARE_SM = 4, Q4_ATTN_EARLY_CACHE = 8 };
 int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias,
                  void* out, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* prefetch,
                  int64_t prefetch_bytes, void* stream);
@@ -208,9 +208,18 @@ int q4_gemv_lut_build(const float* code, const float* code2, int dtype, void* lu
  * rotate_half convention) on the new token's q and k, KV-cache append at *pos, and grouped-query attention of that one query
  * over cache positions [0, *pos], in one launch.  qkv = [nh*hd | nkv*hd | nkv*hd] as the grouped q/k/v GEMV leaves it;
  * cos_tab / sin_tab [max_len, hd/2]; caches [nkv, max_len, hd]; out [nh*hd]; hd must be 128; dtype Q4_F16 / Q4_BF16;
- * flags: Q4_GEMV_PDL.  `pos` is a DEVICE scalar so the call can sit in a replayed CUDA graph. */
+ * flags: Q4_GEMV_PDL.  `pos` is a DEVICE scalar so the call can sit in a replayed CUDA graph.
+ *        Q4_ATTN_EARLY_CACHE (with Q4_GEMV_PDL): the caller guarantees that only `qkv` is produced by the kernel launched just
+ *        before this one -- `pos`, the tables and the cache rows below `pos` were complete before THAT kernel started (true inside a
+ *        decode step: they are written by earlier steps) -- so they are read while the preceding kernel is still running. */
 int q4_decode_attention(const void* qkv, const void* cos_tab, const void* sin_tab, void* k_cache, void* v_cache, const int64_t* pos,
                         void* out, int nh, int nkv, int hd, int max_len, int dtype, int flags, void* stream);
+
+/* Greedy-sampling glue of the same harness: out[0] = index of the largest of the n values of x (lowest index on ties, NaN ranks
+ * highest, like torch.argmax) in one short launch.  workspace: Q4_ARGMAX_WORKSPACE_BYTES of 8-byte aligned device memory, zeroed
+ * once by the caller (the kernel leaves it ready for the next launch, so the call can sit in a replayed CUDA graph). */
+#define Q4_ARGMAX_WORKSPACE_BYTES 4096
+int q4_argmax(const void* x, int64_t n, int dtype, int64_t* out, void* workspace, void* stream);
 
 /* Prefill / batched path with the dequantisation fused into a tcgen05 tensor-core GEMM:
  *     out[m, r] = sum_k X[m, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r]),   m in [0, M), r in [0, N)

@@ -804,3 +804,22 @@ def decode_attention(qkv: Tensor, cos: Tensor, sin: Tensor, k_cache: Tensor, v_c
     if rc:
         check(rc, "decode_attention")
     return out
+
+
+_ARGMAX_WS = {}
+
+
+def argmax(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """Index of the largest element of a contiguous fp16/bf16/fp32 vector as a one-element int64 tensor (greedy sampling of the
+    decode harness; include/quantizations_b200.h: q4_argmax).  One ~3 us launch, capturable in a CUDA graph."""
+    if x.dtype not in _DTYPE_CODE or not x.is_contiguous():
+        raise ValueError("argmax needs a contiguous fp16 / bf16 / fp32 tensor")
+    key = (x.device.type, x.device.index)
+    ws = _ARGMAX_WS.get(key)
+    if ws is None:
+        ws = _ARGMAX_WS[key] = torch.zeros(4096, dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty(1, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().q4_argmax(x.data_ptr(), x.numel(), _DTYPE_CODE[x.dtype], out.data_ptr(), ws.data_ptr(), _stream(x)), "argmax")
+    return out

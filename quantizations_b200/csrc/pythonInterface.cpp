@@ -139,6 +139,11 @@ int q4_decode_attention(const void* qkv, const void* cos_tab, const void* sin_ta
                                 (cudaStream_t)stream);
 }
 
+int q4_argmax(const void* x, int64_t n, int dtype, int64_t* out, void* workspace, void* stream)
+{
+    return q4::argmax(x, n, dtype, (long long*)out, workspace, (cudaStream_t)stream);
+}
+
 int q4_gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, void* stream)
 {
     return q4::gemv_lut_build(code, code2, dtype, lut, (cudaStream_t)stream);

@@ -390,7 +390,9 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                     a.nx_grid = ngrid;
                     a.nx_rt_q = nrt / ngrid;
                     a.nx_rt_r = nrt % ngrid;
-                    a.nx_head = (kBuffers * (kMmaThreads / 32) + nkt - 1) / nkt;
+                    static const int env_head = getenv("Q4_GEMV_HEAD_MULT") ? atoi(getenv("Q4_GEMV_HEAD_MULT")) : 1;  // developer switches
+                    static const int env_tiles = getenv("Q4_GEMV_HEAD_TILES") ? atoi(getenv("Q4_GEMV_HEAD_TILES")) : kBuffers;
+                    a.nx_head = env_head * ((env_tiles * (kMmaThreads / 32) + nkt - 1) / nkt);
                     a.nx_tile_bytes = 4 * nK;  // 8 rows x K/2 bytes
                 }
             }

@@ -36,6 +36,7 @@ int gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, c
 int gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, cudaStream_t stream);
 int decode_attention(const void* qkv, const void* cos_tab, const void* sin_tab, void* k_cache, void* v_cache, const long long* pos,
                      void* out, int nh, int nkv, int hd, int max_len, int dtype, int flags, cudaStream_t stream);
+int argmax(const void* x, int64_t n, int dtype, long long* out, void* workspace, cudaStream_t stream);
 int gemm_4bit(const void* X, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
               int64_t M, int64_t N, int64_t K, int blocksize, int dtype, cudaStream_t stream);
 

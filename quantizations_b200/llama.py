@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .core import decode_attention, gemv_4bit_chain, gemv_4bit_fused
+from .core import argmax, decode_attention, gemv_4bit_chain, gemv_4bit_fused
 
 
 @dataclass
@@ -75,6 +75,10 @@ class Llama(nn.Module):
         self.fuse_glue = True  # fold RMSNorm / SwiGLU / residual adds into the decode GEMV launches (Linear4bit layers only)
         self.fused_ar = None   # tp.FusedAllReduce: the row-parallel all-reduce inside the GEMV epilogue instead of NCCL
         self.fuse_attn = cfg.head_dim == 128  # decode: RoPE + KV append + attention as one launch (q4_decode_attention)
+        # the decode step's attention launch reads `pos`, cos / sin and the cache rows of EARLIER steps while the q/k/v GEMV before
+        # it is still running (only the new token's q/k/v depend on that GEMV)
+        from . import _lib as _l
+        self.attn_flags = _l.Q4_GEMV_PDL | _l.Q4_ATTN_EARLY_CACHE
         self.chain = False     # decode: o -> gate/up -> down -> next layer's q/k/v as ONE persistent launch (q4_gemv_4bit_chain);
                                # measured slower than separate launches under programmatic dependent launch
         g = torch.Generator(device=device).manual_seed(1234)
@@ -99,6 +103,13 @@ class Llama(nn.Module):
         c, s = cos[:, None, :], sin[:, None, :]
         return torch.cat((x1 * c - x2 * s, x2 * c + x1 * s), dim=-1)
 
+    @staticmethod
+    def _hint(nxt):
+        """Exact L2 prefetch hint for a decode launch: (packed weight, in_features) of the Linear4bit / group that runs next."""
+        if nxt is None:
+            return None
+        return (nxt.packed if hasattr(nxt, "packed") else nxt.weight.data, nxt.in_features)
+
     def _allreduce(self, t):
         if self.tp > 1:
             torch.distributed.all_reduce(t, group=self.group)
@@ -122,8 +133,8 @@ class Llama(nn.Module):
             fused = L.qkv is not None and T == 1 and self.fuse_glue
             h = None if fused else F.rms_norm(x, (cfg.hidden,), L.ln1, cfg.eps)
             if fused and self.fuse_attn:
-                qkv = gemv_4bit_fused(x, None, group=L.qkv, rms_weight=L.ln1, rms_eps=cfg.eps)
-                a = decode_attention(qkv, self.cos, self.sin, self.k_cache[li], self.v_cache[li], pos, L.nh, L.nkv)
+                qkv = gemv_4bit_fused(x, None, group=L.qkv, rms_weight=L.ln1, rms_eps=cfg.eps, prefetch=self._hint(L.o_proj))
+                a = decode_attention(qkv, self.cos, self.sin, self.k_cache[li], self.v_cache[li], pos, L.nh, L.nkv, flags=self.attn_flags)
             elif fused:  # RMSNorm folded into the grouped q/k/v launch: the norm kernel and its round trip disappear
                 q, k, v = gemv_4bit_fused(x, None, group=L.qkv, rms_weight=L.ln1, rms_eps=cfg.eps).split(L.qkv.splits, dim=-1)
             elif L.qkv is not None and T == 1:
@@ -142,10 +153,12 @@ class Llama(nn.Module):
                 # o_proj adds the residual stream in its epilogue; norm folded into gate/up; SwiGLU folded into down_proj's
                 # activation staging, residual again in its epilogue: four launches for the layer's seven Linears + glue
                 qs = L.o_proj.weight.quant_state
-                x = gemv_4bit_fused(a, L.o_proj.weight.data, qs, residual=x, allreduce=self.fused_ar)
-                g, u = gemv_4bit_fused(x, None, group=L.gate_up, rms_weight=L.ln2, rms_eps=cfg.eps).split(L.gate_up.splits, dim=-1)
+                nxt = self.layers[li + 1].qkv if li + 1 < len(self.layers) else None
+                x = gemv_4bit_fused(a, L.o_proj.weight.data, qs, residual=x, allreduce=self.fused_ar, prefetch=self._hint(L.gate_up))
+                g, u = gemv_4bit_fused(x, None, group=L.gate_up, rms_weight=L.ln2, rms_eps=cfg.eps,
+                                       prefetch=self._hint(L.down_proj)).split(L.gate_up.splits, dim=-1)
                 x = gemv_4bit_fused(u, L.down_proj.weight.data, L.down_proj.weight.quant_state, gate=g, residual=x,
-                                    allreduce=self.fused_ar)
+                                    allreduce=self.fused_ar, prefetch=self._hint(nxt))
                 continue
             x = x + self._allreduce(L.o_proj(a))
             h = F.rms_norm(x, (cfg.hidden,), L.ln2, cfg.eps)
@@ -166,7 +179,7 @@ class Llama(nn.Module):
         qkv = gemv_4bit_fused(h, None, group=Ls[0].qkv, rms_weight=Ls[0].ln1, rms_eps=cfg.eps)
         gu = torch.empty(1, 1, Ls[0].gate_up.out_features, dtype=h.dtype, device=h.device)
         for li, L in enumerate(Ls):
-            a = decode_attention(qkv, self.cos, self.sin, self.k_cache[li], self.v_cache[li], pos, L.nh, L.nkv)
+            a = decode_attention(qkv, self.cos, self.sin, self.k_cache[li], self.v_cache[li], pos, L.nh, L.nkv, flags=self.attn_flags)
             with gemv_4bit_chain() as ch:
                 ch.add(a, L.o_proj.weight.data, L.o_proj.weight.quant_state, residual=h, out=h, allreduce=self.fused_ar)
                 ch.add(h, None, group=L.gate_up, rms_weight=L.ln2, rms_eps=cfg.eps, out=gu)
@@ -192,7 +205,7 @@ class Llama(nn.Module):
 
         def step():
             lg = self.forward(tok, pos)
-            tok.copy_(lg.argmax().view(1))
+            argmax(lg, out=tok)  # greedy: one short launch straight into the next step's input token
             pos.add_(1)
 
         graph = None

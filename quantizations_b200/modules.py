@@ -102,7 +102,7 @@ class Linear4bit(nn.Linear):
         # decode-launch hints (new; see include/quantizations_b200.h): programmatic dependent launch is always safe --
         # the kernel reads x and writes its output only after the preceding kernel has completed
         self.gemv_flags = _lib.Q4_GEMV_PDL
-        self.prefetch_next = None  # packed weight of the Linear that runs next (pulled into L2 while this one computes)
+        self.prefetch_next = None  # (packed weight, in_features) of the Linear that runs next: its first tiles are pulled into L2
 
     def set_compute_type(self, x):
         """reference modules.py:112-122: fp32 / bf16 inputs set the compute dtype; fp16 keeps the configured one."""

@@ -566,6 +566,73 @@ def test_tcgen05_gemv_matches_mma_sync_gemv(q, shape, dtype):
         assert int(ws[:65536].view(torch.int32).ne(0).sum()) == 0
 
 
+@pytest.mark.parametrize("pos", [0, 1, 7, 64, 65, 200, 255])
+def test_decode_attention_early_cache_reads_change_nothing(q, pos):
+    """Q4_ATTN_EARLY_CACHE only moves loads of data written by earlier steps in front of griddepcontrol.wait and fetches the
+    cached rows in batches of 8 per warp: the output and the appended cache row must be bit-identical to the plain launch, at
+    context lengths that leave batches empty, partly filled and repeated."""
+    from quantizations_b200 import _lib
+    from quantizations_b200.core import decode_attention
+
+    nh, nkv, hd, max_len = 8, 2, 128, 256
+    g = torch.Generator(device=DEV).manual_seed(pos)
+    dt = torch.bfloat16
+    qkv = torch.randn(1, 1, (nh + 2 * nkv) * hd, device=DEV, generator=g).to(dt)
+    ang = torch.rand(max_len, hd // 2, device=DEV, generator=g) * 6.0
+    cos, sin = ang.cos().to(dt), ang.sin().to(dt)
+    kc = torch.randn(nkv, max_len, hd, device=DEV, generator=g).to(dt)
+    vc = torch.randn(nkv, max_len, hd, device=DEV, generator=g).to(dt)
+    p = torch.tensor([pos], device=DEV)
+    outs = []
+    for flags in (_lib.Q4_GEMV_PDL, _lib.Q4_GEMV_PDL | _lib.Q4_ATTN_EARLY_CACHE, 0):
+        k, v = kc.clone(), vc.clone()
+        o = decode_attention(qkv, cos, sin, k, v, p, nh, nkv, flags=flags)
+        outs.append((o.clone(), k, v))
+    for o, k, v in outs[1:]:
+        assert torch.equal(o, outs[0][0]) and torch.equal(k, outs[0][1]) and torch.equal(v, outs[0][2])
+    # and against plain torch attention over positions [0, pos] (fp32 softmax), within bf16 rounding of the output
+    q_ = qkv.view(-1)[: nh * hd].view(nh, hd).float()
+    kn = outs[0][1][:, : pos + 1].float()
+    vn = outs[0][2][:, : pos + 1].float()
+    c, s_ = cos[pos].float(), sin[pos].float()
+    q1, q2 = q_[:, : hd // 2], q_[:, hd // 2:]
+    rnd = lambda t: t.to(dt).float()  # noqa: E731
+    qr = torch.cat((rnd(rnd(q1 * c) - rnd(q2 * s_)), rnd(rnd(q2 * c) + rnd(q1 * s_))), dim=-1)
+    want = torch.empty(nh, hd, device=DEV)
+    for h in range(nh):
+        sc = (kn[h // (nh // nkv)] @ qr[h]) / hd**0.5
+        want[h] = torch.softmax(sc, dim=0) @ vn[h // (nh // nkv)]
+    got = outs[0][0].float().view(nh, hd)
+    assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float32"])
+@pytest.mark.parametrize("n", [1, 7, 8, 1000, 128256, 300001])
+def test_argmax_matches_torch(q, dtype, n):
+    """q4_argmax (greedy sampling glue): the index torch.argmax returns, lowest index on ties, replayable in a CUDA graph."""
+    from quantizations_b200.core import argmax
+
+    g = torch.Generator(device=DEV).manual_seed(n)
+    x = torch.randn(n, device=DEV, generator=g).to(TDT[dtype])
+    assert int(argmax(x)) == int(x.argmax())
+    if n > 8:
+        x[n // 3] = x[n - 2] = x.max() + 1  # a tie: the lowest index wins
+        assert int(argmax(x)) == n // 3
+    out = torch.zeros(1, dtype=torch.int64, device=DEV)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        argmax(x, out=out)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            argmax(x, out=out)
+    for i in range(3):
+        x[(i * 7919) % n] = 1e4 * (i + 1)
+        gr.replay()
+        torch.cuda.synchronize()
+        assert int(out) == (i * 7919) % n
+
+
 def test_fused_decode_attention_matches_torch_attention_path(q):
     """q4_decode_attention (RoPE + KV append + GQA attention in one launch) against the torch ops it replaces inside the same
     decoder (llama.py, head_dim 128): same logits within bf16 rounding, same cache contents, over several decode steps."""
