@@ -181,7 +181,9 @@ __device__ __noinline__ void prefetch_next_share(const uint8_t* next, int64_t ne
 
 // Exact form of the hint: only the head of every next-launch CTA's share -- the tiles it will load into registers during its cold
 // start, ~14 MB over the grid -- goes HBM -> L2.  Measured on the Llama-3-8B stack (1.305 ms/step without a hint): issued in the
-// CTA's first instructions 1.287 ms, after its loop 1.312 ms, right after griddepcontrol.wait 1.357 ms.
+// CTA's first instructions 1.287 ms, after its loop 1.312 ms, right after griddepcontrol.wait 1.357 ms; two / four times the head
+// 1.32 / 1.39 ms; additionally the CTA's OWN range beyond its first tiles 1.38 ms -- bulk L2 prefetch only pays for bytes that
+// are on the critical path of a cold start.
 __device__ __noinline__ void prefetch_next_heads(const uint8_t* next, int nx_grid, int nx_rt_q, int nx_rt_r, int nx_head,
                                                  long long nx_tile_bytes, int lane)
 {
@@ -313,12 +315,17 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     if (c.st[0].lut && tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kLutBytes) : "memory");
+#ifdef Q4_GEMV_EXPERIMENT_SMALLTABLE  // developer experiment (wrong results): what the launch costs with a quarter of the table traffic
+        constexpr int kCopy = kLutBytes / 4;
+#else
+        constexpr int kCopy = kLutBytes;
+#endif
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kCopy) : "memory");
 #pragma unroll
         for (int i = 0; i < 4; i++)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             lut_saddr + kImm + i * (kLutBytes / 4)),
-                         "l"(reinterpret_cast<const uint8_t*>(c.st[0].lut) + i * (kLutBytes / 4)), "r"(kLutBytes / 4), "r"(bar)
+                             lut_saddr + kImm + i * (kCopy / 4)),
+                         "l"(reinterpret_cast<const uint8_t*>(c.st[0].lut) + i * (kCopy / 4)), "r"(kCopy / 4), "r"(bar)
                          : "memory");
     }
     mma_trace(c.st[0], 7);
