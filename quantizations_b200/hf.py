@@ -22,7 +22,7 @@ import torch
 
 from . import core, modules
 
-__all__ = ["namespace", "install", "replace_with_bnb_linear", "quantize_model"]
+__all__ = ["namespace", "install", "replace_with_bnb_linear", "quantize_model", "graph_generate"]
 
 _NS = None
 
@@ -98,3 +98,56 @@ def quantize_model(model: torch.nn.Module, quantization_config, device="cuda", m
             if b is not None:
                 m.bias = torch.nn.Parameter(b.to(device), requires_grad=False)
     return model.to(device)
+
+
+@torch.no_grad()
+def graph_generate(model: torch.nn.Module, input_ids: torch.Tensor, max_new_tokens: int, max_cache_len: int = None,
+                   use_graph: bool = True):
+    """Greedy batch-1 decoding of an HF causal LM with transformers' StaticCache and the single-token forward captured ONCE in a
+    CUDA graph (quantizations_b200.graphs.capture) -- what `generate()` cannot do for the reference, whose kernels run on the
+    legacy default stream.  HF's eager `generate()` spends ~15 ms of host time per token at batch 1 whatever
+    the Linear layers cost; replayed as a graph the step costs what its kernels cost.  Works for any model whose forward accepts
+    `past_key_values=StaticCache, cache_position=`; every Linear4bit launch of this engine is capturable.
+
+    `use_graph=False` runs the same static-cache loop eagerly (the same kernels launch by launch: identical tokens).
+    Returns (new tokens [1, max_new_tokens], seconds spent in the decode loop)."""
+    import time
+
+    from transformers import StaticCache
+
+    from .graphs import capture
+
+    if input_ids.shape[0] != 1:
+        raise ValueError("graph_generate decodes one sequence")
+    dev = input_ids.device
+    P = input_ids.shape[1]
+    cache = StaticCache(config=model.config, max_cache_len=max_cache_len or P + max_new_tokens + 8)
+    out = model(input_ids, past_key_values=cache, cache_position=torch.arange(P, device=dev), use_cache=True)
+    tok = out.logits[:, -1].argmax(-1, keepdim=True)
+    pos = torch.full((1,), P, device=dev, dtype=torch.long)
+    new = torch.empty(1, max_new_tokens, dtype=torch.long, device=dev)
+
+    def step():
+        o = model(tok, past_key_values=cache, cache_position=pos, use_cache=True)
+        tok.copy_(o.logits[:, -1].argmax(-1, keepdim=True))
+        pos.add_(1)
+
+    graph = None
+    if use_graph:
+        tok0, pos0 = tok.clone(), pos.clone()
+        graph = capture(step, warmup=2)  # warm-up steps write cache rows >= P: masked until the real steps overwrite them
+        tok.copy_(tok0)
+        pos.copy_(pos0)
+        for layer in getattr(cache, "layers", ()):  # transformers >= 5: a static layer counts its own write position on the device
+            if isinstance(getattr(layer, "cumulative_length", None), torch.Tensor):
+                layer.cumulative_length.fill_(P)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(max_new_tokens):
+        new[:, i:i + 1].copy_(tok)
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+    torch.cuda.synchronize(dev)
+    return new, time.perf_counter() - t0

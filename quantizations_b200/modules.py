@@ -5,6 +5,7 @@ reference: /root/reference/modules.py:28-64 (matmul_4bit), :67-151 (Linear4bit).
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -124,9 +125,51 @@ class Linear4bit(nn.Linear):
         weight = self.weight
         if weight.quant_state is None:
             raise RuntimeError("Linear4bit weight is not quantized yet: move the module to a CUDA device first")
+        if x.numel() == x.shape[-1] and x.dtype in _FAST_DTYPES and x.is_contiguous() and x.shape[-1] == self.in_features:
+            out = self._decode(x, weight, bias)
+            if out is not None:
+                return out if out.dtype == inp_dtype else out.to(inp_dtype)
         out = matmul_4bit(x, weight.data, bias=bias, quant_state=weight.quant_state, flags=self.gemv_flags,
                           prefetch=self.prefetch_next)
         return out if out.dtype == inp_dtype else out.to(inp_dtype)
+
+
+_FAST_DTYPES = (torch.float16, torch.bfloat16)
+_DECODE_CACHE = weakref.WeakKeyDictionary()  # Linear4bit -> cached launch descriptor of its single-vector forward
+
+
+def _linear4bit_decode(self, x, weight, bias):
+    """Single-vector forward with a cached launch descriptor (q4_gemv_fused_t): everything that does not change between calls --
+    weight, statistics, tables -- is bound once, so a call costs one allocation, three pointer stores and the launch.  Under HF
+    generate() the host side of 224 Linear calls per token is what batch-1 decode waits for.  Same launch as core.gemv_4bit."""
+    qs = weight.quant_state
+    if qs.blocksize != 64:
+        return None
+    key = (weight.data_ptr(), id(qs), qs.absmax.data_ptr(), x.dtype, self.gemv_flags)
+    c = _DECODE_CACHE.get(self)  # kept outside the module: ctypes descriptors must not be deep-copied / pickled with it
+    if c is None or c[0] != key:
+        import ctypes
+
+        from .core import _DTYPE_CODE, _ws_args
+
+        stats, lut = qs.native_stats(), qs.lut(x.dtype)
+        f = _lib.GemvFused(None, None, None, 0.0, weight.data_ptr(), ctypes.pointer(stats), None, None, 1, qs.code.data_ptr(), None, None,
+                           qs.shape[0], qs.shape[1], 64, _DTYPE_CODE[x.dtype], self.gemv_flags, None, 0, lut.data_ptr(),
+                           *_ws_args(x.device))
+        c = _DECODE_CACHE[self] = (key, f, ctypes.byref(f), (stats, lut), _lib.lib().q4_gemv_4bit_fused, qs.shape[0])
+    f = c[1]
+    out = torch.empty(x.shape[:-1] + (c[5],), dtype=x.dtype, device=x.device)
+    f.x, f.out, f.bias = x.data_ptr(), out.data_ptr(), (None if bias is None else bias.data_ptr())
+    nxt = self.prefetch_next
+    if nxt is not None:
+        t, k = nxt if isinstance(nxt, tuple) else (nxt, 0)
+        f.prefetch, f.prefetch_bytes, f.prefetch_K = t.data_ptr(), t.numel() * t.element_size(), k
+    else:
+        f.prefetch, f.prefetch_bytes, f.prefetch_K = None, 0, 0
+    rc = c[4](c[2], torch.cuda.current_stream(x.device).cuda_stream)
+    if rc:
+        _lib.check(rc, "gemv_4bit")
+    return out
 
 
 class Linear4bitGroup(nn.Module):
@@ -211,3 +254,6 @@ class Linear4bitGroup(nn.Module):
         if x.numel() == x.shape[-1] and x.dtype in (torch.float16, torch.bfloat16) and x.is_contiguous():
             return self.forward_fused(x).split(self.splits, dim=-1)
         return tuple(lin(x) for lin in self.members)
+
+
+Linear4bit._decode = _linear4bit_decode

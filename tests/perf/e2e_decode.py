@@ -1,10 +1,10 @@
 """End-to-end batch-1 decode tok/s (BASELINE config 3): random-init Llama-3-8B, 32-token prompt, 60 new tokens, greedy.
 
-    python tools/e2e_decode.py [--layers 32] [--which ours-graph,ours-eager,ref-asshipped,ref-bf16,dense]
+    python tests/perf/e2e_decode.py [--layers 32] [--which ours-graph,ours-eager,ref-asshipped,ref-bf16,dense]
 """
 import argparse, json, os, sys, time
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from quantizations_b200 import llama
 

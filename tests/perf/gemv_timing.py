@@ -1,6 +1,6 @@
 """Developer tool: per-shape GEMV timing on one GPU (product vs the reference kernel when oracle/_ref is present).
 
-    python tools/gemv_timing.py [--dtype bf16] [--quant nf4] [--pool-mb 1024] [--iters 400]
+    python tests/perf/gemv_timing.py [--dtype bf16] [--quant nf4] [--pool-mb 1024] [--iters 400]
 
 Weights rotate through a pool larger than L2 so every byte comes from HBM; times are CUDA-event averages over
 back-to-back launches on the current stream.  Not part of the product; bench.py is the contract benchmark.
@@ -13,7 +13,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import quantizations_b200 as q  # noqa: E402
 from quantizations_b200 import _lib  # noqa: E402

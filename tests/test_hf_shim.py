@@ -65,3 +65,26 @@ def test_hf_llama_quantised_through_the_shim_matches_dense_twin():
         assert (sq - sd).abs().max().item() <= 3e-2 * sd.abs().max().item()
         out = model.generate(ids, max_new_tokens=8, do_sample=False)
         assert out.shape == (1, 24)
+
+
+@pytest.mark.gpu
+def test_graph_generate_replays_the_eager_static_cache_loop():
+    """quantizations_b200.hf.graph_generate: the HF model's single-token forward captured in a CUDA graph yields exactly the
+    tokens of the same static-cache loop run eagerly, and the first token is generate()'s (later ones may differ from the dynamic
+    cache path by rounding on a random-init model)."""
+    from transformers import BitsAndBytesConfig
+
+    from quantizations_b200 import hf
+
+    dev = "cuda:0"
+    model = _tiny().to(torch.bfloat16)
+    cfg = BitsAndBytesConfig(load_in_4bit=True, bnb_4bit_quant_type="nf4", bnb_4bit_use_double_quant=True,
+                             bnb_4bit_compute_dtype=torch.bfloat16)
+    hf.quantize_model(model, cfg, device=dev)
+    ids = torch.arange(3, 19, device=dev).view(1, -1)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        eager, _ = hf.graph_generate(model, ids, 12, use_graph=False)
+        graph, _ = hf.graph_generate(model, ids, 12)
+        ref = model.generate(ids, max_new_tokens=1, do_sample=False, pad_token_id=0)
+    assert torch.equal(eager, graph)
+    assert int(ref[0, -1]) == int(graph[0, 0])
