@@ -387,6 +387,10 @@ def run_ours(args, rank, world, device):
             raise RuntimeError(f"e2e output {k} differs from the C-ABI output")
 
     if rank != 0:
+        if not args.no_decode:  # the tensor-parallel decode leg runs on every rank
+            del mods, graph, g2
+            torch.cuda.empty_cache()
+            decode_tok_s(args, device, "ours", rank, world)
         return None
     peak, peak_src = measured_peak()
     per_launch_us = ms_per_step * 1e3 / launches_per_step
@@ -432,10 +436,10 @@ def run_ours(args, rank, world, device):
         res["blockwise"] = blockwise_rates(device, peak)
     if world == 1 and not args.no_cpu:
         res["cpu_baseline"] = cpu_baseline(mods[:7], x_in, budget_s=args.cpu_seconds)
-    if world == 1 and not args.no_decode:
+    if not args.no_decode:
         del mods, graph, g2
         torch.cuda.empty_cache()
-        res["decode"] = decode_tok_s(args, device, "ours")
+        res["decode"] = decode_tok_s(args, device, "ours", rank, world)
     return res
 
 
@@ -490,16 +494,25 @@ def blockwise_rates(device, peak, N=14336, K=4096, pool=6, iters=30):
                            "algorithmic_bytes": d_bytes, "kernel": "q4::dequantize_4bit_kernel<bf16, NF4, nested>"}}
 
 
-def decode_tok_s(args, device, impl):
-    """Second half of BASELINE's metric: Llama-3-8B batch-1 greedy decode tok/s (random-init, 32-token prompt, 60 new tokens,
+def decode_tok_s(args, device, impl, rank=0, world=1):
+    """Second half of BASELINE's metric: Llama-3 batch-1 greedy decode tok/s (random-init, 32-token prompt, 60 new tokens,
     best of 3) inside quantizations_b200.llama -- ours under a CUDA graph; the reference's kernels eagerly on the legacy
-    default stream (they cannot be captured), same NF4 / bf16 configuration."""
+    default stream (they cannot be captured), same NF4 / bf16 configuration.  world > 1: the whole model tensor-parallel over the
+    ranks (BASELINE config 5), row-parallel all-reduces inside the GEMV epilogues, time = max over ranks."""
+    import dataclasses
+
     from quantizations_b200 import llama
 
-    cfg = llama.LlamaConfig(layers=args.layers or 32)
+    base = llama.LLAMA3_70B if getattr(args, "model", "llama3-8b") == "llama3-70b" else llama.LLAMA3_8B
+    cfg = dataclasses.replace(base, layers=args.layers or base.layers)
     prompt = torch.arange(1, 33, device=device)
     if impl == "ours":
-        model = llama.Llama(cfg, llama.linear4bit_factory(device, torch.bfloat16, "nf4"), device, torch.bfloat16)
+        model = llama.Llama(cfg, llama.linear4bit_factory(device, torch.bfloat16, "nf4", tp_rank=rank, tp=world), device, torch.bfloat16,
+                            tp=world)
+        if world > 1:
+            from quantizations_b200 import tp as tpmod
+
+            model.fused_ar = None if args.nccl_allreduce else tpmod.FusedAllReduce(cfg.hidden, device=device)
         ctx, graph = torch.cuda.stream(torch.cuda.Stream(device=device)), True
     else:
         from oracle import ref_linear
@@ -508,10 +521,19 @@ def decode_tok_s(args, device, impl):
         ctx, graph = torch.cuda.stream(torch.cuda.default_stream(device)), False
     with ctx:
         model.generate(prompt, 8, use_graph=False)
-        best = min(model.generate(prompt, 60, use_graph=graph)[1] for _ in range(3))
+        times = []
+        for _ in range(3):
+            dt = model.generate(prompt, 60, use_graph=graph)[1]
+            if world > 1:
+                t = torch.tensor([dt], device=device, dtype=torch.float64)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                dt = float(t.item())
+            times.append(dt)
+        best = min(times)
     return {"tok_s": round(60 / best, 1), "ms_per_token": round(best / 60 * 1e3, 3),
-            "config": f"Llama-3-8B shapes, {cfg.layers} layers, random-init, NF4 + double-quant Linear4bit, bf16, bs=1, 32-token prompt, "
-                      f"60 new tokens, greedy, {'CUDA-graph decode step' if graph else 'eager (legacy default stream)'}"}
+            "config": f"Llama-3 hidden {cfg.hidden} shapes, {cfg.layers} layers, random-init, NF4 + double-quant Linear4bit, bf16, bs=1, 32-token "
+                      f"prompt, 60 new tokens, greedy, {'CUDA-graph decode step' if graph else 'eager (legacy default stream)'}"
+                      + (f", tensor-parallel tp{world} ({'NCCL all-reduce' if model.fused_ar is None else 'all-reduce fused into the o_proj / down_proj epilogues'})" if world > 1 else "")}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle/ port)
@@ -692,7 +714,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))  # a rank that went missing fails the run fast
     try:
         res = run_ours(args, rank, world, device)
         if rank == 0:

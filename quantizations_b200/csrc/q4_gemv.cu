@@ -382,6 +382,10 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             const int grid = plan_grid(a.rt_total, a.kt);
             // exact prefetch hint: how the next launch will split ITS rows, and how many row tiles each of its CTAs loads before its
             // activation exists (kBuffers tiles per warp, k fastest: ceil(kBuffers * warps / kt) row tiles)
+            if (a.next && pro && pro->next_K > 0 && !(pro->next_K >= 512 && (pro->next_K % 512) == 0 && a.next_bytes % (pro->next_K * 4) == 0)) {
+                a.next = nullptr;  // a hint with in_features the head computation does not cover (ragged k tiles): no prefetch rather than
+                a.next_bytes = 0;  // the whole-range one
+            }
             if (a.next && pro && pro->next_K >= 512 && (pro->next_K % 512) == 0 && a.next_bytes % (pro->next_K * 4) == 0) {
                 const int64_t nK = pro->next_K, nrows = a.next_bytes * 2 / nK;
                 const int nkt = (int)(nK / 512), nrt = (int)(nrows / 8);
