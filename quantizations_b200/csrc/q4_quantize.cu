@@ -153,12 +153,15 @@ template <int QT> __device__ __forceinline__ uint32_t encode_lut(uint32_t lut_la
     }
 }
 
-template <typename T, int BS, int QT>
+template <typename T, int BS, int QT, int EPT>
 __global__ void __launch_bounds__(256, 4)
 quantize_4bit_lut_kernel(const T* __restrict__ A, float* __restrict__ absmax, uint8_t* __restrict__ out, int64_t ngroups)
 {
-    constexpr int TPB = BS / 8;  // lanes that share one quantization block (<= 32)
-    constexpr int UNROLL = sizeof(T) == 2 ? 4 : 2;
+    // A thread owns EPT consecutive elements (16 for 16-bit inputs: 32 bytes in, 8 bytes out, one reciprocal per 16 elements and
+    // only log2(BS/16) shuffles for the block maximum; 8 for fp32 inputs or when n is not a multiple of 16).
+    constexpr int TPB = BS / EPT;                         // lanes that share one quantization block (<= 32)
+    constexpr int W = EPT * (int)sizeof(T) / 4;           // 32-bit words a thread loads per group (4 or 8)
+    constexpr int UNROLL = W == 8 ? 2 : 4;                // 64 bytes in flight per thread
     extern __shared__ __align__(16) uint8_t enc_smem[];
     for (int b = threadIdx.x; b < Q4_ENC_BINS; b += 256) {  // replica 0 of every bin ...
         float thr;
@@ -172,17 +175,28 @@ quantize_4bit_lut_kernel(const T* __restrict__ A, float* __restrict__ absmax, ui
     __syncthreads();
     const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(enc_smem) + (threadIdx.x & 15) * 8 - 0x80000000u;
 
+    auto elem = [](const uint32_t (&raw)[W], int j) -> float {
+        if constexpr (sizeof(T) == 4) return __uint_as_float(raw[j]);
+        else {
+            const float2 p = unpack2<T>(raw[j >> 1]);
+            return (j & 1) ? p.y : p.x;
+        }
+    };
     const int64_t nchunks = (ngroups + 255) / 256;
     for (int64_t c0 = (int64_t)blockIdx.x * UNROLL; c0 < nchunks; c0 += (int64_t)gridDim.x * UNROLL) {
-        float v[UNROLL][8];
+        uint32_t raw[UNROLL][W];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t g = (c0 + u) * 256 + threadIdx.x;
-            if (g < ngroups) {
-                load8<T>(A, g * 8, g * 8 + 8, v[u]);
-            } else {
 #pragma unroll
-                for (int j = 0; j < 8; j++) v[u][j] = 0.0f;  // out-of-range slots read as 0 (kernels.cu:410)
+            for (int j = 0; j < W; j++) raw[u][j] = 0;  // out-of-range slots read as 0 (kernels.cu:410)
+            if (g < ngroups) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(A) + g * (W * 4);
+#pragma unroll
+                for (int h = 0; h < W / 4; h++) {
+                    const uint4 q4v = ldg_stream_128(src + 16 * h);
+                    raw[u][4 * h] = q4v.x; raw[u][4 * h + 1] = q4v.y; raw[u][4 * h + 2] = q4v.z; raw[u][4 * h + 3] = q4v.w;
+                }
             }
         }
 #pragma unroll
@@ -190,25 +204,28 @@ quantize_4bit_lut_kernel(const T* __restrict__ A, float* __restrict__ absmax, ui
             const int64_t g = (c0 + u) * 256 + threadIdx.x;
             float m = -FLT_MAX;
 #pragma unroll
-            for (int j = 0; j < 8; j++) m = fmaxf(m, fabsf(v[u][j]));
+            for (int j = 0; j < EPT; j++) m = fmaxf(m, fabsf(elem(raw[u], j)));
 #pragma unroll
             for (int o = TPB / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (g >= ngroups) continue;
             if ((threadIdx.x & (TPB - 1)) == 0) absmax[g / TPB] = m;
             const float inv = __fdiv_rn(1.0f, m);  // IEEE divide, kernels.cu:438
-            uint32_t word = 0;
+            uint32_t word[EPT / 8];
+#pragma unroll
+            for (int h = 0; h < EPT / 8; h++) word[h] = 0;
             if (m >= FLT_MIN && m <= FLT_MAX) {  // |v * inv| <= 1 + 2^-23 (or v is NaN): the binned encoder's domain
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    word |= encode_lut<QT>(lut_lane, __fmul_rn(v[u][j], inv)) << (8 * (j >> 1) + ((j & 1) ? 0 : 4));
+                for (int j = 0; j < EPT; j++)
+                    word[j >> 3] |= encode_lut<QT>(lut_lane, __fmul_rn(elem(raw[u], j), inv)) << (8 * ((j & 7) >> 1) + ((j & 1) ? 0 : 4));
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float xn = __fmul_rn(v[u][j], inv);
-                    word |= (QT == Q4_NF4 ? encode_nf4(xn) : encode_fp4(xn)) << (8 * (j >> 1) + ((j & 1) ? 0 : 4));
+                for (int j = 0; j < EPT; j++) {
+                    const float xn = __fmul_rn(elem(raw[u], j), inv);
+                    word[j >> 3] |= (QT == Q4_NF4 ? encode_nf4(xn) : encode_fp4(xn)) << (8 * ((j & 7) >> 1) + ((j & 1) ? 0 : 4));
                 }
             }
-            *reinterpret_cast<uint32_t*>(out + g * 4) = word;
+            if constexpr (EPT == 16) *reinterpret_cast<uint2*>(out + g * 8) = make_uint2(word[0], word[1]);
+            else *reinterpret_cast<uint32_t*>(out + g * 4) = word[0];
         }
     }
 }
@@ -221,22 +238,30 @@ static int launch_quantize(const float* code, const T* A, float* absmax, uint8_t
     const int64_t nblocks = (n + blocksize - 1) / blocksize;
     if constexpr (QT != Q4_GENERAL8BIT) {
         if ((n & 7) == 0 && blocksize <= 256) {
-            const int64_t ngroups = n / 8;
-            constexpr int UNROLL = sizeof(T) == 2 ? 4 : 2;
-            const int64_t want = (ngroups + 256 * UNROLL - 1) / (256 * UNROLL);
+            // 16 elements per thread for 16-bit inputs (n % 16 == 0, 8-byte aligned output), else 8
+            const bool wide = sizeof(T) == 2 && (n & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+            const int64_t ngroups = wide ? n / 16 : n / 8;
+            const int unroll = (wide || sizeof(T) == 4) ? 2 : 4;
+            const int64_t want = (ngroups + 256 * unroll - 1) / (256 * unroll);
             const int64_t cap = (int64_t)sm_count() * 4;
             const unsigned grid = (unsigned)(want < cap ? want : cap);
-#define Q4_LUT_CASE(BS)                                                                                                   \
-    case BS: {                                                                                                            \
+#define Q4_LUT_LAUNCH(BS, EPT)                                                                                            \
+    {                                                                                                                     \
         static bool attr = false;                                                                                         \
         if (!attr) {                                                                                                      \
-            cudaError_t e = cudaFuncSetAttribute(quantize_4bit_lut_kernel<T, BS, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncLutBytes); \
+            cudaError_t e = cudaFuncSetAttribute(quantize_4bit_lut_kernel<T, BS, QT, EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncLutBytes); \
             if (e != cudaSuccess) return (int)e;                                                                          \
             attr = true;                                                                                                  \
         }                                                                                                                 \
-        quantize_4bit_lut_kernel<T, BS, QT><<<grid, 256, kEncLutBytes, stream>>>(A, absmax, out, ngroups);               \
+        quantize_4bit_lut_kernel<T, BS, QT, EPT><<<grid, 256, kEncLutBytes, stream>>>(A, absmax, out, ngroups);          \
         return finish_launch();                                                                                           \
     }
+#define Q4_LUT_CASE(BS)                                                                                                   \
+    case BS:                                                                                                              \
+        if constexpr (sizeof(T) == 2) {                                                                                   \
+            if (wide) Q4_LUT_LAUNCH(BS, 16)                                                                               \
+        }                                                                                                                 \
+        Q4_LUT_LAUNCH(BS, 8)
             switch (blocksize) {
                 Q4_LUT_CASE(64)
                 Q4_LUT_CASE(128)
@@ -244,6 +269,7 @@ static int launch_quantize(const float* code, const T* A, float* absmax, uint8_t
                 default: break;
             }
 #undef Q4_LUT_CASE
+#undef Q4_LUT_LAUNCH
         }
     }
 #define Q4_CASE(BS)                                                                                              \
