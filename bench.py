@@ -13,6 +13,10 @@ value           device-timed (CUDA events around K graph replays), inputs reside
 e2e             the same step through the public Python API (Linear4bit.forward under quantizations_b200.graphs), with
                 the activations copied from pinned host memory and the outputs copied back inside the timed region
 roofline        the GEMV kernel: algorithmic bytes per launch / average launch duration vs MEASURED_PEAKS.json hbm_gbs
+                (roofline.traffic: DRAM bytes per launch from the committed ncu launch list, profiles/gemv_traffic.json)
+blockwise       the path's other two HBM-bound kernels, quantize and dequantize of a 14336x4096 weight (kernel-only, N = 1)
+decode          whole-model batch-1 greedy decode tok/s in the quantizations_b200.llama harness (CUDA-graph step); with
+                --gpus N the model is tensor-parallel over the ranks (all-reduces fused into the GEMV epilogues)
 cpu_baseline    oracle/q4_torch_cpu.py (torch-CPU dequantize -> matmul port) on the box's host cores, bounded sample
 --impl reference   the reference's own kernels (oracle/_ref, built from /root/reference for sm_100a) driven with the
                 reference's gemv_4bit call sequence (core.py:467-499) on the same workload
