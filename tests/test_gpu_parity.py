@@ -532,6 +532,55 @@ def test_fused_decode_glue_matches_separate_torch_ops(q, dtype):
     assert torch.equal(q.gemv_4bit_fused(x, packed, state), q.gemv_4bit(x, packed, state=state))
 
 
+@pytest.mark.parametrize("next_shape", [(4096, 4096), (28672, 4096), (4096, 14336), (1024, 1792), (8, 512), (300, 2048)])
+def test_prefetch_hint_never_changes_the_result(q, next_shape):
+    """q4_gemv_fused_t.prefetch / prefetch_K is a hint: whatever the next weight looks like (more or fewer row tiles than CTAs,
+    ragged k tiles -> the hint is dropped, a bare tensor -> the whole-range form), the output is bit-identical."""
+    torch.manual_seed(11)
+    N, K = 4096, 4096
+    W = (torch.randn(N, K, device=DEV) * 0.02).to(torch.bfloat16)
+    packed, state = q.quantize_4bit(W, quant_type="nf4")
+    x = torch.randn(1, 1, K, device=DEV, dtype=torch.bfloat16)
+    nN, nK = next_shape
+    nxt = torch.randint(0, 255, (nN * nK // 2, 1), device=DEV, dtype=torch.uint8)
+    want = q.gemv_4bit_fused(x, packed, state)
+    for hint in ((nxt, nK), nxt, (nxt, 0)):
+        got = q.gemv_4bit_fused(x, packed, state, prefetch=hint)
+        assert torch.equal(got, want)
+        assert torch.equal(q.gemv_4bit(x, packed, state=state, flags=q._lib.Q4_GEMV_PDL, prefetch=hint), want)
+    torch.cuda.synchronize()
+
+
+def test_linear4bit_cached_descriptor_follows_the_weight(q):
+    """Linear4bit.forward keeps a cached launch descriptor for single-vector calls; it must notice a new weight, a changed launch
+    flag, a prefetch hint and another activation dtype, and must agree with core.gemv_4bit every time."""
+    torch.manual_seed(12)
+    K, N = 1024, 512
+    lin = q.Linear4bit(K, N, bias=True, compute_dtype=torch.bfloat16, quant_type="nf4")
+    W1 = (torch.randn(N, K) * 0.02).to(torch.bfloat16)
+    lin.weight = q.Params4bit(W1, requires_grad=False, quant_type="nf4", module=lin)
+    lin.bias.data = torch.randn(N).to(torch.bfloat16)
+    lin = lin.to(DEV)
+    x = torch.randn(1, 1, K, device=DEV, dtype=torch.bfloat16)
+
+    def direct():
+        return q.gemv_4bit(x, lin.weight.data, state=lin.weight.quant_state, bias=lin.bias, flags=lin.gemv_flags)
+
+    y1 = lin(x)
+    assert torch.equal(y1, direct()) and torch.equal(lin(x), y1)
+    lin.gemv_flags = 0
+    assert torch.equal(lin(x), direct())
+    lin.prefetch_next = (lin.weight.data, K)
+    assert torch.equal(lin(x), y1)
+    W2 = (torch.randn(N, K) * 0.02).to(torch.bfloat16)
+    lin.weight = q.Params4bit(W2, requires_grad=False, quant_type="fp4", module=lin).to(DEV)
+    y2 = lin(x)
+    assert torch.equal(y2, direct()) and not torch.equal(y2, y1)
+    xh = x.to(torch.float16)   # fp16 input keeps the configured bf16 compute dtype (reference modules.py:112-122): cast in, cast out
+    yh = lin(xh)
+    assert yh.dtype == torch.float16 and torch.equal(yh, lin(xh.to(torch.bfloat16)).to(torch.float16))
+
+
 @pytest.mark.parametrize("shape", [(4096, 4096), (14336, 4096), (4096, 14336), (1000, 512), (136, 256)])
 @pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
 def test_tcgen05_gemv_matches_mma_sync_gemv(q, shape, dtype):
