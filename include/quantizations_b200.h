@@ -109,7 +109,7 @@ int q4_dequantize_blockwise_4bit(const uint8_t* A, const q4_absmax_t* stats, voi
  * prefetch / prefetch_bytes (optional, NULL / 0): a byte range that the NEXT call will stream (typically the packed
  * weight of the following Linear4bit).  It is pulled into the 126 MB L2 with TMA bulk prefetches while this call
  * computes, so HBM never idles between dependent launches.  Purely a hint: results do not depend on it. */
-enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2, Q4_GEMV_SHARE_SM = 4, Q4_ATTN_EARLY_CACHE = 8 };
+enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2, Q4_GEMV_SHARE_SM = 4, Q4_ATTN_EARLY_CACHE = 8, Q4_GEMV_SWIGLU = 16 };
 int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias,
                  void* out, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* prefetch,
                  int64_t prefetch_bytes, void* stream);
@@ -146,7 +146,12 @@ typedef struct q4_allreduce_t {
  *   x_gate     : the activation is silu(x_gate[k]) * x[k]  (SwiGLU: x = up-projection output, x_gate = gate output)
  *   bias       : added to the output; it may alias `out`, which makes it a residual stream updated in place
  *   nmat > 1   : grouped launch, see q4_gemv_4bit_grouped (offsets / row_end as there; NULL for a single matrix)
- * so a decoder layer's Linear4bit work is four launches: norm+qkv, o+residual, norm+gate/up, swiglu+down+residual.
+ *   flags & Q4_GEMV_SWIGLU (q4_gemv_4bit_fused only): nmat == 2 and the two matrices (gate, up; equally long) are stored
+ *                INTERLEAVED in chunks of 4 rows -- rows 8t..8t+3 of B / of the statistics are gate rows 4t..4t+3, rows 8t+4..8t+7
+ *                the up rows 4t..4t+3 (4 rows x K/64 blocks must be a multiple of blocksize2, i.e. K % 4096 == 0 for the usual
+ *                64 / 256) -- and the launch stores out[j] = silu(gate_j) * up_j for j in [0, rows/2): every CTA owns both halves of
+ *                its outputs, so SwiGLU costs nothing and the down projection stages a plain vector.  No bias / allreduce.
+ * so a decoder layer's Linear4bit work is four launches: norm+qkv, o+residual, norm+gate/up(+swiglu), (swiglu+)down+residual.
  * fp16/bf16 activations, blocksize 64, K % 64 == 0; with rms_weight K <= 16384. */
 typedef struct q4_gemv_fused_t {
     const void* x;

@@ -690,10 +690,17 @@ def gemv_4bit_fused(
     for t in (gate, rms_weight):
         if t is not None and (t.dtype != A.dtype or t.numel() != K):
             raise ValueError("gate / rms_weight must match the activation's dtype and length")
+    out_rows = rows
+    if flags & _lib.Q4_GEMV_SWIGLU:  # interleaved (gate, up) pair: the launch stores silu(gate) * up
+        if group is None or not getattr(group, "swiglu", False) or residual is not None or allreduce is not None:
+            raise ValueError("Q4_GEMV_SWIGLU needs a SwiGLU Linear4bitGroup and no residual / allreduce")
+        out_rows = rows // 2
     if residual is not None and (residual.dtype != A.dtype or residual.numel() != rows):
         raise ValueError("residual must match the output's dtype and length")
     if out is None:
-        out = torch.empty(A.shape[:-1] + (rows,), dtype=A.dtype, device=A.device)
+        out = torch.empty(A.shape[:-1] + (out_rows,), dtype=A.dtype, device=A.device)
+    elif out.numel() != out_rows or out.dtype != A.dtype:
+        raise ValueError("out must match the output's dtype and length")
     f = _lib.GemvFused(
         A.data_ptr(), None if gate is None else gate.data_ptr(), None if rms_weight is None else rms_weight.data_ptr(), float(rms_eps),
         packed.data_ptr(), ctypes.pointer(stats), offsets, row_end, nmat, code.data_ptr(),

@@ -200,7 +200,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         }
         static const int env_impl = getenv("Q4_GEMV_IMPL") ? atoi(getenv("Q4_GEMV_IMPL")) : 0;  // 1: force the mma.sync kernel
         // tcgen05 kernel (q4_gemv_tc.cuh): needs the prebuilt table image and the split-K workspace
-        if (fast && env_impl != 1 && !stage_out && pro && pro->lut && pro->workspace && !pro->ar && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&
+        if (fast && env_impl != 1 && !stage_out && !(flags & Q4_GEMV_SWIGLU) && pro && pro->lut && pro->workspace && !pro->ar && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&
             (reinterpret_cast<uintptr_t>(pro->workspace) & 15) == 0) {
             const int bpr = (int)(K / 64);
             const int rt_total = (int)((N + kTcRows - 1) / kTcRows);
@@ -339,6 +339,12 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
             static const int env_debug_mma = getenv("Q4_GEMV_DEBUG") ? atoi(getenv("Q4_GEMV_DEBUG")) : 0;
             a.debug = env_debug_mma;
             a.multi = multi ? 1 : 0;
+            if (flags & Q4_GEMV_SWIGLU) {
+                // interleaved gate/up pair: whole 8-row tiles, the two members equally long, nothing else in the epilogue
+                if (nmat != 2 || (N % 8) != 0 || !row_end || row_end[0] * 2 != N || bias || (pro && pro->ar && pro->ar->world > 1) || stage_out)
+                    return Q4_ERR_SHAPE;
+                a.swiglu = 1;
+            }
             if (stage_out) {  // q4_gemv_4bit_chain: hand the prepared stage back instead of launching it
                 stage_out->a = a;
                 stage_out->nested = nested;
@@ -416,7 +422,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
         }
     }
     if (stage_out) return kStageNotChainable;
-    if (nmat > 1 || (pro && (pro->x_gate || pro->rms_weight || (pro->ar && pro->ar->world > 1)))) return Q4_ERR_SHAPE;  // only the fast path groups / fuses
+    if (nmat > 1 || (flags & Q4_GEMV_SWIGLU) || (pro && (pro->x_gate || pro->rms_weight || (pro->ar && pro->ar->world > 1)))) return Q4_ERR_SHAPE;  // only the fast path groups / fuses
     // generic: x as fp32 in shared memory
     const size_t smem = 128 + sizeof(float) * (size_t)K;
     if (smem > 200 * 1024) return Q4_ERR_SHAPE;

@@ -70,6 +70,8 @@ struct MmaGemvArgs {
     long long pw_step, pw_wrap;
     int ab_step, ab_wrap, d_rt, d_kt;
     int multi;  // grouped launch with per-matrix offsets (nested statistics)
+    int swiglu; // Q4_GEMV_SWIGLU: two matrices (gate, up) interleaved in chunks of 4 rows -- rows 8t..8t+3 are gate rows 4t..4t+3, rows
+                // 8t+4..8t+7 the up rows of the same index -- and the launch stores silu(gate) * up [rows / 2] instead of the rows
     int rt_q, rt_r;  // rt_total / grid, rt_total % grid: CTA b owns row tiles [b*rt_q + min(b, rt_r), ...) -- no division on the device
     // exact prefetch hint (nx_grid > 0): the NEXT launch runs nx_grid CTAs over `next`, CTA j owning row tiles
     // [j*nx_rt_q + min(j, nx_rt_r), ...) of nx_tile_bytes each and loading the first nx_head of them before its activation exists
@@ -557,7 +559,8 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
             float o = off[0];
             if (MULTI) {
                 const int row = (rt0 + c.rt) * 8 + g;
-                o = row < a.row_end[0] ? off[0] : (row < a.row_end[1] ? off[1] : (row < a.row_end[2] ? off[2] : off[3]));
+                if (a.swiglu) o = (g & 4) ? off[1] : off[0];  // 8-row tiles are aligned to the 4 + 4 interleave
+                else o = row < a.row_end[0] ? off[0] : (row < a.row_end[1] ? off[1] : (row < a.row_end[2] ? off[2] : off[3]));
             }
             const float q0 = __uint_as_float(lut_lookup<0, kImm + 128>(r.q, lane_base));
             const float q1 = __uint_as_float(lut_lookup<1, kImm + 128>(r.q, lane_base));
@@ -647,6 +650,18 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
                 total += __uint_as_float(v);
             }
             finish(i, total);
+        }
+    } else if (a.swiglu) {
+        // SwiGLU in the epilogue: every 8-row tile holds four (gate, up) pairs, so this CTA owns both halves of each of its outputs.
+        // Rounded exactly as the separate steps would: gate and up to T (what the plain launch stores), silu(gate) to T, the product
+        // to T -- the same expressions as stage_x_fused, hence bit-identical to "grouped gate/up launch, then SwiGLU staging".
+        T* hout = reinterpret_cast<T*>(a.out);
+        for (int i = tid; i < (nrows >> 1); i += nthr) {
+            const int t8 = (i >> 2) * 8, m = i & 3;
+            const float gq = Elem<T>::to_f32(Elem<T>::from_f32(row_total(t8 + m)));
+            const float uq = Elem<T>::to_f32(Elem<T>::from_f32(row_total(t8 + 4 + m)));
+            const float sg = Elem<T>::to_f32(Elem<T>::from_f32(__fdividef(gq, 1.0f + __expf(-gq))));
+            hout[(row_lo >> 1) + i] = Elem<T>::from_f32(sg * uq);
         }
     } else {
         for (int i = tid; i < nrows; i += nthr) finish(i, row_total(i));

@@ -57,15 +57,19 @@ class DecoderLayer(nn.Module):
         self.ln1 = nn.Parameter(torch.ones(h))
         self.ln2 = nn.Parameter(torch.ones(h))
         # siblings that read the same activation are served by one grouped decode launch when they are Linear4bit
-        self.qkv = self.gate_up = None
+        self.qkv = self.gate_up = self.gate_up_sw = None
         try:
             from .modules import Linear4bit, Linear4bitGroup
 
             if all(isinstance(m, Linear4bit) for m in (self.q_proj, self.k_proj, self.v_proj, self.gate_proj, self.up_proj)):
                 self.qkv = Linear4bitGroup([self.q_proj, self.k_proj, self.v_proj])
                 self.gate_up = Linear4bitGroup([self.gate_proj, self.up_proj])
+                try:  # decode: silu(gate) * up straight out of the gate/up launch (an interleaved second copy of the pair)
+                    self.gate_up_sw = Linear4bitGroup([self.gate_proj, self.up_proj], swiglu=True)
+                except ValueError:
+                    self.gate_up_sw = None
         except ValueError:
-            self.qkv = self.gate_up = None
+            self.qkv = self.gate_up = self.gate_up_sw = None
 
 
 class Llama(nn.Module):
@@ -74,6 +78,7 @@ class Llama(nn.Module):
         self.cfg, self.tp, self.group, self.dtype = cfg, tp, group, dtype
         self.fuse_glue = True  # fold RMSNorm / SwiGLU / residual adds into the decode GEMV launches (Linear4bit layers only)
         self.fused_ar = None   # tp.FusedAllReduce: the row-parallel all-reduce inside the GEMV epilogue instead of NCCL
+        self.fuse_swiglu = False  # decode: silu(gate) * up in the gate/up launch's epilogue (layers whose gate_up_sw group exists)
         self.fuse_attn = cfg.head_dim == 128  # decode: RoPE + KV append + attention as one launch (q4_decode_attention)
         # the decode step's attention launch reads `pos`, cos / sin and the cache rows of EARLIER steps while the q/k/v GEMV before
         # it is still running (only the new token's q/k/v depend on that GEMV)
@@ -154,7 +159,14 @@ class Llama(nn.Module):
                 # activation staging, residual again in its epilogue: four launches for the layer's seven Linears + glue
                 qs = L.o_proj.weight.quant_state
                 nxt = self.layers[li + 1].qkv if li + 1 < len(self.layers) else None
-                x = gemv_4bit_fused(a, L.o_proj.weight.data, qs, residual=x, allreduce=self.fused_ar, prefetch=self._hint(L.gate_up))
+                sw = L.gate_up_sw if self.fuse_swiglu else None
+                x = gemv_4bit_fused(a, L.o_proj.weight.data, qs, residual=x, allreduce=self.fused_ar,
+                                    prefetch=self._hint(sw if sw is not None else L.gate_up))
+                if sw is not None:  # SwiGLU in the gate/up epilogue: down_proj stages a plain vector
+                    hmid = sw.forward_swiglu(x, rms_weight=L.ln2, rms_eps=cfg.eps, prefetch_override=self._hint(L.down_proj))
+                    x = gemv_4bit_fused(hmid, L.down_proj.weight.data, L.down_proj.weight.quant_state, residual=x,
+                                        allreduce=self.fused_ar, prefetch=self._hint(nxt))
+                    continue
                 g, u = gemv_4bit_fused(x, None, group=L.gate_up, rms_weight=L.ln2, rms_eps=cfg.eps,
                                        prefetch=self._hint(L.down_proj)).split(L.gate_up.splits, dim=-1)
                 x = gemv_4bit_fused(u, L.down_proj.weight.data, L.down_proj.weight.quant_state, gate=g, residual=x,

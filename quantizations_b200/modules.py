@@ -183,12 +183,21 @@ class Linear4bitGroup(nn.Module):
     N_i * K / 64 a multiple of 256 so that no second-level block straddles two members.
     """
 
-    def __init__(self, linears):
+    def __init__(self, linears, swiglu: bool = False):
+        """swiglu=True (two equally shaped members: gate, up): a SECOND copy of the pair is laid out interleaved in chunks of four
+        rows (rows 8t..8t+3 = gate rows 4t..4t+3, rows 8t+4..8t+7 = up rows 4t..4t+3; packed bytes, 8-bit absmax codes and
+        second-level absmax alike), which lets `forward_swiglu` return silu(gate(x)) * up(x) from ONE launch: every CTA then owns
+        both halves of its outputs (q4_gemv_fused_t flags & Q4_GEMV_SWIGLU).  The members keep their own storage for the other
+        paths (prefill), so the pair costs twice its packed size."""
         super().__init__()
         import ctypes
 
         from ._lib import AbsmaxStats
 
+        self.swiglu = bool(swiglu)
+        if self.swiglu:
+            self._init_swiglu(linears)
+            return
         self.members = nn.ModuleList(linears)
         first = linears[0].weight.quant_state
         K = linears[0].in_features
@@ -239,6 +248,55 @@ class Linear4bitGroup(nn.Module):
         self.prefetch_next = None
         self.device_ = dev
 
+    def _init_swiglu(self, linears):
+        import ctypes
+
+        from ._lib import AbsmaxStats
+
+        if len(linears) != 2:
+            raise ValueError("a SwiGLU group has exactly two members (gate, up)")
+        gate, up = linears
+        self.members = nn.ModuleList(linears)
+        qg, qu = gate.weight.quant_state, up.weight.quant_state
+        K, N = gate.in_features, gate.out_features
+        if qg is None or qu is None or up.in_features != K or up.out_features != N or qg.blocksize != 64 or qu.blocksize != 64 \
+                or qg.quant_type != qu.quant_type or qg.nested != qu.nested or gate.bias is not None or up.bias is not None:
+            raise ValueError("SwiGLU group members must be quantised alike, equally shaped, without bias")
+        nested = qg.nested
+        per4 = 4 * K // 64                       # 64-wide blocks in a 4-row chunk
+        if N % 4 or K % 64 or (nested and (per4 % qg.state2.blocksize or qg.state2.blocksize != qu.state2.blocksize)):
+            raise ValueError("interleaving needs out_features % 4 == 0 and 4 rows to hold whole second-level blocks (in_features % 4096 == 0)")
+
+        def weave(a, b, width):                  # [N/4 chunks, width] each -> chunks alternating a, b
+            return torch.stack((a.reshape(N // 4, width), b.reshape(N // 4, width)), dim=1).reshape(-1)
+
+        self.in_features, self.splits, self.out_features = K, [N, N], 2 * N
+        self.packed = weave(gate.weight.data.reshape(-1), up.weight.data.reshape(-1), 4 * K // 2).reshape(-1, 1)
+        self.absmax = weave(qg.absmax, qu.absmax, per4)
+        self.code, self.blocksize, self.nested = qg.code, 64, nested
+        if nested:
+            self.absmax2 = weave(qg.state2.absmax, qu.state2.absmax, per4 // qg.state2.blocksize)
+            self._stats = AbsmaxStats(None, self.absmax.data_ptr(), qg.state2.code.data_ptr(), self.absmax2.data_ptr(),
+                                      qg.offset.data_ptr(), int(qg.state2.blocksize))
+            self._offsets = (ctypes.c_void_p * 2)(qg.offset.data_ptr(), qu.offset.data_ptr())
+        else:
+            self.absmax2 = None
+            self._stats = AbsmaxStats(self.absmax.data_ptr(), None, None, None, None, 0)
+            self._offsets = None
+        self._row_end = (ctypes.c_int * 2)(N, 2 * N)
+        self.gemv_flags = _lib.Q4_GEMV_PDL
+        self.prefetch_next = None
+        self.device_ = gate.weight.device
+
+    def forward_swiglu(self, x: torch.Tensor, out: torch.Tensor = None, prefetch_override=None, **kw) -> torch.Tensor:
+        """[.., K] single vector -> silu(gate(x)) * up(x)  [.., N], one launch (optionally with the RMSNorm fused in: rms_weight=)."""
+        from .core import gemv_4bit_fused
+
+        if not self.swiglu:
+            raise ValueError("not a SwiGLU group")
+        return gemv_4bit_fused(x, None, group=self, out=out, flags=self.gemv_flags | _lib.Q4_GEMV_SWIGLU,
+                               prefetch=prefetch_override if prefetch_override is not None else self.prefetch_next, **kw)
+
     def lut(self, dtype):
         """Decode table image shared by the members (same code tables by construction)."""
         return self.members[0].weight.quant_state.lut(dtype)
@@ -247,10 +305,15 @@ class Linear4bitGroup(nn.Module):
         """[.., K] single vector -> [.., sum N_i] (concatenated member outputs)."""
         from .core import gemv_4bit_fused
 
+        if self.swiglu:
+            raise ValueError("a SwiGLU group's rows are interleaved: use forward_swiglu")
+
         return gemv_4bit_fused(x, None, group=self, out=out, flags=self.gemv_flags, prefetch=self.prefetch_next)
 
     def forward(self, x: torch.Tensor):
         """Returns one output per member, like calling them in turn."""
+        if self.swiglu:  # the interleaved copy only serves forward_swiglu
+            return tuple(lin(x) for lin in self.members)
         if x.numel() == x.shape[-1] and x.dtype in (torch.float16, torch.bfloat16) and x.is_contiguous():
             return self.forward_fused(x).split(self.splits, dim=-1)
         return tuple(lin(x) for lin in self.members)

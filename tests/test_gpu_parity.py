@@ -532,6 +532,47 @@ def test_fused_decode_glue_matches_separate_torch_ops(q, dtype):
     assert torch.equal(q.gemv_4bit_fused(x, packed, state), q.gemv_4bit(x, packed, state=state))
 
 
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+@pytest.mark.parametrize("nested", [True, False])
+@pytest.mark.parametrize("N,K", [(14336, 4096), (1792, 4096), (512, 8192), (8, 4096)])
+def test_swiglu_group_equals_grouped_launch_then_swiglu_staging(q, dtype, nested, N, K):
+    """Linear4bitGroup(swiglu=True).forward_swiglu: gate / up rows interleaved in chunks of four, silu(gate) * up formed in the
+    launch's epilogue.  Same rounding steps as the grouped gate/up launch followed by the SwiGLU activation staging of the down
+    projection, so: bit-identical to silu-staging's input, and the down projection gives bit-identical outputs either way."""
+    torch.manual_seed(N + K)
+    dt = TDT[dtype]
+    lins = []
+    for i in range(2):
+        lin = q.Linear4bit(K, N, bias=False, compute_dtype=dt, quant_type="nf4", compress_statistics=nested)
+        lin.weight = q.Params4bit((torch.randn(N, K) * 0.02).to(dt), requires_grad=False, quant_type="nf4", module=lin,
+                                  compress_statistics=nested)
+        lins.append(lin.to(DEV))
+    down = q.Linear4bit(N, 256, bias=False, compute_dtype=dt, quant_type="nf4")
+    down.weight = q.Params4bit((torch.randn(256, N) * 0.02).to(dt), requires_grad=False, quant_type="nf4", module=down)
+    down = down.to(DEV)
+    x = torch.randn(1, 1, K, device=DEV, dtype=dt)
+    gamma = (1 + 0.1 * torch.randn(K, device=DEV)).to(dt)
+    sw = q.Linear4bitGroup(lins, swiglu=True)
+    g, u = lins[0](x), lins[1](x)
+    h = sw.forward_swiglu(x)
+    assert h.shape == (1, 1, N)
+    want = (torch.nn.functional.silu(g.float()).to(dt).float() * u.float()).to(dt)
+    assert (h.float() - want.float()).abs().max().item() <= 2e-2 * want.float().abs().max().item()
+    if N % 64 == 0:  # the down projection: plain staging of h == SwiGLU staging of (g, u), bit for bit
+        st = down.weight.quant_state
+        y_sw = q.gemv_4bit_fused(h, down.weight.data, st)
+        y_ref = q.gemv_4bit_fused(u, down.weight.data, st, gate=g)
+        assert torch.equal(y_sw, y_ref)
+    # with the RMSNorm fused in, against the unfused sequence
+    hn = sw.forward_swiglu(x, rms_weight=gamma, rms_eps=1e-5)
+    xn = torch.nn.functional.rms_norm(x, (K,), gamma, 1e-5)
+    wantn = (torch.nn.functional.silu(lins[0](xn).float()).to(dt).float() * lins[1](xn).float()).to(dt)
+    assert (hn.float() - wantn.float()).abs().max().item() <= 3e-2 * wantn.float().abs().max().item()
+    with pytest.raises(ValueError):
+        sw.forward_fused(x)
+    assert all(torch.equal(a, b) for a, b in zip(sw(x), (g, u)))
+
+
 @pytest.mark.parametrize("next_shape", [(4096, 4096), (28672, 4096), (4096, 14336), (1024, 1792), (8, 512), (300, 2048)])
 def test_prefetch_hint_never_changes_the_result(q, next_shape):
     """q4_gemv_fused_t.prefetch / prefetch_K is a hint: whatever the next weight looks like (more or fewer row tiles than CTAs,
