@@ -11,6 +11,7 @@ Tensor parallelism: q/k/v/gate/up column-parallel, o/down row-parall
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Optional
 
@@ -64,10 +65,13 @@ class DecoderLayer(nn.Module):
             if all(isinstance(m, Linear4bit) for m in (self.q_proj, self.k_proj, self.v_proj, self.gate_proj, self.up_proj)):
                 self.qkv = Linear4bitGroup([self.q_proj, self.k_proj, self.v_proj])
                 self.gate_up = Linear4bitGroup([self.gate_proj, self.up_proj])
-                try:  # decode: silu(gate) * up straight out of the gate/up launch (an interleaved second copy of the pair)
-                    self.gate_up_sw = Linear4bitGroup([self.gate_proj, self.up_proj], swiglu=True)
-                except ValueError:
-                    self.gate_up_sw = None
+                if os.environ.get("Q4_SWIGLU", "0") == "1":
+                    # opt-in: silu(gate) * up straight out of the gate/up launch, from an interleaved SECOND copy of the pair.
+                    # Measured 571 vs 566 tok/s on Llama-3-8B: not worth twice the gate/up memory by default.
+                    try:
+                        self.gate_up_sw = Linear4bitGroup([self.gate_proj, self.up_proj], swiglu=True)
+                    except ValueError:
+                        self.gate_up_sw = None
         except ValueError:
             self.qkv = self.gate_up = self.gate_up_sw = None
 
@@ -78,7 +82,7 @@ class Llama(nn.Module):
         self.cfg, self.tp, self.group, self.dtype = cfg, tp, group, dtype
         self.fuse_glue = True  # fold RMSNorm / SwiGLU / residual adds into the decode GEMV launches (Linear4bit layers only)
         self.fused_ar = None   # tp.FusedAllReduce: the row-parallel all-reduce inside the GEMV epilogue instead of NCCL
-        self.fuse_swiglu = False  # decode: silu(gate) * up in the gate/up launch's epilogue (layers whose gate_up_sw group exists)
+        self.fuse_swiglu = True  # decode: silu(gate) * up in the gate/up launch's epilogue (layers whose gate_up_sw group exists)
         self.fuse_attn = cfg.head_dim == 128  # decode: RoPE + KV append + attention as one launch (q4_decode_attention)
         # the decode step's attention launch reads `pos`, cos / sin and the cache rows of EARLIER steps while the q/k/v GEMV before
         # it is still running (only the new token's q/k/v depend on that GEMV)
