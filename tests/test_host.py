@@ -109,3 +109,49 @@ def test_binned_4bit_encoder_equals_compare_tree_on_every_float(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-fopenmp", os.path.join(root, "tests", "encode_lut_check.c"), "-lm", "-o", exe])
     r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+def _fake_quantised_linear(N, K, seed, nested=True):
+    """A Linear4bit whose packed bytes / statistics are arbitrary CPU tensors of the right shapes (layout logic only)."""
+    g = torch.Generator().manual_seed(seed)
+    lin = q.Linear4bit(K, N, bias=False, compute_dtype=torch.bfloat16, quant_type="nf4", device="meta")
+    nb = N * K // 64
+    packed = torch.randint(0, 256, (N * K // 2, 1), dtype=torch.uint8, generator=g)
+    code = q.get_4bit_type("nf4", device="cpu")
+    if nested:
+        s2 = q.QuantState(absmax=torch.rand(nb // 256, generator=g), code=q.create_dynamic_map(), blocksize=256, dtype=torch.float32)
+        qs = q.QuantState(absmax=torch.randint(0, 256, (nb,), dtype=torch.uint8, generator=g), shape=torch.Size((N, K)), code=code,
+                          blocksize=64, quant_type="nf4", dtype=torch.bfloat16, offset=torch.tensor(0.01 * seed), state2=s2)
+    else:
+        qs = q.QuantState(absmax=torch.rand(nb, generator=g), shape=torch.Size((N, K)), code=code, blocksize=64, quant_type="nf4",
+                          dtype=torch.bfloat16)
+    lin.weight = q.Params4bit(packed, requires_grad=False, quant_state=qs, quant_type="nf4", bnb_quantized=True, module=lin)
+    return lin
+
+
+@pytest.mark.parametrize("nested", [True, False])
+@pytest.mark.parametrize("N,K", [(16, 4096), (8, 8192)])
+def test_swiglu_group_interleaves_four_row_chunks(nested, N, K):
+    """Linear4bitGroup(swiglu=True): rows 8t..8t+3 of the shared buffers are gate rows 4t..4t+3, rows 8t+4..8t+7 the up rows --
+    packed bytes, block statistics and second-level statistics alike (what q4_gemv_fused_t's Q4_GEMV_SWIGLU flag expects)."""
+    gate, up = _fake_quantised_linear(N, K, 1, nested), _fake_quantised_linear(N, K, 2, nested)
+    grp = q.Linear4bitGroup([gate, up], swiglu=True)
+    assert grp.swiglu and grp.out_features == 2 * N and list(grp._row_end) == [N, 2 * N]
+    pk = grp.packed.view(2 * N, K // 2)
+    am = grp.absmax.view(2 * N, K // 64)
+    for r in range(2 * N):
+        src, row = (gate, up)[(r // 4) % 2], (r // 8) * 4 + r % 4
+        assert torch.equal(pk[r], src.weight.data.view(N, K // 2)[row])
+        assert torch.equal(am[r], src.weight.quant_state.absmax.view(N, K // 64)[row])
+    if nested:
+        per = 4 * K // 64 // 256   # second-level entries per 4-row chunk
+        a2 = grp.absmax2.view(2 * N // 4, per)
+        for c in range(2 * N // 4):
+            src = (gate, up)[c % 2]
+            assert torch.equal(a2[c], src.weight.quant_state.state2.absmax.view(N // 4, per)[c // 2])
+    # the members keep their own storage (prefill and the plain grouped launch do not see the interleaved copy)
+    assert gate.weight.data.data_ptr() != grp.packed.data_ptr()
+    with pytest.raises(ValueError):
+        q.Linear4bitGroup([gate, up, gate], swiglu=True)
+    with pytest.raises(ValueError):
+        q.Linear4bitGroup([gate, _fake_quantised_linear(N, 2048, 3, nested)], swiglu=True)
