@@ -129,7 +129,11 @@ def graph_generate(model: torch.nn.Module, input_ids: torch.Tensor, max_new_toke
 
     def step():
         o = model(tok, past_key_values=cache, cache_position=pos, use_cache=True)
-        tok.copy_(o.logits[:, -1].argmax(-1, keepdim=True))
+        lg = o.logits[:, -1]
+        if lg.is_cuda and lg.is_contiguous() and lg.dtype in core._DTYPE_CODE and (lg.data_ptr() & 15) == 0:
+            core.argmax(lg.view(-1), out=tok.view(-1))  # one ~3 us launch instead of torch's 40-us reduction over the vocabulary
+        else:
+            tok.copy_(lg.argmax(-1, keepdim=True))
         pos.add_(1)
 
     graph = None
