@@ -96,3 +96,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "q4_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_ctypes_structs_have_the_headers_layout(tmp_path):
+    """The Python mirror of q4_gemv_fused_t / q4_absmax_t / q4_allreduce_t (quantizations_b200/_lib.py) must have exactly the C
+    layout of include/quantizations_b200.h: compile a probe against the header and compare sizes and every field offset."""
+    import ctypes
+    import subprocess
+
+    from quantizations_b200 import _lib
+
+    structs = {"q4_gemv_fused_t": _lib.GemvFused, "q4_absmax_t": _lib.AbsmaxStats, "q4_allreduce_t": _lib.AllReduce}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "quantizations_b200.h")}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "probe")
+    subprocess.check_call(["gcc", "-std=c11", str(src), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out.strip().splitlines()}
+    for cname, cls in structs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, f"{cname}.{fname}"
