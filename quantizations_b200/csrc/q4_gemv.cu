@@ -131,10 +131,11 @@ struct MmaStage {
 constexpr int kStagePrepared = 1, kStageNotChainable = 2;  // positive returns of gemv_dispatch(..., stage_out)
 
 template <typename T, bool NESTED>
-static void* mma_kernel_ptr(bool compact, bool ktail, bool chain)
+static void* mma_kernel_ptr(bool compact, bool ktail, bool chain, bool swiglu)
 {
     using ChainT = void (*)(const MmaChainArgs);
     using KernT = void (*)(const MmaSingleArgs);
+    if (swiglu) return (compact && !ktail && !chain) ? (void*)(KernT)gemv_mma_kernel<T, NESTED, true, false, false, true> : nullptr;
     if (chain) return (void*)(ChainT)gemv_mma_kernel<T, NESTED, true, false, true>;  // chains: compact layout, no ragged shapes
     KernT k = compact ? (ktail ? (KernT)gemv_mma_kernel<T, NESTED, true, true, false> : (KernT)gemv_mma_kernel<T, NESTED, true, false, false>)
                       : (ktail ? (KernT)gemv_mma_kernel<T, NESTED, false, true, false> : (KernT)gemv_mma_kernel<T, NESTED, false, false, false>);
@@ -146,13 +147,15 @@ template <typename T>
 static int launch_mma(const MmaChainArgs& c, bool nested, bool compact, bool ktail, int grid, size_t smem, bool pdl, cudaStream_t stream)
 {
     const bool chain = c.n > 1;
-    void* kern = nested ? mma_kernel_ptr<T, true>(compact, ktail, chain) : mma_kernel_ptr<T, false>(compact, ktail, chain);
-    static bool attr_set[2][2][2][2] = {};
-    if (!attr_set[nested][compact][ktail][chain]) {
+    const bool swiglu = c.st[0].swiglu != 0;
+    void* kern = nested ? mma_kernel_ptr<T, true>(compact, ktail, chain, swiglu) : mma_kernel_ptr<T, false>(compact, ktail, chain, swiglu);
+    if (!kern) return Q4_ERR_SHAPE;  // the SwiGLU epilogue exists for the compact layout and whole tiles only
+    static bool attr_set[2][2][2][2][2] = {};
+    if (!attr_set[nested][compact][ktail][chain][swiglu]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        attr_set[nested][compact][ktail][chain] = true;
+        attr_set[nested][compact][ktail][chain][swiglu] = true;
     }
     if (chain) return launch_pdl((void (*)(const MmaChainArgs))kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, c);
     MmaSingleArgs one = {};

@@ -70,13 +70,12 @@ struct MmaGemvArgs {
     long long pw_step, pw_wrap;
     int ab_step, ab_wrap, d_rt, d_kt;
     int multi;  // grouped launch with per-matrix offsets (nested statistics)
-    int swiglu; // Q4_GEMV_SWIGLU: two matrices (gate, up) interleaved in chunks of 4 rows -- rows 8t..8t+3 are gate rows 4t..4t+3, rows
-                // 8t+4..8t+7 the up rows of the same index -- and the launch stores silu(gate) * up [rows / 2] instead of the rows
     int rt_q, rt_r;  // rt_total / grid, rt_total % grid: CTA b owns row tiles [b*rt_q + min(b, rt_r), ...) -- no division on the device
     // exact prefetch hint (nx_grid > 0): the NEXT launch runs nx_grid CTAs over `next`, CTA j owning row tiles
     // [j*nx_rt_q + min(j, nx_rt_r), ...) of nx_tile_bytes each and loading the first nx_head of them before its activation exists
     int nx_grid, nx_rt_q, nx_rt_r, nx_head;
     long long nx_tile_bytes;
+    int swiglu;  // Q4_GEMV_SWIGLU (host side only: selects the SWIGLU instantiation of the kernel)
 };
 
 // A launch runs `n` dependent GEMVs back to back ("chain": e.g. o_proj -> gate/up -> down_proj -> next layer's q/k/v): one
@@ -285,7 +284,10 @@ constexpr int kMmaThreads = 256;
 #endif
 constexpr int kBuffers = 3;     // weight tiles a warp holds in registers (one being consumed, the others in flight)
 
-template <typename T, bool NESTED, bool COMPACT, bool TAIL, bool CHAIN>
+// SWIGLU (Q4_GEMV_SWIGLU): two matrices (gate, up) interleaved in chunks of 4 rows -- rows 8t..8t+3 are gate rows 4t..4t+3, rows
+// 8t+4..8t+7 the up rows of the same index -- and the launch stores silu(gate) * up [rows / 2] instead of the rows.  A template
+// parameter, not a run-time flag: as a flag it cost the plain kernel three registers and 5 % of its speed (1.341 vs 1.270 ms/step).
+template <typename T, bool NESTED, bool COMPACT, bool TAIL, bool CHAIN, bool SWIGLU = false>
 __global__ void __launch_bounds__(kMmaThreads, 512 / kMmaThreads)
 gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChainArgs, MmaSingleArgs>::type c)
 {
@@ -559,7 +561,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
             float o = off[0];
             if (MULTI) {
                 const int row = (rt0 + c.rt) * 8 + g;
-                if (a.swiglu) o = (g & 4) ? off[1] : off[0];  // 8-row tiles are aligned to the 4 + 4 interleave
+                if (SWIGLU) o = (g & 4) ? off[1] : off[0];  // 8-row tiles are aligned to the 4 + 4 interleave
                 else o = row < a.row_end[0] ? off[0] : (row < a.row_end[1] ? off[1] : (row < a.row_end[2] ? off[2] : off[3]));
             }
             const float q0 = __uint_as_float(lut_lookup<0, kImm + 128>(r.q, lane_base));
@@ -651,7 +653,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
             }
             finish(i, total);
         }
-    } else if (a.swiglu) {
+    } else if (SWIGLU) {
         // SwiGLU in the epilogue: every 8-row tile holds four (gate, up) pairs, so this CTA owns both halves of each of its outputs.
         // Rounded exactly as the separate steps would: gate and up to T (what the plain launch stores), silu(gate) to T, the product
         // to T -- the same expressions as stage_x_fused, hence bit-identical to "grouped gate/up launch, then SwiGLU staging".
