@@ -189,6 +189,29 @@ def run_ours(args, rank, world, device):
 
             fused_ar = tpmod.FusedAllReduce(cfg["hidden"], device=device)
 
+    # ---- tensor-parallel correctness, before anything is timed: every row-parallel unit once through the epilogue all-reduce
+    #      (the product path) and once as a plain GEMV of the same shard + NCCL all-reduce of the partials
+    tp_check = None
+    if fused_ar is not None:
+        worst = 0.0
+        row_units = [m for m in units if m.parallel == "row"]
+        picked = row_units[:4] + row_units[-2:]  # both layer kinds, both halves of the double buffer, epochs beyond the first
+        for rep, m in enumerate(picked):
+            xk = torch.randn(1, 1, m.in_features, device=device, dtype=dtype, generator=torch.Generator(device=device).manual_seed(77 + rep + 1000 * rank))
+            st = m.weight.quant_state
+            part = q.gemv_4bit(xk, m.weight.data, state=st).float()
+            comm.all_reduce(part)
+            got = q.gemv_4bit_fused(xk, m.weight.data, st, allreduce=fused_ar)
+            err = ((got.float() - part).abs().max() / part.abs().max()).item()
+            worst = max(worst, err)
+            if not err <= 1e-2:
+                raise RuntimeError(f"tp_check: fused all-reduce of {m.name_} differs from NCCL's by {err} (rank {rank})")
+            gathered = [torch.empty_like(got) for _ in range(world)]
+            comm.all_gather(gathered, got)
+            if not all(torch.equal(gathered[0], t) for t in gathered):
+                raise RuntimeError(f"tp_check: ranks hold different bits after the fused all-reduce of {m.name_}")
+        tp_check = {"status": "ok", "units": len(picked), "max_rel_err_vs_nccl": worst, "bit_identical_across_ranks": True}
+
     pdl = _lib.Q4_GEMV_PDL if args.pdl else 0
     # A decoder layer's Linear4bit calls form a small DAG: q/k/v share their input and are independent of each other, so do
     # gate/up; o_proj and down_proj each depend on what precedes them.  The step is launched exactly like that: independent
@@ -387,7 +410,7 @@ def run_ours(args, rank, world, device):
 
     # sanity: the e2e outputs equal the C-ABI outputs (same kernels)
     for k in out_keys:
-        if not torch.equal(y_host[k].to(device), outs[k]) and world == 1:
+        if not torch.equal(y_host[k].to(device), outs[k]):
             raise RuntimeError(f"e2e output {k} differs from the C-ABI output")
 
     if rank != 0:
@@ -409,20 +432,21 @@ def run_ours(args, rank, world, device):
         traffic = None
     res = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {
-            "workload": f"{args.model} Linear4bit stack, NF4 + double-quant, blocksize 64, bs=1 decode: {layers} layers x "
-                        f"(q,k,v,o,gate,up,down) = {len(mods)} GEMVs/step per GPU"
-                        + (f" in {len(units)} launches (q/k/v and gate/up grouped: they share their input)" if args.group else "") + (f", tensor-parallel tp{world} (" + ("NCCL all-reduce after" if fused_ar is None else "all-reduce fused into the epilogue of") + " o_proj/down_proj)" if world > 1 else ""),
+        "config": {"workload": workload_string(args.model, layers, len(mods) if world == 1 else 7 * layers),
+                   "parallelism": f"tp{world}" if world > 1 else "single GPU"},
+        "launch": (f"{len(units)} launches/step" + (" (q/k/v and gate/up grouped: they share their input)" if args.group else "")
+                   + (", CUDA graph replay" if graph is not None else ", eager") + (" + programmatic dependent launch" if args.pdl else "")
+                   + (", chained: 1 + layers persistent launches per step (o -> gate/up -> down -> next q/k/v per launch)" if use_chain else "")
+                   + (", q/k/v and gate/up as parallel graph branches (co-resident CTAs)" if args.branches else "")
+                   + (", next launch's first tiles prefetched into L2" if args.prefetch else "")
+                   + (f", tensor-parallel tp{world} (" + ("NCCL all-reduce after" if fused_ar is None else "all-reduce fused into the epilogue of")
+                      + " o_proj/down_proj)" if world > 1 else "")),
+        "workload_detail": {
             "shapes": sorted({f"{m.out_features}x{m.in_features}" for m in mods}),
             "packed_weight_bytes_per_gpu": packed_bytes, "algorithmic_bytes_per_step": step_bytes,
             "l2_policy": "inputs larger than L2: every layer has its own weights (3.5 GB/step >> 126 MB L2), no flush needed",
-            "launch": ("CUDA graph replay" if graph is not None else "eager") + (" + programmatic dependent launch" if args.pdl else "")
-                      + (", chained: 1 + layers persistent launches per step (o -> gate/up -> down -> next q/k/v per launch)" if use_chain else "")
-                      + (", q/k/v and gate/up as parallel graph branches (co-resident CTAs)" if args.branches else "")
-                      + (", next launch's first tiles prefetched into L2" if args.prefetch else ""),
-            "parallelism": f"tp{world}" if world > 1 else "single GPU",
         },
         "pct_of_8TBs": round(value / world / 8000 * 100, 2),
         "decode_linear_tok_s": round(1e3 / ms_per_step, 1),
@@ -436,6 +460,8 @@ def run_ours(args, rank, world, device):
                      "avg_launch_us": round(per_launch_us, 3), "algorithmic_bytes_per_launch": step_bytes_local // launches_per_step,
                      "traffic": traffic, "timed_blocks_ms": [round(t, 3) for t in times[:5]]},
     }
+    if tp_check is not None:
+        res["tp_check"] = tp_check
     if world == 1 and not args.no_blockwise:
         res["blockwise"] = blockwise_rates(device, peak)
     if world == 1 and not args.no_cpu:
@@ -578,19 +604,35 @@ def cpu_baseline(mods, x_in, budget_s=12.0):
 # ------------------------------------------------------------------------------------------------ reference arm
 
 
+def workload_string(model: str, layers: int, ngemv: int) -> str:
+    """config.workload: the SAME string for both arms (what is computed); how each arm launches it is in `launch`."""
+    return (f"{model} Linear4bit stack, NF4 + double-quant, blocksize 64, bf16, bs=1 decode: {layers} layers x "
+            f"(q,k,v,o,gate,up,down) = {ngemv} GEMVs/step")
+
+
 def run_reference(args, rank, world, device):
     """The reference's own CUDA kernels (oracle/_ref/kbkim_lib.so + ref_shim.so, compiled from /root/reference for sm_100a)
     on the same workload, driven with the reference's gemv_4bit call sequence (core.py:467-499): dequantize_blockwise of the
     8-bit absmax, torch `+= offset`, then the GEMV kernel -- three launches per Linear.  bf16 uses the kernel instance the
-    reference instantiates but does not export (ops.cu:177), NF4 its code-table argument."""
+    reference instantiates but does not export (ops.cu:177), NF4 its code-table argument.
+
+    Nothing of quantizations_b200 is imported or loaded on this arm: the weights are quantised by the reference's own kernels
+    (core.py:536-576 re-enacted: blockwise 4-bit quantise, absmax.mean(), 8-bit blockwise quantise of the shifted absmax with
+    the dynamic map).  The reference has no NF4 quantiser (ops.cuh:6-10), so the nibbles come from its FP4 quantiser and are
+    DECODED with the NF4 table (kernels.cu:851) -- the GEMV's time does not depend on the nibble values."""
     if rank != 0:
         return None
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    cfg = LLAMA3_8B
+    layers = args.layers or cfg["layers"]
+    ngemv = 7 * layers
     base = {"impl": "reference", "metric": METRIC, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic"}
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic"}
     have_gpu = torch.cuda.is_available()
     if have_gpu and os.path.exists(os.path.join(ref_dir, "ref_shim.so")) and os.path.exists(os.path.join(ref_dir, "kbkim_lib.so")):
-        import quantizations_b200 as q
+        import numpy as np
+
+        from oracle import q4_oracle as orc  # tables only (dynamic map, NF4 values): numpy, no compute
 
         sys.path.insert(0, ref_dir)
         import kbkim_lib
@@ -599,26 +641,46 @@ def run_reference(args, rank, world, device):
         vp, i32 = ctypes.c_void_p, ctypes.c_int
         shim.ref_gemv_bf16_async.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32]
         shim.ref_gemv_bf16_async.restype = None
+        shim.ref_quant_fp4_bf16.argtypes = [vp, vp, vp, i32, i32]
+        shim.ref_quant_fp4_bf16.restype = i32
         dtype = torch.bfloat16
-        cfg = LLAMA3_8B
-        layers = args.layers or cfg["layers"]
-        mods = build_stack(cfg, 1, 0, device, dtype, "nf4", layers, q)
-        step_bytes = sum(algo_bytes(m.out_features, m.in_features) for m in mods)
-        x_in = {K: torch.randn(1, 1, K, device=device, dtype=dtype) for K in {m.in_features for m in mods}}
-        outs = {(m.name_, m.out_features): torch.empty(1, 1, m.out_features, device=device, dtype=dtype) for m in mods}
-        absmax_buf = {m.weight.quant_state.absmax.numel(): torch.empty(m.weight.quant_state.absmax.numel(), device=device)
-                      for m in mods}
+        dyn = torch.from_numpy(np.ascontiguousarray(orc.dynamic_map())).to(device)
+        code = torch.from_numpy(np.ascontiguousarray(orc.nf4_table())).to(device)
+        mods = []
+        g = torch.Generator(device=device)
+        for layer in range(layers):
+            for j, (name, N, K, _par) in enumerate(layer_shapes(cfg, 1)):
+                g.manual_seed(1000 * layer + j)  # the same weights as the other arm's build_stack
+                W = torch.randn(N, K, device=device, dtype=torch.float32, generator=g).mul_(0.02).to(dtype)
+                n = N * K
+                absmax = torch.zeros(n // 64, device=device, dtype=torch.float32)
+                packed = torch.zeros(n // 2, device=device, dtype=torch.uint8)
+                if shim.ref_quant_fp4_bf16(W.data_ptr(), absmax.data_ptr(), packed.data_ptr(), 64, n):   # core.py:552
+                    raise RuntimeError("reference quantize kernel failed")
+                offset = absmax.mean()                                                                   # core.py:563
+                absmax -= offset                                                                         # core.py:564
+                nb = absmax.numel()
+                qabs = torch.zeros(nb, device=device, dtype=torch.uint8)
+                absmax2 = torch.zeros(-(nb // -256), device=device, dtype=torch.float32)
+                kbkim_lib.cquantize_blockwise_fp32(dyn.data_ptr(), absmax.data_ptr(), absmax2.data_ptr(), qabs.data_ptr(), 256, nb)  # :565
+                torch.cuda.synchronize()
+                mods.append(dict(name=name, N=N, K=K, packed=packed, qabs=qabs, absmax2=absmax2, offset=offset))
+                del W, absmax
+        step_bytes = sum(algo_bytes(m["N"], m["K"]) for m in mods)
+        torch.manual_seed(1)
+        x_in = {K: torch.randn(1, 1, K, device=device, dtype=dtype) for K in sorted({m["K"] for m in mods})}
+        outs = {(m["name"], m["N"]): torch.empty(1, 1, m["N"], device=device, dtype=dtype) for m in mods}
+        absmax_buf = {m["qabs"].numel(): torch.empty(m["qabs"].numel(), device=device) for m in mods}
 
         def step():
             for m in mods:
-                st = m.weight.quant_state
-                am = absmax_buf[st.absmax.numel()]
-                kbkim_lib.cdequantize_blockwise_fp32(st.state2.code.data_ptr(), st.absmax.data_ptr(), st.state2.absmax.data_ptr(),
-                                                     am.data_ptr(), 256, st.absmax.numel())        # core.py:467
-                am += st.offset                                                                   # core.py:468
-                N, K = m.out_features, m.in_features
-                shim.ref_gemv_bf16_async(N, 1, K, x_in[K].data_ptr(), m.weight.data_ptr(), am.data_ptr(), st.code.data_ptr(),
-                                   outs[(m.name_, N)].data_ptr(), N, (K + 1) // 2, N, 64)          # core.py:486-499
+                nb = m["qabs"].numel()
+                am = absmax_buf[nb]
+                kbkim_lib.cdequantize_blockwise_fp32(dyn.data_ptr(), m["qabs"].data_ptr(), m["absmax2"].data_ptr(), am.data_ptr(), 256, nb)  # core.py:467
+                am += m["offset"]                                                                 # core.py:468
+                N, K = m["N"], m["K"]
+                shim.ref_gemv_bf16_async(N, 1, K, x_in[K].data_ptr(), m["packed"].data_ptr(), am.data_ptr(), code.data_ptr(),
+                                         outs[(m["name"], N)].data_ptr(), N, (K + 1) // 2, N, 64)   # core.py:486-499
 
         # the reference launches on the legacy default stream (ops.cu:170): run everything there
         with torch.cuda.stream(torch.cuda.default_stream(device)):
@@ -640,15 +702,15 @@ def run_reference(args, rank, world, device):
             wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         v = step_bytes / (ms * 1e-3) / 1e9
         return {**base, "value": round(v, 1), "ms_per_step": round(ms, 4),
-                "config": {"workload": f"llama3-8b Linear4bit stack, NF4 + double-quant, bs=1 decode: {layers} layers x 7 = {len(mods)} "
-                                       "reference gemv_4bit calls/step (3 launches each), reference CUDA kernels rebuilt for sm_100a",
-                           "algorithmic_bytes_per_step": step_bytes},
+                "config": {"workload": workload_string("llama3-8b", layers, ngemv), "parallelism": "single GPU"},
+                "launch": "reference gemv_4bit call sequence, 3 launches per Linear on the legacy default stream, eager; reference CUDA "
+                          "kernels rebuilt for sm_100a (oracle/_ref), weights quantised by the reference's own kernels",
+                "algorithmic_bytes_per_step": step_bytes,
                 "cpu_baseline": {"value": round(v, 1), "unit": "GB/s", "cores": 0, "kind": "reference",
                                  "sample": "whole step; the reference's implementation of this path is CUDA (it has no CPU path), "
                                            "so it is timed on the same B200 rather than on host cores"},
                 "e2e": {"value": round(step_bytes / (wall_ms * 1e-3) / 1e9, 1), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "clocks": clk.summary(), "gpu_launches": 3 * len(mods) * args.steps,
-                **({} if args.no_decode else {"decode": decode_tok_s(args, device, "reference")})}
+                "clocks": clk.summary(), "gpu_launches": 3 * len(mods) * args.steps}
     # no GPU / no compiled reference: the oracle port on host cores
     from oracle import q4_oracle as orc  # noqa: F401
     import numpy as np

@@ -18,7 +18,7 @@ static std::atomic<int64_t> g_launches{0};
 int finish_launch()
 {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return (int)cudaPeekAtLastError();
+    return (int)cudaGetLastError();  // clears a non-sticky launch error so it is reported once, not by every later call
 }
 
 int sm_count()

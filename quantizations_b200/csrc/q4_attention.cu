@@ -67,6 +67,7 @@ decode_attention_kernel(const DecodeAttnArgs a)
     if (!EARLY) pdl_wait();  // qkv comes from the preceding GEMV
     pdl_launch_dependents();
     const long long pos = *a.pos;
+    if (pos < 0 || pos >= a.max_len) __trap();  // the cache row / cos-sin row of `pos` would be out of bounds: fail loudly, never overwrite a neighbour
     const T* qkv = reinterpret_cast<const T*>(a.qkv);
     const int d0 = lane * 4;
     float q[4], kn[4], vn[4], c[4], s[4];

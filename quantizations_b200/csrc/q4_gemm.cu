@@ -29,6 +29,7 @@
 
 #include "q4_common.cuh"
 #include "q4_launch.h"
+#include "q4_tma.h"
 
 namespace q4 {
 
@@ -363,36 +364,6 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-static bool make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
-                        uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw)
-{
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {row_bytes};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 static int pick_bn(int64_t M)
 {

@@ -1,0 +1,709 @@
+// q4_gemv_ring.cuh -- the batch-1 decode GEMV as a persistent, warp-specialised streaming kernel (fp16 / bf16 activations,
+// blocksize 64, K % 128 == 0).
+//
+//   out[r] = sum_b absmax[r,b] * sum_{k in block b} x[k] * code[nib(r,k)]            (+ bias[r])
+//
+// Replaces reference csrc/kernels.cu:1061-1219 (kgemm_4bit_inference_naive), its launcher ops.cu:167-171 and the two launches
+// core.py:467-468 issues before every call.  HBM-bound: every packed byte is read once.
+//
+// One CTA per SM, (NC consumer warps + 1 producer warp):
+//
+//   producer   one elected thread streams the CTA's share of the packed weight HBM -> shared memory with 2-D TMA
+//              (cp.async.bulk.tensor, 128-byte swizzle) into a ring of 2-KB slots guarded by full / empty mbarriers.  The weight
+//              does not depend on the activation, so the producer never waits for anything but a free slot: it runs ahead
+//              ACROSS the dependent GEMVs ("stages") of a launch -- while the consumers sit at the grid barrier between o_proj and
+//              gate/up, the ring is already filling with gate/up's first tiles -- and it starts before griddepcontrol.wait under
+//              programmatic dependent launch.  The bytes in flight per SM are the ring (>= 100 KB), not registers.
+//   consumers  take slots round-robin.  A slot is an 8-row x 512-k tile (8 quantisation blocks per row); a lane copies its 64
+//              packed bytes out of the slot (4 conflict-free LDS.128, the swizzle spreads the 8 rows over the banks), releases the
+//              slot at once, then decodes ONE packed byte per shared-memory lookup (256-row table of lane-private
+//              {code[b>>4], code[b&15]} pairs, address spliced by one PRMT) and feeds the pairs to mma.sync.m16n8k16 as
+//              A-fragments: the tensor pipe does the multiply-accumulate and the k-reduction, its 8 B columns are used as 8
+//              quantisation blocks so that D holds the 64 per-(row, block) sums of the tile, each scaled by its decoded absmax
+//              (double-quant decode fused: code2[q] * absmax2 + offset, fp32 multiply then add as kernels.cu:552 + core.py:468).
+//
+// Work split ("inter-CTA split-K").  A stage's tiles form a flat list, k fastest; CTA b owns a contiguous range of it, so every
+// SM streams the same number of bytes (+-1 tile) whatever the row count -- 4096 rows are 4096 tiles over 148 CTAs = 27 or 28 each,
+// not 3 or 4 row tiles.  A row tile cut by a range boundary is finished by the CTA that holds its first k tile: the other CTA
+// meets that row tile FIRST in its own range, publishes the 8 partial sums (value + epoch tag, one 8-byte store each) as soon as
+// its warps are through with it, and the owner picks them up at the end of its range -- fixed order, no atomics on data, no
+// extra grid-wide step.  Between stages the consumers synchronise on one global counter (all CTAs are co-resident: grid = SMs).
+#pragma once
+
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "q4_common.cuh"
+#include "q4_gemv_mma.cuh"
+
+namespace q4 {
+namespace ring {
+
+constexpr int kSlotBytes = 2048;   // 8 rows x 256 packed bytes = two 128-byte-wide TMA boxes
+constexpr int kMaxStages = 4;
+constexpr int kConsumerBar = 1;    // named barrier of the consumer warps
+// workspace layout (Q4_GEMV_RING_WS_BYTES, zeroed once by the caller, owned by one stream at a time)
+constexpr int kWsEpochOff = 1024;  // u32 [kWsMaxCtas]: stages run so far, per CTA (tags of the split-tile hand-over)
+constexpr int kWsFixOff = 8192;    // {f32, u32} [kWsMaxCtas][8]: partial sums of the row tile a CTA shares with its predecessor
+constexpr int kWsMaxCtas = 1024;
+
+struct Stage {
+    alignas(64) CUtensorMap map;  // packed weight as u8 [rows, K/2], box {128, 8}, SWIZZLE_128B
+    const void* x;
+    const void* x_gate;      // optional: effective activation = silu(x_gate[k]) * x[k]
+    const void* rms_weight;  // optional: effective activation = x * rsqrt(mean(x^2) + eps) * rms_weight
+    AbsmaxView s;
+    const float* offsets[kMaxMats];  // nested: per-matrix offset scalars (device pointers)
+    int row_end[kMaxMats];           // exclusive end row of each matrix (INT_MAX for unused slots)
+    void* out;
+    const void* bias;        // [rows] or nullptr (may alias out: residual stream updated in place)
+    float rms_eps;
+    int rows, K;
+    int KT;                  // ceil(K / 512): k tiles per row tile
+    int multi;               // grouped launch with per-matrix offsets
+    int gran;                // units per assignment quantum: 1 (row tiles may be split between CTAs) or KT (never split)
+    int active, per, rem;    // CTA b < active owns quanta [b*per + min(b, rem), +per + (b < rem)); the others idle in this stage
+    // fused one-shot all-reduce over tensor-parallel ranks (q4_allreduce_t), ar_world <= 1: off
+    void* const* ar_peer_bases;
+    int ar_world, ar_rank, ar_max_rows;
+};
+
+struct Args {
+    Stage st[kMaxStages];
+    int n;
+    const void* lut;      // prebuilt 64-KB table image, or nullptr: built in the kernel from code / code2
+    const float* code;
+    unsigned* ws;         // workspace (see above); required when n > 1 or any stage has gran == 1
+    int slots;            // ring depth
+    int x_bytes;          // shared-memory bytes reserved for the activation vector: max over the stages of KT * 1024
+    int part_bytes;       // ... for the per-tile partial sums: max over the stages of (tiles per CTA) * 32
+    unsigned long long* trace;  // developer: [stage][cta][8] globaltimer marks
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// blocks until the barrier's phase with the given parity has completed.  A pipeline bug must not hang the GPU: after ~2^25 failed
+// probes (seconds; a probe itself suspends the thread for a while) the kernel traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spin = 0;; spin++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin > (1u << 25)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// the CTA's range of a stage's flat tile list, in units (tiles)
+__device__ __forceinline__ void cta_range(const Stage& a, int b, int& u0, int& u1)
+{
+    if (b >= a.active) {
+        u0 = u1 = 0;
+        return;
+    }
+    const int q0 = b * a.per + (b < a.rem ? b : a.rem);
+    const int q1 = q0 + a.per + (b < a.rem ? 1 : 0);
+    u0 = q0 * a.gran;
+    u1 = q1 * a.gran;
+    const int total = ((a.rows + 7) >> 3) * a.KT;
+    if (u1 > total) u1 = total;  // gran == KT never overshoots; kept for safety
+}
+
+// Activation staging by the consumer threads, decode glue fused in (see q4_gemv_fused_t):
+//   x_gate:      x_eff = silu(gate) * x, F.silu rounded to T, then the product rounded to T (as the separate torch kernels round)
+//   rms_weight:  x_eff = x * rsqrt(mean(x^2) + eps) * weight in fp32, rounded to T once
+// chunk c (8 activations) = (block c>>3, piece c&7) lands at piece (c&7) ^ (block&7): the eight lanes that later fetch eight
+// different blocks piece by piece hit eight different bank groups
+template <typename T>
+__device__ __noinline__ void stage_x_glue(const void* x, const void* x_gate, const void* rms_weight, float rms_eps, int K, uint4* s_x,
+                                          float* s_red, int nchunk, int npad, int tid, int nthr)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    auto slot = [](int c) { return (c & ~7) | ((c ^ (c >> 3)) & 7); };
+    float ss = 0.0f;
+#pragma unroll 1
+    for (int c = tid; c < npad; c += nthr) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < nchunk) {
+            v = __ldcg(reinterpret_cast<const uint4*>(x) + c);
+            uint32_t uw[4] = {v.x, v.y, v.z, v.w};
+            if (x_gate) {
+                const uint4 g4 = __ldcg(reinterpret_cast<const uint4*>(x_gate) + c);
+                const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int q2 = 0; q2 < 4; q2++) {
+                    const float2 gg = unpack2<T>(gw[q2]), u = unpack2<T>(uw[q2]);
+                    // every CTA recomputes the whole vector: the fast exp / divide (~1e-6 relative, far below the rounding to T)
+                    const float2 sg = unpack2<T>(pack2<T>(__fdividef(gg.x, 1.0f + __expf(-gg.x)), __fdividef(gg.y, 1.0f + __expf(-gg.y))));
+                    uw[q2] = pack2<T>(sg.x * u.x, sg.y * u.y);
+                }
+                v = make_uint4(uw[0], uw[1], uw[2], uw[3]);
+            }
+#pragma unroll
+            for (int q2 = 0; q2 < 4; q2++) {
+                const float2 f = unpack2<T>(uw[q2]);
+                ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+            }
+        }
+        s_x[slot(c)] = v;
+    }
+    if (!rms_weight) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) s_red[warp] = ss;
+    bar_sync(kConsumerBar, nthr);
+    ss = 0.0f;
+    for (int i = 0; i < (nthr >> 5); i++) ss += s_red[i];
+    const float rs = rsqrtf(ss / (float)K + rms_eps);
+#pragma unroll 1
+    for (int c = tid; c < nchunk; c += nthr) {  // each thread rescales the chunks it wrote itself
+        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(rms_weight) + c);
+        const uint4 v = s_x[slot(c)];
+        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+        uint32_t xw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q2 = 0; q2 < 4; q2++) {
+            const float2 f = unpack2<T>(xw[q2]), gm = unpack2<T>(ww[q2]);
+            xw[q2] = pack2<T>(f.x * rs * gm.x, f.y * rs * gm.y);
+        }
+        s_x[slot(c)] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+    }
+}
+
+template <typename T, bool NESTED, int NC>
+__global__ void __launch_bounds__((NC + 1) * 32, 1)
+gemv_ring_kernel(const __grid_constant__ Args c)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // Shared-memory plan: [table 64 KB][ring: slots x 2 KB][x][partials][barriers][scratch].  The PRMT splice of the lookups needs
+    // the table at (64-KB aligned window address) + (compile-time immediate): it is the first thing in dynamic shared memory,
+    // which starts kDynBase into the CTA's window (probed on the host, trapped here if violated).  kDynBase + 64 KB is a multiple
+    // of 1024, which the 128-byte TMA swizzle of the ring slots needs.
+    constexpr int kImm = kDynBase;
+    constexpr int kCons = NC * 32;
+    const uint32_t smem_saddr = smem_u32(smem);
+    if (smem_saddr != kDynBase) __trap();
+    uint8_t* lut = smem;
+    uint8_t* ringp = smem + kLutBytes;
+    const int D = c.slots;
+    uint4* s_x = reinterpret_cast<uint4*>(ringp + (size_t)D * kSlotBytes);
+    float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_x) + c.x_bytes);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_part) + c.part_bytes);  // [0] table, [1 + i] full, [1 + D + i] empty
+    float* s_red = reinterpret_cast<float*>(s_bar + 1 + 2 * D);                                          // 32 floats
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_red + 32);  // [0] head-piece counter, [1] epoch base, [2] all-reduce epoch
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int bx = blockIdx.x, G = gridDim.x;
+    const uint32_t bar0 = smem_u32(s_bar);
+    const uint32_t ring_saddr = smem_saddr + kLutBytes;
+    auto full = [&](int i) { return bar0 + 8u * (uint32_t)(1 + i); };
+    auto empty = [&](int i) { return bar0 + 8u * (uint32_t)(1 + D + i); };
+    auto mark = [&](int stage, int slot) {
+        if (c.trace) c.trace[((size_t)stage * G + bx) * 8 + slot] = gtime();
+    };
+
+    pdl_launch_dependents();
+    if (tid == NC * 32) {  // producer lane: barriers first
+        mbar_init(bar0, 1);
+        for (int i = 0; i < D; i++) {
+            mbar_init(full(i), 1);
+            mbar_init(empty(i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_misc[0] = 0;
+        mark(0, 0);
+    }
+    __syncthreads();
+
+    if (warp == NC) {
+        // ============================================================ producer
+        if (lane == 0) {
+            if (c.lut) {  // table image: one expect, four bulk copies
+                mbar_expect_tx(bar0, kLutBytes);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_saddr + i * (kLutBytes / 4)),
+                                 "l"(reinterpret_cast<const uint8_t*>(c.lut) + i * (kLutBytes / 4)), "r"(kLutBytes / 4), "r"(bar0)
+                                 : "memory");
+            }
+            int pos = 0;
+            uint32_t ph = 0;
+            for (int s = 0; s < c.n; s++) {
+                const Stage& a = c.st[s];
+                int u0, u1;
+                cta_range(a, bx, u0, u1);
+                const int KT = a.KT, half = a.K >> 1;
+                int rt = u0 / KT, kt = u0 - rt * KT;
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map) : "memory");
+                mark(s, 6);
+                for (int u = u0; u < u1; u++) {
+                    mbar_wait(empty(pos), ph ^ 1u);
+                    const uint32_t dst = ring_saddr + (uint32_t)pos * kSlotBytes;
+                    const bool two = kt * 256 + 128 < half;  // a ragged last k tile may hold one box only
+                    mbar_expect_tx(full(pos), two ? kSlotBytes : kSlotBytes / 2);
+                    tma_load_2d(dst, &a.map, kt * 256, rt * 8, full(pos));
+                    if (two) tma_load_2d(dst + 1024, &a.map, kt * 256 + 128, rt * 8, full(pos));
+                    if (++kt == KT) {
+                        kt = 0;
+                        rt++;
+                    }
+                    if (++pos == D) {
+                        pos = 0;
+                        ph ^= 1u;
+                    }
+                }
+                mark(s, 7);
+            }
+        }
+        return;
+    }
+
+    // ================================================================ consumers
+    const int g = lane >> 2, t4 = lane & 3;
+    // byte offsets of the lane's four 16-byte pieces inside a slot: row g of the 8 x 128-byte box, chunks 2*t4, 2*t4+1 (block t4
+    // of the half) as the 128-byte swizzle stores them (chunk ^ row)
+    const uint32_t off_a0 = (uint32_t)(g * 128 + (((2 * t4) ^ g) << 4)), off_a1 = (uint32_t)(g * 128 + (((2 * t4 + 1) ^ g) << 4));
+    const uint32_t lane_base = (uint32_t)(lane * 4);  // table window address is 0: the PRMT splice needs only the lane's word
+    const bool xrole = t4 == (g & 3);  // this lane feeds column g of the B operand: x of the tile's block g
+    const uint32_t x_saddr = smem_u32(s_x), xswz = (uint32_t)(g * 16);
+    uint32_t epoch_base = 0;  // stages this CTA ran in earlier launches (workspace counter): read after griddepcontrol.wait
+    int base_seq = 0;  // tiles this CTA has taken from the ring in earlier stages
+
+    for (int stage = 0; stage < c.n; stage++) {
+        const Stage& a = c.st[stage];
+        const int K = a.K, R = a.rows, KT = a.KT;
+        const int bpr = K >> 6;
+        int u0, u1;
+        cta_range(a, bx, u0, u1);
+        const int nloc = u1 - u0;
+        const bool MULTI = a.multi != 0;
+        float off[kMaxMats];
+#pragma unroll
+        for (int m = 0; m < kMaxMats; m++) off[m] = (NESTED && (MULTI || m == 0) && a.offsets[m]) ? __ldg(a.offsets[m]) : 0.0f;
+        // ---- the warp's tiles: local index j = warp, warp + NC, ...; ring position and phase of the first one
+        struct Cursor { int j, rt, kt; };
+        Cursor cur;
+        {
+            const int u = u0 + warp;
+            cur.j = warp;
+            cur.rt = u / KT;
+            cur.kt = u - cur.rt * KT;
+        }
+        const int d_rt = NC / KT, d_kt = NC - d_rt * KT;
+        auto advance = [&](Cursor& q) {
+            q.j += NC;
+            q.rt += d_rt;
+            q.kt += d_kt;
+            if (q.kt >= KT) {
+                q.kt -= KT;
+                q.rt++;
+            }
+        };
+        int pos;
+        uint32_t ph;
+        {
+            const int seq = base_seq + warp;
+            const int w = seq / D;
+            pos = seq - w * D;
+            ph = (uint32_t)w & 1u;
+        }
+        const int d_wrap = NC / D, d_pos = NC - d_wrap * D;
+
+        // absmax of the lane's two blocks (2*t4, 2*t4+1 of row g of the tile), fetched one tile ahead
+        struct Stat { uint32_t q; float s0, s1; };
+        auto load_stat = [&](const Cursor& q) {
+            Stat r;
+            r.q = 0;
+            r.s0 = r.s1 = 0.0f;
+            const int row = q.rt * 8 + g;
+            const int blk = q.kt * 8 + 2 * t4;
+            if (blk < bpr) {  // bpr is even: the pair is valid together
+                const int sb = (row < R ? row : R - 1) * bpr + blk;  // rows past the end read a valid row and are never stored
+                if (NESTED) {
+                    r.q = __ldg(reinterpret_cast<const unsigned short*>(a.s.qabsmax + sb));
+                    r.s0 = __ldg(a.s.absmax2 + (sb >> a.s.shift2));
+                } else {
+                    const float2 f = __ldg(reinterpret_cast<const float2*>(a.s.absmax + sb));
+                    r.s0 = f.x;
+                    r.s1 = f.y;
+                }
+            }
+            return r;
+        };
+        Stat st_cur = {0, 0.0f, 0.0f};
+        if (cur.j < nloc) st_cur = load_stat(cur);  // statistics do not depend on the previous stage: before the barrier
+
+        // ---- everything below may read the previous kernel's (stage 0) or the previous stage's output
+        if (tid == 0) mark(stage, 1);
+        if (stage == 0) {
+            pdl_wait();
+            if (tid == 0) s_misc[1] = c.ws ? __ldcg(c.ws + kWsEpochOff / 4 + bx) : 0u;  // written by this CTA index of the previous launch
+        } else {
+            // grid-wide barrier of the consumers: every CTA's stores of the previous stage are visible afterwards
+            bar_sync(kConsumerBar, kCons);
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(c.ws, 1u);
+                const unsigned target = (unsigned)stage * (unsigned)G;
+                unsigned v;
+                for (long long spin = 0;; spin++) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.ws) : "memory");
+                    if (v >= target) break;
+                    if (spin > (1ll << 27)) __trap();  // a CTA never arrived: fail loudly instead of hanging the GPU
+                }
+            }
+            bar_sync(kConsumerBar, kCons);
+        }
+        if (tid == 0) mark(stage, 2);
+
+        {
+            const int nchunk = K >> 3;  // 16-byte chunks of x
+            const int npad = KT * 64;   // staged chunks (zero tail up to whole tiles)
+            if (a.x_gate || a.rms_weight) {
+                stage_x_glue<T>(a.x, a.x_gate, a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, npad, tid, kCons);
+            } else {
+                for (int cb = tid; cb < npad; cb += 4 * kCons) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int cc = cb + j * kCons;
+                        v[j] = make_uint4(0, 0, 0, 0);
+                        if (cc < nchunk) v[j] = __ldcg(reinterpret_cast<const uint4*>(a.x) + cc);  // coherent: may be a previous stage's output
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int cc = cb + j * kCons;
+                        if (cc < npad) s_x[(cc & ~7) | ((cc ^ (cc >> 3)) & 7)] = v[j];
+                    }
+                }
+            }
+            if (tid == 0) s_misc[0] = 0;  // head-piece counter of this stage
+        }
+        if (stage == 0) {
+            if (!c.lut) {  // callers without a prebuilt image: build the table here
+                const float* code2 = a.s.code2;
+                for (int cc = tid; cc < kLutBytes / 16; cc += kCons) {
+                    const int seg = cc >> 3, b = seg >> 1;
+                    uint32_t word;
+                    if (seg & 1) word = NESTED ? __float_as_uint(__ldg(code2 + b)) : 0u;
+                    else word = pack2<T>(__ldg(c.code + (b >> 4)), __ldg(c.code + (b & 15)));
+                    *reinterpret_cast<uint4*>(lut + cc * 16) = make_uint4(word, word, word, word);
+                }
+            }
+        }
+        bar_sync(kConsumerBar, kCons);
+        if (stage == 0 && c.lut) mbar_wait(bar0, 0);  // table landed?
+        if (stage == 0) epoch_base = s_misc[1];
+        const uint32_t epoch = epoch_base + (uint32_t)stage + 1u;  // tag of this stage's split-tile hand-over
+        if (tid == 0) mark(stage, 3);
+
+        // split row tiles of this CTA's range: `head` tiles at its start belong to a row tile that began in the previous CTA
+        const int rt_first = nloc > 0 ? u0 / KT : 0;
+        const int head = (nloc > 0 && u0 > rt_first * KT) ? ((rt_first + 1) * KT - u0 < nloc ? (rt_first + 1) * KT - u0 : nloc) : 0;
+
+        // ---- main loop
+        uint32_t xr[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) xr[i] = 0;
+        int kt_loaded = -1;
+
+        while (cur.j < nloc) {
+            Cursor nxt = cur;
+            advance(nxt);
+            Stat st_nxt = {0, 0.0f, 0.0f};
+            if (nxt.j < nloc) st_nxt = load_stat(nxt);
+
+            if (cur.kt != kt_loaded) {  // warp-uniform
+                if (xrole) {
+                    // chunk i of block kt*8+g sits at piece i ^ g: byte offset (kt*1024 + g*128 + i*16) ^ (g*16)
+                    const uint32_t xb = x_saddr + (uint32_t)(cur.kt * 1024 + g * 128);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint4 v = lds128((xb | (uint32_t)(i * 16)) ^ xswz);
+                        xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+                    }
+                }
+                kt_loaded = cur.kt;
+            }
+
+            // the tile's packed bytes: slot -> registers, slot released at once
+            mbar_wait(full(pos), ph);
+            const uint32_t sl = ring_saddr + (uint32_t)pos * kSlotBytes;
+            const uint4 a0 = lds128(sl + off_a0), a1 = lds128(sl + off_a1);
+            const uint4 b0 = lds128(sl + 1024 + off_a0), b1 = lds128(sl + 1024 + off_a1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(pos));
+            const uint32_t wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const uint32_t wb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+
+            // MMA j covers bytes 2j, 2j+1 of both pieces = k 4j .. 4j+3 of the lane's blocks.  The lookups run kAhead MMAs ahead of
+            // the tensor pipe (software pipeline, everything unrolled).
+            float ce[4] = {0.0f, 0.0f, 0.0f, 0.0f}, co[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            constexpr int kAhead = 3;
+            uint32_t f[kAhead + 1][4];
+            auto fetch = [&](uint32_t (&d)[4], int j) {
+                const uint32_t va = wa[j >> 1], vb = wb[j >> 1];
+                if (j & 1) {
+                    d[0] = lut_lookup<2, kImm>(va, lane_base); d[1] = lut_lookup<2, kImm>(vb, lane_base);
+                    d[2] = lut_lookup<3, kImm>(va, lane_base); d[3] = lut_lookup<3, kImm>(vb, lane_base);
+                } else {
+                    d[0] = lut_lookup<0, kImm>(va, lane_base); d[1] = lut_lookup<0, kImm>(vb, lane_base);
+                    d[2] = lut_lookup<1, kImm>(va, lane_base); d[3] = lut_lookup<1, kImm>(vb, lane_base);
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < kAhead; j++) fetch(f[j], j);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j + kAhead < 16) fetch(f[(j + kAhead) % (kAhead + 1)], j + kAhead);
+                uint32_t(&a4)[4] = f[j % (kAhead + 1)];
+                if (j & 1) Hmma<T>::run(co, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
+                else Hmma<T>::run(ce, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
+            }
+            // the lane's two useful sums: blocks 2t, 2t+1 of the tile (columns 2t, 2t+1; first half -> rows 0-7, second -> 8-15)
+            const float u0s = t4 < 2 ? ce[0] + co[0] : ce[2] + co[2];
+            const float u1s = t4 < 2 ? ce[1] + co[1] : ce[3] + co[3];
+            float am0, am1;
+            if (NESTED) {
+                float o = off[0];
+                if (MULTI) {
+                    const int row = cur.rt * 8 + g;
+                    o = row < a.row_end[0] ? off[0] : (row < a.row_end[1] ? off[1] : (row < a.row_end[2] ? off[2] : off[3]));
+                }
+                const float q0 = __uint_as_float(lut_lookup<0, kImm + 128>(st_cur.q, lane_base));
+                const float q1 = __uint_as_float(lut_lookup<1, kImm + 128>(st_cur.q, lane_base));
+                am0 = __fadd_rn(__fmul_rn(q0, st_cur.s0), o);  // reference: kernels.cu:552 then core.py:468
+                am1 = __fadd_rn(__fmul_rn(q1, st_cur.s0), o);
+                if (cur.kt * 8 + 2 * t4 >= bpr) am0 = am1 = 0.0f;  // ragged k tile: blocks past the row's end
+            } else {
+                am0 = st_cur.s0;
+                am1 = st_cur.s1;
+            }
+            float part = fmaf(u0s, am0, u1s * am1);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (t4 == 0) s_part[cur.j * 8 + g] = part;
+
+            if (cur.j < head) {
+                // this tile belongs to the row tile shared with the previous CTA: the warp that completes the head piece publishes
+                // its 8 partial sums (fixed order over the k tiles) for the owner
+                __syncwarp();
+                unsigned old = 0;
+                if (lane == 0) {
+                    __threadfence_block();
+                    old = atomicAdd(&s_misc[0], 1u);
+                }
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == (unsigned)head - 1u && lane < 8) {
+                    __threadfence_block();
+                    float total = 0.0f;
+                    for (int j = 0; j < head; j++) total += reinterpret_cast<volatile float*>(s_part)[j * 8 + lane];
+                    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c.ws) + kWsFixOff) + (size_t)bx * 8 + lane;
+                    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(total)), "r"(epoch) : "memory");
+                }
+            }
+
+            cur = nxt;
+            st_cur = st_nxt;
+            pos += d_pos;
+            ph ^= (uint32_t)d_wrap & 1u;
+            if (pos >= D) {
+                pos -= D;
+                ph ^= 1u;
+            }
+        }
+        base_seq += nloc;
+        if (tid == 0) mark(stage, 4);
+        bar_sync(kConsumerBar, kCons);
+
+        // ---- fixed-order sum over the k tiles of every row tile this CTA owns (= holds the first k tile of), [the partner's
+        //      partials of a split row tile,] [all-reduce over tensor-parallel ranks,] bias / residual, store
+        uint32_t ar_epoch = 0;
+        if (a.ar_world > 1) {
+            // exchanges are counted per CTA in the rank's own exchange area, by EVERY CTA whether or not it owns rows in this stage: all
+            // counters of all ranks stay equal, so a tag identifies one exchange whatever the row -> CTA mapping of the layer is
+            if (tid == 0) {
+                uint32_t* ep = reinterpret_cast<uint32_t*>(a.ar_peer_bases[a.ar_rank]) + bx;
+                const uint32_t e = *ep + 1;
+                *ep = e;
+                s_misc[2] = e;
+            }
+            bar_sync(kConsumerBar, kCons);
+            ar_epoch = s_misc[2];
+        }
+        if (nloc > 0) {
+            const int rt_own0 = (u0 + KT - 1) / KT;   // first row tile whose k tile 0 lies in [u0, u1)
+            const int rt_own1 = (u1 + KT - 1) / KT;   // one past the last
+            const int nrows_own = (rt_own1 - rt_own0) * 8;
+            const int row_lo = rt_own0 * 8;
+            auto row_total = [&](int i) {  // i = row index relative to row_lo
+                const int rt = rt_own0 + (i >> 3), gg = i & 7;
+                const int j0 = rt * KT - u0;
+                const int j1 = j0 + KT < nloc ? j0 + KT : nloc;
+                float total = 0.0f;
+                for (int j = j0; j < j1; j++) total += s_part[j * 8 + gg];
+                if (j0 + KT > nloc) {
+                    // split row tile: its remaining k tiles are the head piece of CTA bx + 1
+                    const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(c.ws) + kWsFixOff) + (size_t)(bx + 1) * 8 + gg;
+                    uint32_t v, e;
+                    for (long long spin = 0;; spin++) {
+                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
+                        if (e == epoch) break;
+                        if (spin > (1ll << 26)) __trap();
+                    }
+                    total += __uint_as_float(v);
+                }
+                return total;
+            };
+            auto finish = [&](int i, float total) {
+                const int r = row_lo + i;
+                if (r >= R) return;
+                T y = Elem<T>::from_f32(total);
+                const T* bias = reinterpret_cast<const T*>(a.bias);
+                if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + Elem<T>::to_f32(__ldcg(bias + r)));  // torch `out += bias`
+                reinterpret_cast<T*>(a.out)[r] = y;
+            };
+            if (a.ar_world > 1) {
+                // One-shot all-reduce in the epilogue (include/quantizations_b200.h: q4_allreduce_t): every partial travels as ONE 8-byte
+                // store {value, epoch} into every peer's exchange area; the owner of a row polls the W slots of that row until they
+                // carry the current epoch.  The same CTA owns the same rows on every rank (identical launch), launches are counted per
+                // CTA on the device, slots are double-buffered by epoch parity.
+                const int W = a.ar_world, me = a.ar_rank;
+                uint8_t* mine = reinterpret_cast<uint8_t*>(a.ar_peer_bases[me]);
+                const size_t halfsel = (size_t)(ar_epoch & 1) * W * a.ar_max_rows;
+                for (int i = tid; i < nrows_own; i += kCons) {
+                    if (row_lo + i >= R) continue;
+                    const float total = row_total(i);
+                    for (int p = 0; p < W; p++) {
+                        uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.ar_peer_bases[p]) + kArDataOffset) + halfsel +
+                                     (size_t)me * a.ar_max_rows + row_lo + i;
+                        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(total)), "r"(ar_epoch) : "memory");
+                    }
+                }
+                const uint2* slots = reinterpret_cast<const uint2*>(mine + kArDataOffset) + halfsel;
+                for (int i = tid; i < nrows_own; i += kCons) {
+                    if (row_lo + i >= R) continue;
+                    float total = 0.0f;
+                    for (int p = 0; p < W; p++) {  // rank order: every rank computes the same sum
+                        const uint2* src = slots + (size_t)p * a.ar_max_rows + row_lo + i;
+                        uint32_t v, e;
+                        for (long long spin = 0;; spin++) {
+                            asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
+                            if (e == ar_epoch) break;
+                            if (spin > (1ll << 26)) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
+                        }
+                        total += __uint_as_float(v);
+                    }
+                    finish(i, total);
+                }
+            } else {
+                for (int i = tid; i < nrows_own; i += kCons) finish(i, row_total(i));
+            }
+        }
+        if (tid == 0) mark(stage, 5);
+    }  // stage loop
+
+    // ---- leave the workspace ready for the next launch: the grid-barrier counter back at zero (last CTA), this CTA's epoch advanced
+    if (c.ws) {
+        bar_sync(kConsumerBar, kCons);
+        if (tid == 0) {
+            c.ws[kWsEpochOff / 4 + bx] = epoch_base + (uint32_t)c.n;
+            if (c.n > 1) {
+                __threadfence();
+                const unsigned old = atomicAdd(c.ws, 1u);
+                if (old == (unsigned)c.n * (unsigned)G - 1u) c.ws[0] = 0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host-side planning
+
+// how a stage's flat tile list is dealt to G CTAs.  split_ok (a workspace is available): tile granularity, a row tile may be cut
+// between two neighbouring CTAs -- never three: every active CTA gets at least KT tiles; else whole row tiles.
+inline void plan_stage(Stage& a, int rows, int K, int G, bool split_ok)
+{
+    a.rows = rows;
+    a.K = K;
+    a.KT = (K + 511) / 512;
+    const int RT = (rows + 7) / 8;
+    const long long units = (long long)RT * a.KT;
+    long long Q;
+    if (split_ok) {
+        a.gran = 1;
+        Q = units;
+        long long act = units / a.KT;  // = RT
+        a.active = (int)(act < G ? (act < 1 ? 1 : act) : G);
+    } else {
+        a.gran = a.KT;
+        Q = RT;
+        a.active = RT < G ? RT : G;
+    }
+    a.per = (int)(Q / a.active);
+    a.rem = (int)(Q % a.active);
+}
+
+// shared-memory plan of a launch: fills x_bytes / part_bytes / slots, returns the dynamic shared-memory size (0: does not fit)
+inline size_t plan_launch(Args& c, size_t max_smem = 226 * 1024, int max_slots = 96)
+{
+    c.x_bytes = 0;
+    c.part_bytes = 0;
+    for (int i = 0; i < c.n; i++) {
+        const Stage& a = c.st[i];
+        if (a.KT * 1024 > c.x_bytes) c.x_bytes = a.KT * 1024;
+        const int tiles = (a.per + (a.rem ? 1 : 0)) * a.gran;
+        if (tiles * 32 > c.part_bytes) c.part_bytes = tiles * 32;
+    }
+    c.part_bytes = (c.part_bytes + 127) & ~127;
+    const size_t fixed = (size_t)kLutBytes + c.x_bytes + c.part_bytes + 128 /* s_red */ + 64 /* s_misc */ + 8 /* table barrier */;
+    if (fixed + 4 * (kSlotBytes + 16) > max_smem) return 0;
+    int slots = (int)((max_smem - fixed) / (kSlotBytes + 16));
+    if (slots > max_slots) slots = max_slots;
+    c.slots = slots;
+    return fixed + (size_t)slots * (kSlotBytes + 16);
+}
+
+}  // namespace ring
+}  // namespace q4

@@ -9,8 +9,8 @@
 namespace q4 {
 
 // Called once after every kernel launch: bumps the launch counter (q4_launch_count) and returns the launch status
-// (the reference never checks: ops.cu:28,50,82-94,125-127,170).  cudaPeekAtLastError keeps sticky errors visible to
-// the caller's own checks.
+// (the reference never checks: ops.cu:28,50,82-94,125-127,170).  cudaGetLastError: a non-sticky launch error is reported
+// once and cleared; sticky errors stay visible to the caller's own checks anyway.
 int finish_launch();
 
 int quantize_4bit(const void* A, float* absmax, uint8_t* out, int blocksize, int64_t n, int quant_type, int in_dtype,

@@ -121,6 +121,8 @@ def graph_generate(model: torch.nn.Module, input_ids: torch.Tensor, max_new_toke
         raise ValueError("graph_generate decodes one sequence")
     dev = input_ids.device
     P = input_ids.shape[1]
+    if max_cache_len is not None and P + max_new_tokens + (3 if use_graph else 0) > max_cache_len:
+        raise ValueError(f"prompt ({P}) + max_new_tokens ({max_new_tokens}) + graph warm-up steps exceed max_cache_len ({max_cache_len})")
     cache = StaticCache(config=model.config, max_cache_len=max_cache_len or P + max_new_tokens + 8)
     out = model(input_ids, past_key_values=cache, cache_position=torch.arange(P, device=dev), use_cache=True)
     tok = out.logits[:, -1].argmax(-1, keepdim=True)

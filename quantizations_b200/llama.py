@@ -214,6 +214,12 @@ class Llama(nn.Module):
 
         dev = prompt.device
         P = prompt.shape[0]
+        # positions written: P prompt tokens, `new_tokens` decode steps, plus the warm-up / capture steps of the graph path (their
+        # tok / pos are restored, but they do run and do write cache rows P .. P+2)
+        last = P + new_tokens + (3 if use_graph else 0)
+        if last > self.cfg.max_len:
+            raise ValueError(f"prompt ({P}) + new_tokens ({new_tokens})" + (" + 3 graph warm-up steps" if use_graph else "")
+                             + f" = {last} exceeds the KV cache (cfg.max_len = {self.cfg.max_len})")
         logits = self.forward(prompt, torch.arange(P, device=dev))
         tok = logits.argmax().view(1)
         pos = torch.full((1,), P, device=dev, dtype=torch.int64)
