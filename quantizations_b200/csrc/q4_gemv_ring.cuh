@@ -36,20 +36,24 @@
 
 #include "q4_common.cuh"
 #include "q4_gemv_mma.cuh"
+#include "q4_tma.h"
 
 namespace q4 {
 namespace ring {
 
-constexpr int kSlotBytes = 2048;   // 8 rows x 256 packed bytes = two 128-byte-wide TMA boxes
+constexpr int kSub = 4;                     // 8-row sub-tiles per ring slot
+constexpr int kSlotBytes = kSub * 2048;     // 32 rows x 256 packed bytes = two 128-byte-wide, 32-row TMA boxes
+constexpr int kProdLanes = 4;               // producer lanes issuing slots in lockstep
 constexpr int kMaxStages = 4;
 constexpr int kConsumerBar = 1;    // named barrier of the consumer warps
 // workspace layout (Q4_GEMV_RING_WS_BYTES, zeroed once by the caller, owned by one stream at a time)
 constexpr int kWsEpochOff = 1024;  // u32 [kWsMaxCtas]: stages run so far, per CTA (tags of the split-tile hand-over)
-constexpr int kWsFixOff = 8192;    // {f32, u32} [kWsMaxCtas][8]: partial sums of the row tile a CTA shares with its predecessor
-constexpr int kWsMaxCtas = 1024;
+constexpr int kWsFixOff = 8192;    // {f32, u32} [kWsMaxCtas][32]: partial sums of the row group a CTA shares with its predecessor
+constexpr int kWsMaxCtas = 256;
+constexpr int kWsBytes = kWsFixOff + kWsMaxCtas * kSub * 8 * 8;
 
 struct Stage {
-    alignas(64) CUtensorMap map;  // packed weight as u8 [rows, K/2], box {128, 8}, SWIZZLE_128B
+    alignas(64) CUtensorMap map;  // packed weight as u8 [rows, K/2], box {128 bytes, 32 rows}, SWIZZLE_128B
     const void* x;
     const void* x_gate;      // optional: effective activation = silu(x_gate[k]) * x[k]
     const void* rms_weight;  // optional: effective activation = x * rsqrt(mean(x^2) + eps) * rms_weight
@@ -62,7 +66,7 @@ struct Stage {
     int rows, K;
     int KT;                  // ceil(K / 512): k tiles per row tile
     int multi;               // grouped launch with per-matrix offsets
-    int gran;                // units per assignment quantum: 1 (row tiles may be split between CTAs) or KT (never split)
+    int gran;                // slots per assignment quantum: 1 (a row group may be split between two CTAs) or KT (never split)
     int active, per, rem;    // CTA b < active owns quanta [b*per + min(b, rem), +per + (b < rem)); the others idle in this stage
     // fused one-shot all-reduce over tensor-parallel ranks (q4_allreduce_t), ar_world <= 1: off
     void* const* ar_peer_bases;
@@ -134,7 +138,9 @@ __device__ __forceinline__ unsigned long long gtime()
     return t;
 }
 
-// the CTA's range of a stage's flat tile list, in units (tiles)
+__device__ __forceinline__ int range_start(const Stage& a, int b) { return (b * a.per + (b < a.rem ? b : a.rem)) * a.gran; }
+
+// the CTA's range of a stage's flat slot list
 __device__ __forceinline__ void cta_range(const Stage& a, int b, int& u0, int& u1)
 {
     if (b >= a.active) {
@@ -145,7 +151,7 @@ __device__ __forceinline__ void cta_range(const Stage& a, int b, int& u0, int& u
     const int q1 = q0 + a.per + (b < a.rem ? 1 : 0);
     u0 = q0 * a.gran;
     u1 = q1 * a.gran;
-    const int total = ((a.rows + 7) >> 3) * a.KT;
+    const int total = ((a.rows + kSub * 8 - 1) / (kSub * 8)) * a.KT;
     if (u1 > total) u1 = total;  // gran == KT never overshoots; kept for safety
 }
 
@@ -210,17 +216,26 @@ __device__ __noinline__ void stage_x_glue(const void* x, const void* x_gate, con
     }
 }
 
-template <typename T, bool NESTED, int NC>
-__global__ void __launch_bounds__((NC + 1) * 32, 1)
+// NC consumer warps; WPS of them share a ring slot (each takes kSub / WPS of its sub-tiles)
+// With 16 consumer warps a 17th (producer) warp would cost every thread registers (5 warps on one scheduler: 96 per thread, and the
+// consumer loop spills).  The block then carries a whole producer warpgroup (warps NC .. NC+3, one of them working) that hands
+// its registers to the consumers with setmaxnreg: 24 for the producers, kConsumerRegs for the consumers.
+constexpr int ring_threads(int nc) { return nc >= 16 ? (nc + 4) * 32 : (nc + 1) * 32; }
+template <typename T, bool NESTED, int NC, int WPS>
+__global__ void __launch_bounds__(ring_threads(NC), 1)
 gemv_ring_kernel(const __grid_constant__ Args c)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // Shared-memory plan: [table 64 KB][ring: slots x 2 KB][x][partials][barriers][scratch].  The PRMT splice of the lookups needs
+    // Shared-memory plan: [table 64 KB][ring: slots x 8 KB][x][partials][barriers][scratch].  The PRMT splice of the lookups needs
     // the table at (64-KB aligned window address) + (compile-time immediate): it is the first thing in dynamic shared memory,
     // which starts kDynBase into the CTA's window (probed on the host, trapped here if violated).  kDynBase + 64 KB is a multiple
     // of 1024, which the 128-byte TMA swizzle of the ring slots needs.
     constexpr int kImm = kDynBase;
     constexpr int kCons = NC * 32;
+    constexpr int kWarpsPerSlot = WPS;
+    constexpr int NP = NC / kWarpsPerSlot;  // slots in work at once: ring sequence number q goes to warp group q % NP
+    static_assert(NC % kWarpsPerSlot == 0 && kSub % kWarpsPerSlot == 0, "warps per slot");
+    constexpr int kSubPerWarp = kSub / kWarpsPerSlot;
     const uint32_t smem_saddr = smem_u32(smem);
     if (smem_saddr != kDynBase) __trap();
     uint8_t* lut = smem;
@@ -244,11 +259,11 @@ gemv_ring_kernel(const __grid_constant__ Args c)
     };
 
     pdl_launch_dependents();
-    if (tid == NC * 32) {  // producer lane: barriers first
+    if (tid == NC * 32) {  // producer lane 0: barriers first
         mbar_init(bar0, 1);
         for (int i = 0; i < D; i++) {
             mbar_init(full(i), 1);
-            mbar_init(empty(i), 1);
+            mbar_init(empty(i), kWarpsPerSlot);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_misc[0] = 0;
@@ -256,108 +271,139 @@ gemv_ring_kernel(const __grid_constant__ Args c)
     }
     __syncthreads();
 
-    if (warp == NC) {
-        // ============================================================ producer
-        if (lane == 0) {
-            if (c.lut) {  // table image: one expect, four bulk copies
-                mbar_expect_tx(bar0, kLutBytes);
+    constexpr bool kRegSplit = NC >= 16;
+    if (warp >= NC) {
+        if (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        // ============================================================ producer (warp NC; the rest of its warpgroup only donates registers)
+        if (warp != NC) return;
+        if (lane == 0 && c.lut) {  // table image: one expect, four bulk copies
+            mbar_expect_tx(bar0, kLutBytes);
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     smem_saddr + i * (kLutBytes / 4)),
-                                 "l"(reinterpret_cast<const uint8_t*>(c.lut) + i * (kLutBytes / 4)), "r"(kLutBytes / 4), "r"(bar0)
-                                 : "memory");
-            }
-            int pos = 0;
-            uint32_t ph = 0;
+            for (int i = 0; i < 4; i++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_saddr + i * (kLutBytes / 4)),
+                             "l"(reinterpret_cast<const uint8_t*>(c.lut) + i * (kLutBytes / 4)), "r"(kLutBytes / 4), "r"(bar0)
+                             : "memory");
+        }
+        if (lane < kProdLanes) {
+            // kProdLanes lanes in lockstep, lane l taking slots l, l + kProdLanes, ... of the CTA's sequence: the latency of the
+            // empty-barrier probe and the issue cost of the copies are paid once per kProdLanes slots
+            int base = 0;
             for (int s = 0; s < c.n; s++) {
                 const Stage& a = c.st[s];
-                int u0, u1;
-                cta_range(a, bx, u0, u1);
-                const int KT = a.KT, half = a.K >> 1;
-                int rt = u0 / KT, kt = u0 - rt * KT;
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map) : "memory");
-                mark(s, 6);
-                for (int u = u0; u < u1; u++) {
+                int S0, S1;
+                cta_range(a, bx, S0, S1);
+                const int n = S1 - S0, KT = a.KT, half = a.K >> 1;
+                if (lane == 0) {
+                    asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map) : "memory");
+                    mark(s, 6);
+                }
+                // lane l fills the ring sequence numbers q = l (mod kProdLanes); D is a multiple of kProdLanes, so a ring position is
+                // always filled by the same lane, fill after fill: its parity wait can never alias an older phase
+                int i = lane - base % kProdLanes;
+                if (i < 0) i += kProdLanes;
+                int rg = (S0 + i) / KT, kt = (S0 + i) - rg * KT;
+                int pos;
+                uint32_t ph;
+                {
+                    const int q = base + i, w = q / D;
+                    pos = q - w * D;
+                    ph = (uint32_t)w & 1u;
+                }
+                const int d_rg = kProdLanes / KT, d_kt = kProdLanes - d_rg * KT;
+                const int d_wrap = kProdLanes / D, d_pos = kProdLanes - d_wrap * D;
+                while (i < n) {
                     mbar_wait(empty(pos), ph ^ 1u);
                     const uint32_t dst = ring_saddr + (uint32_t)pos * kSlotBytes;
                     const bool two = kt * 256 + 128 < half;  // a ragged last k tile may hold one box only
                     mbar_expect_tx(full(pos), two ? kSlotBytes : kSlotBytes / 2);
-                    tma_load_2d(dst, &a.map, kt * 256, rt * 8, full(pos));
-                    if (two) tma_load_2d(dst + 1024, &a.map, kt * 256 + 128, rt * 8, full(pos));
-                    if (++kt == KT) {
-                        kt = 0;
-                        rt++;
+                    tma_load_2d(dst, &a.map, kt * 256, rg * 32, full(pos));
+                    if (two) tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 32, full(pos));
+                    i += kProdLanes;
+                    rg += d_rg;
+                    kt += d_kt;
+                    if (kt >= KT) {
+                        kt -= KT;
+                        rg++;
                     }
-                    if (++pos == D) {
-                        pos = 0;
+                    pos += d_pos;
+                    ph ^= (uint32_t)d_wrap & 1u;
+                    if (pos >= D) {
+                        pos -= D;
                         ph ^= 1u;
                     }
                 }
-                mark(s, 7);
+                base += n;
+                if (lane == 0) mark(s, 7);
             }
         }
         return;
     }
 
     // ================================================================ consumers
+    if (kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int g = lane >> 2, t4 = lane & 3;
-    // byte offsets of the lane's four 16-byte pieces inside a slot: row g of the 8 x 128-byte box, chunks 2*t4, 2*t4+1 (block t4
+    const int grp = warp / kWarpsPerSlot, wh = warp % kWarpsPerSlot;  // warp group (slot owner) and the warp's share of the slot's sub-tiles
+    // byte offsets of the lane's 16-byte pieces inside a sub-tile: row g of the 8 x 128-byte block, chunks 2*t4, 2*t4+1 (block t4
     // of the half) as the 128-byte swizzle stores them (chunk ^ row)
     const uint32_t off_a0 = (uint32_t)(g * 128 + (((2 * t4) ^ g) << 4)), off_a1 = (uint32_t)(g * 128 + (((2 * t4 + 1) ^ g) << 4));
     const uint32_t lane_base = (uint32_t)(lane * 4);  // table window address is 0: the PRMT splice needs only the lane's word
     const bool xrole = t4 == (g & 3);  // this lane feeds column g of the B operand: x of the tile's block g
     const uint32_t x_saddr = smem_u32(s_x), xswz = (uint32_t)(g * 16);
     uint32_t epoch_base = 0;  // stages this CTA ran in earlier launches (workspace counter): read after griddepcontrol.wait
-    int base_seq = 0;  // tiles this CTA has taken from the ring in earlier stages
+    int base_seq = 0;         // slots this CTA has taken from the ring in earlier stages
 
     for (int stage = 0; stage < c.n; stage++) {
         const Stage& a = c.st[stage];
         const int K = a.K, R = a.rows, KT = a.KT;
         const int bpr = K >> 6;
-        int u0, u1;
-        cta_range(a, bx, u0, u1);
-        const int nloc = u1 - u0;
+        int S0, S1;
+        cta_range(a, bx, S0, S1);
+        const int nloc = S1 - S0;
         const bool MULTI = a.multi != 0;
         float off[kMaxMats];
 #pragma unroll
         for (int m = 0; m < kMaxMats; m++) off[m] = (NESTED && (MULTI || m == 0) && a.offsets[m]) ? __ldg(a.offsets[m]) : 0.0f;
-        // ---- the warp's tiles: local index j = warp, warp + NC, ...; ring position and phase of the first one
-        struct Cursor { int j, rt, kt; };
+        // ---- the warp's slots: ring sequence numbers q = base_seq + i with q % NP == grp, i.e. local index i = i0, i0 + NP, ...
+        // D is a multiple of NP: a ring position always belongs to the same warp group, which meets every fill of it in order -- a
+        // parity wait can never alias an older phase.  Within a stage the group's k tile is constant whenever NP % KT == 0.
+        struct Cursor { int i, rg, kt; };
         Cursor cur;
         {
-            const int u = u0 + warp;
-            cur.j = warp;
-            cur.rt = u / KT;
-            cur.kt = u - cur.rt * KT;
+            int i0 = grp - (base_seq % NP);
+            if (i0 < 0) i0 += NP;
+            const int S = S0 + i0;
+            cur.i = i0;
+            cur.rg = S / KT;
+            cur.kt = S - cur.rg * KT;
         }
-        const int d_rt = NC / KT, d_kt = NC - d_rt * KT;
+        const int d_rg = NP / KT, d_kt = NP - d_rg * KT;
         auto advance = [&](Cursor& q) {
-            q.j += NC;
-            q.rt += d_rt;
+            q.i += NP;
+            q.rg += d_rg;
             q.kt += d_kt;
             if (q.kt >= KT) {
                 q.kt -= KT;
-                q.rt++;
+                q.rg++;
             }
         };
         int pos;
         uint32_t ph;
         {
-            const int seq = base_seq + warp;
+            const int seq = base_seq + cur.i;
             const int w = seq / D;
             pos = seq - w * D;
             ph = (uint32_t)w & 1u;
         }
-        const int d_wrap = NC / D, d_pos = NC - d_wrap * D;
+        const int d_wrap = NP / D, d_pos = NP - d_wrap * D;
 
-        // absmax of the lane's two blocks (2*t4, 2*t4+1 of row g of the tile), fetched one tile ahead
-        struct Stat { uint32_t q; float s0, s1; };
-        auto load_stat = [&](const Cursor& q) {
+        // absmax of the lane's two blocks (2*t4, 2*t4+1 of row g of a sub-tile), fetched one slot ahead
+        struct Stat { uint32_t q; float s0; };  // nested: two 8-bit codes + their second-level absmax; else the two fp32 absmax values
+        auto load_stat = [&](const Cursor& q, int sub) {
             Stat r;
             r.q = 0;
-            r.s0 = r.s1 = 0.0f;
-            const int row = q.rt * 8 + g;
+            r.s0 = 0.0f;
+            const int row = (q.rg * kSub + sub) * 8 + g;
             const int blk = q.kt * 8 + 2 * t4;
             if (blk < bpr) {  // bpr is even: the pair is valid together
                 const int sb = (row < R ? row : R - 1) * bpr + blk;  // rows past the end read a valid row and are never stored
@@ -365,17 +411,26 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     r.q = __ldg(reinterpret_cast<const unsigned short*>(a.s.qabsmax + sb));
                     r.s0 = __ldg(a.s.absmax2 + (sb >> a.s.shift2));
                 } else {
-                    const float2 f = __ldg(reinterpret_cast<const float2*>(a.s.absmax + sb));
-                    r.s0 = f.x;
-                    r.s1 = f.y;
+                    const float2 f2 = __ldg(reinterpret_cast<const float2*>(a.s.absmax + sb));
+                    r.q = __float_as_uint(f2.x);
+                    r.s0 = f2.y;
                 }
             }
             return r;
         };
-        Stat st_cur = {0, 0.0f, 0.0f};
-        if (cur.j < nloc) st_cur = load_stat(cur);  // statistics do not depend on the previous stage: before the barrier
+        Stat st_cur[kSubPerWarp];
+#pragma unroll
+        for (int q2 = 0; q2 < kSubPerWarp; q2++) {
+            st_cur[q2].q = 0;
+            st_cur[q2].s0 = 0.0f;
+            if (cur.i < nloc) st_cur[q2] = load_stat(cur, wh * kSubPerWarp + q2);  // statistics do not depend on the previous stage: before the barrier
+        }
 
         // ---- everything below may read the previous kernel's (stage 0) or the previous stage's output
+        // A plain activation whose k tile is the same for all of a warp group's slots (NP % KT == 0: K = 4096 with 16 consumer warps)
+        // is not staged at all: the lanes that feed the B operand read their 64 activations straight from global memory (L2) into
+        // registers -- no shared-memory pass, no CTA-wide barrier after the grid barrier.
+        const bool private_x = false;  // measured: 16 warps x 148 CTAs hammering the same 8 KB of L2 costs ~3 us per stage; staged once per CTA instead
         if (tid == 0) mark(stage, 1);
         if (stage == 0) {
             pdl_wait();
@@ -384,8 +439,8 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             // grid-wide barrier of the consumers: every CTA's stores of the previous stage are visible afterwards
             bar_sync(kConsumerBar, kCons);
             if (tid == 0) {
-                __threadfence();
-                atomicAdd(c.ws, 1u);
+                // release at gpu scope: cumulative over what the bar.sync above ordered before this thread, i.e. every store of the CTA
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.ws), "r"(1u) : "memory");
                 const unsigned target = (unsigned)stage * (unsigned)G;
                 unsigned v;
                 for (long long spin = 0;; spin++) {
@@ -393,69 +448,125 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     if (v >= target) break;
                     if (spin > (1ll << 27)) __trap();  // a CTA never arrived: fail loudly instead of hanging the GPU
                 }
+                s_misc[0] = 0;  // head-piece counter of this stage
             }
             bar_sync(kConsumerBar, kCons);
         }
         if (tid == 0) mark(stage, 2);
 
-        {
+        if (!private_x) {
             const int nchunk = K >> 3;  // 16-byte chunks of x
             const int npad = KT * 64;   // staged chunks (zero tail up to whole tiles)
             if (a.x_gate || a.rms_weight) {
                 stage_x_glue<T>(a.x, a.x_gate, a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, npad, tid, kCons);
             } else {
-                for (int cb = tid; cb < npad; cb += 4 * kCons) {
-                    uint4 v[4];
+                constexpr int kU = NC >= 16 ? 4 : 8;  // loads in flight per thread: the whole vector in one round trip
+                for (int cb = tid; cb < npad; cb += kU * kCons) {
+                    uint4 v[kU];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < kU; j++) {
                         const int cc = cb + j * kCons;
                         v[j] = make_uint4(0, 0, 0, 0);
                         if (cc < nchunk) v[j] = __ldcg(reinterpret_cast<const uint4*>(a.x) + cc);  // coherent: may be a previous stage's output
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < kU; j++) {
                         const int cc = cb + j * kCons;
                         if (cc < npad) s_x[(cc & ~7) | ((cc ^ (cc >> 3)) & 7)] = v[j];
                     }
                 }
             }
-            if (tid == 0) s_misc[0] = 0;  // head-piece counter of this stage
         }
-        if (stage == 0) {
-            if (!c.lut) {  // callers without a prebuilt image: build the table here
-                const float* code2 = a.s.code2;
-                for (int cc = tid; cc < kLutBytes / 16; cc += kCons) {
-                    const int seg = cc >> 3, b = seg >> 1;
-                    uint32_t word;
-                    if (seg & 1) word = NESTED ? __float_as_uint(__ldg(code2 + b)) : 0u;
-                    else word = pack2<T>(__ldg(c.code + (b >> 4)), __ldg(c.code + (b & 15)));
-                    *reinterpret_cast<uint4*>(lut + cc * 16) = make_uint4(word, word, word, word);
-                }
+        if (stage == 0 && !c.lut) {  // callers without a prebuilt image: build the table here
+            const float* code2 = a.s.code2;
+            for (int cc = tid; cc < kLutBytes / 16; cc += kCons) {
+                const int seg = cc >> 3, b = seg >> 1;
+                uint32_t word;
+                if (seg & 1) word = NESTED ? __float_as_uint(__ldg(code2 + b)) : 0u;
+                else word = pack2<T>(__ldg(c.code + (b >> 4)), __ldg(c.code + (b & 15)));
+                *reinterpret_cast<uint4*>(lut + cc * 16) = make_uint4(word, word, word, word);
             }
         }
-        bar_sync(kConsumerBar, kCons);
+        if (stage == 0 || !private_x) bar_sync(kConsumerBar, kCons);
         if (stage == 0 && c.lut) mbar_wait(bar0, 0);  // table landed?
         if (stage == 0) epoch_base = s_misc[1];
-        const uint32_t epoch = epoch_base + (uint32_t)stage + 1u;  // tag of this stage's split-tile hand-over
+        const uint32_t epoch = epoch_base + (uint32_t)stage + 1u;  // tag of this stage's split-row-group hand-over
         if (tid == 0) mark(stage, 3);
 
-        // split row tiles of this CTA's range: `head` tiles at its start belong to a row tile that began in the previous CTA
-        const int rt_first = nloc > 0 ? u0 / KT : 0;
-        const int head = (nloc > 0 && u0 > rt_first * KT) ? ((rt_first + 1) * KT - u0 < nloc ? (rt_first + 1) * KT - u0 : nloc) : 0;
+        // split row groups of this CTA's range: the first `head` slots belong to a row group that began in the previous CTA
+        const int head = (nloc > 0 && (S0 % KT) != 0) ? (KT - S0 % KT < nloc ? KT - S0 % KT : nloc) : 0;
 
-        // ---- main loop
+        // ---- main loop: the warp's sub-tiles as ONE continuous stream.  The table lookups run kAhead MMAs ahead of the tensor pipe
+        // and keep running across sub-tile and slot boundaries: the next sub-tile's packed bytes replace the current one's in the
+        // same registers as soon as those are dead (words 0-3 after MMA 7, words 4-7 after the lookups of MMA 15), so a warp never
+        // drains its pipeline between sub-tiles and a slot is released as soon as its last byte has been copied out.
         uint32_t xr[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) xr[i] = 0;
         int kt_loaded = -1;
+        constexpr int kAhead = 3;
+        uint32_t wa[8], wb[8];        // packed bytes of (row g, block t4) and (row g, block 4 + t4) of the sub-tile in work
+        uint32_t f[kAhead + 1][4];    // looked-up A fragments in flight
+        auto fetch = [&](uint32_t (&d)[4], int j) {
+            const uint32_t va = wa[j >> 1], vb = wb[j >> 1];
+#ifdef Q4_RING_EXPERIMENT_SKIPLOOKUP  // developer experiment (wrong results): every 4th MMA step decodes without shared-memory lookups
+            if ((j & 3) == 3) {
+                d[0] = va ^ 0x3c003c00u; d[1] = vb ^ 0x3c003c00u; d[2] = (va >> 1) ^ 0x3c003c00u; d[3] = (vb >> 1) ^ 0x3c003c00u;
+                return;
+            }
+#endif
+            if (j & 1) {
+                d[0] = lut_lookup<2, kImm>(va, lane_base); d[1] = lut_lookup<2, kImm>(vb, lane_base);
+                d[2] = lut_lookup<3, kImm>(va, lane_base); d[3] = lut_lookup<3, kImm>(vb, lane_base);
+            } else {
+                d[0] = lut_lookup<0, kImm>(va, lane_base); d[1] = lut_lookup<0, kImm>(vb, lane_base);
+                d[2] = lut_lookup<1, kImm>(va, lane_base); d[3] = lut_lookup<1, kImm>(vb, lane_base);
+            }
+        };
+        auto load_lo = [&](uint32_t sa) {  // words 0-3 of both pieces
+            const uint4 a0 = lds128(sa + off_a0), b0 = lds128(sa + kSlotBytes / 2 + off_a0);
+            wa[0] = a0.x; wa[1] = a0.y; wa[2] = a0.z; wa[3] = a0.w;
+            wb[0] = b0.x; wb[1] = b0.y; wb[2] = b0.z; wb[3] = b0.w;
+        };
+        auto load_hi = [&](uint32_t sa) {  // words 4-7
+            const uint4 a1 = lds128(sa + off_a1), b1 = lds128(sa + kSlotBytes / 2 + off_a1);
+            wa[4] = a1.x; wa[5] = a1.y; wa[6] = a1.z; wa[7] = a1.w;
+            wb[4] = b1.x; wb[5] = b1.y; wb[6] = b1.z; wb[7] = b1.w;
+        };
+        auto sub_addr = [&](int p, int q2) { return ring_saddr + (uint32_t)p * kSlotBytes + (uint32_t)((wh * kSubPerWarp + q2) * 1024); };
 
-        while (cur.j < nloc) {
+        if (cur.i < nloc) {  // prologue: the first sub-tile's bytes and its first lookups
+            mbar_wait(full(pos), ph);
+            const uint32_t sa = sub_addr(pos, 0);
+            load_lo(sa);
+            load_hi(sa);
+            if (kSubPerWarp == 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty(pos));
+            }
+#pragma unroll
+            for (int j = 0; j < kAhead; j++) fetch(f[j], j);
+        }
+
+        while (cur.i < nloc) {
             Cursor nxt = cur;
             advance(nxt);
-            Stat st_nxt = {0, 0.0f, 0.0f};
-            if (nxt.j < nloc) st_nxt = load_stat(nxt);
+            int pos_n = pos + d_pos;
+            uint32_t ph_n = ph ^ ((uint32_t)d_wrap & 1u);
+            if (pos_n >= D) {
+                pos_n -= D;
+                ph_n ^= 1u;
+            }
+            const bool has_next = nxt.i < nloc;
+            Stat st_nxt[kSubPerWarp];
+#pragma unroll
+            for (int q2 = 0; q2 < kSubPerWarp; q2++) {
+                st_nxt[q2].q = 0;
+                st_nxt[q2].s0 = 0.0f;
+                if (has_next) st_nxt[q2] = load_stat(nxt, wh * kSubPerWarp + q2);
+            }
 
-            if (cur.kt != kt_loaded) {  // warp-uniform
+            if (cur.kt != kt_loaded) {  // warp-uniform; the lookups in flight do not depend on it
                 if (xrole) {
                     // chunk i of block kt*8+g sits at piece i ^ g: byte offset (kt*1024 + g*128 + i*16) ^ (g*16)
                     const uint32_t xb = x_saddr + (uint32_t)(cur.kt * 1024 + g * 128);
@@ -468,67 +579,87 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 kt_loaded = cur.kt;
             }
 
-            // the tile's packed bytes: slot -> registers, slot released at once
-            mbar_wait(full(pos), ph);
-            const uint32_t sl = ring_saddr + (uint32_t)pos * kSlotBytes;
-            const uint4 a0 = lds128(sl + off_a0), a1 = lds128(sl + off_a1);
-            const uint4 b0 = lds128(sl + 1024 + off_a0), b1 = lds128(sl + 1024 + off_a1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty(pos));
-            const uint32_t wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const uint32_t wb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-
-            // MMA j covers bytes 2j, 2j+1 of both pieces = k 4j .. 4j+3 of the lane's blocks.  The lookups run kAhead MMAs ahead of
-            // the tensor pipe (software pipeline, everything unrolled).
-            float ce[4] = {0.0f, 0.0f, 0.0f, 0.0f}, co[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            constexpr int kAhead = 3;
-            uint32_t f[kAhead + 1][4];
-            auto fetch = [&](uint32_t (&d)[4], int j) {
-                const uint32_t va = wa[j >> 1], vb = wb[j >> 1];
-                if (j & 1) {
-                    d[0] = lut_lookup<2, kImm>(va, lane_base); d[1] = lut_lookup<2, kImm>(vb, lane_base);
-                    d[2] = lut_lookup<3, kImm>(va, lane_base); d[3] = lut_lookup<3, kImm>(vb, lane_base);
+#pragma unroll
+            for (int q2 = 0; q2 < kSubPerWarp; q2++) {
+                const int sub = wh * kSubPerWarp + q2;
+                const bool last_sub = q2 == kSubPerWarp - 1;
+                // what follows this sub-tile in the warp's stream: the slot's next sub-tile, or the first one of the warp's next slot
+                const uint32_t sa_next = last_sub ? sub_addr(pos_n, 0) : sub_addr(pos, q2 + 1);
+                const bool follows = last_sub ? has_next : true;
+                float ce[4] = {0.0f, 0.0f, 0.0f, 0.0f}, co[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#ifdef Q4_RING_EXPERIMENT_NOCOMPUTE  // developer experiment (wrong results): the ring's streaming rate without the decode
+                {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc ^= wa[j] ^ wb[j];
+                    ce[0] = __uint_as_float(acc & 0x3fffffffu);
+                    if (follows) {
+                        if (last_sub) mbar_wait(full(pos_n), ph_n);
+                        load_lo(sa_next);
+                        load_hi(sa_next);
+                        const bool rel = last_sub ? kSubPerWarp == 1 : q2 + 1 == kSubPerWarp - 1;
+                        if (rel) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(empty(last_sub ? pos_n : pos));
+                        }
+                    }
+                }
+#else
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    // MMA j covers bytes 2j, 2j+1 of both pieces = k 4j .. 4j+3 of the lane's blocks; lookups kAhead MMAs ahead, wrapping
+                    // into the following sub-tile (whose words 0-3 are in place from j == 8 on)
+                    fetch(f[(j + kAhead) % (kAhead + 1)], (j + kAhead) % 16);
+                    uint32_t(&a4)[4] = f[j % (kAhead + 1)];
+#ifdef Q4_RING_EXPERIMENT_NOMMA  // developer experiment (wrong results): the lookups without the tensor pipe
+                    ce[j & 3] = __uint_as_float((__float_as_uint(ce[j & 3]) ^ a4[0] ^ a4[1] ^ a4[2] ^ a4[3] ^ xr[2 * j]) & 0x3fffffffu);
+#else
+                    if (j & 1) Hmma<T>::run(co, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
+                    else Hmma<T>::run(ce, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
+#endif
+                    if (j == 8 && follows) {  // words 0-3 are dead (last used by the lookups of MMA 7, issued at j == 4)
+                        if (last_sub) mbar_wait(full(pos_n), ph_n);
+                        load_lo(sa_next);
+                    }
+                    if (j == 12 && follows) {  // words 4-7 are dead (the lookups of MMA 15 were issued above)
+                        load_hi(sa_next);
+                        // the warp holds every byte it needs of a slot once the bytes of its last sub-tile there are in registers
+                        const bool rel = last_sub ? kSubPerWarp == 1 : q2 + 1 == kSubPerWarp - 1;
+                        if (rel) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(empty(last_sub ? pos_n : pos));
+                        }
+                    }
+                }
+#endif
+                // the lane's two useful sums: blocks 2t, 2t+1 of the tile (columns 2t, 2t+1; first half -> rows 0-7, second -> 8-15)
+                const float u0s = t4 < 2 ? ce[0] + co[0] : ce[2] + co[2];
+                const float u1s = t4 < 2 ? ce[1] + co[1] : ce[3] + co[3];
+                float am0, am1;
+                if (NESTED) {
+                    float o = off[0];
+                    if (MULTI) {
+                        const int row = (cur.rg * kSub + sub) * 8 + g;
+                        o = row < a.row_end[0] ? off[0] : (row < a.row_end[1] ? off[1] : (row < a.row_end[2] ? off[2] : off[3]));
+                    }
+                    const float q0 = __uint_as_float(lut_lookup<0, kImm + 128>(st_cur[q2].q, lane_base));
+                    const float q1 = __uint_as_float(lut_lookup<1, kImm + 128>(st_cur[q2].q, lane_base));
+                    am0 = __fadd_rn(__fmul_rn(q0, st_cur[q2].s0), o);  // reference: kernels.cu:552 then core.py:468
+                    am1 = __fadd_rn(__fmul_rn(q1, st_cur[q2].s0), o);
+                    if (cur.kt * 8 + 2 * t4 >= bpr) am0 = am1 = 0.0f;  // ragged k tile: blocks past the row's end
                 } else {
-                    d[0] = lut_lookup<0, kImm>(va, lane_base); d[1] = lut_lookup<0, kImm>(vb, lane_base);
-                    d[2] = lut_lookup<1, kImm>(va, lane_base); d[3] = lut_lookup<1, kImm>(vb, lane_base);
+                    am0 = __uint_as_float(st_cur[q2].q);
+                    am1 = st_cur[q2].s0;
                 }
-            };
-#pragma unroll
-            for (int j = 0; j < kAhead; j++) fetch(f[j], j);
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (j + kAhead < 16) fetch(f[(j + kAhead) % (kAhead + 1)], j + kAhead);
-                uint32_t(&a4)[4] = f[j % (kAhead + 1)];
-                if (j & 1) Hmma<T>::run(co, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
-                else Hmma<T>::run(ce, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
+                float part = fmaf(u0s, am0, u1s * am1);
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                if (t4 == 0) s_part[(cur.i * kSub + sub) * 8 + g] = part;
             }
-            // the lane's two useful sums: blocks 2t, 2t+1 of the tile (columns 2t, 2t+1; first half -> rows 0-7, second -> 8-15)
-            const float u0s = t4 < 2 ? ce[0] + co[0] : ce[2] + co[2];
-            const float u1s = t4 < 2 ? ce[1] + co[1] : ce[3] + co[3];
-            float am0, am1;
-            if (NESTED) {
-                float o = off[0];
-                if (MULTI) {
-                    const int row = cur.rt * 8 + g;
-                    o = row < a.row_end[0] ? off[0] : (row < a.row_end[1] ? off[1] : (row < a.row_end[2] ? off[2] : off[3]));
-                }
-                const float q0 = __uint_as_float(lut_lookup<0, kImm + 128>(st_cur.q, lane_base));
-                const float q1 = __uint_as_float(lut_lookup<1, kImm + 128>(st_cur.q, lane_base));
-                am0 = __fadd_rn(__fmul_rn(q0, st_cur.s0), o);  // reference: kernels.cu:552 then core.py:468
-                am1 = __fadd_rn(__fmul_rn(q1, st_cur.s0), o);
-                if (cur.kt * 8 + 2 * t4 >= bpr) am0 = am1 = 0.0f;  // ragged k tile: blocks past the row's end
-            } else {
-                am0 = st_cur.s0;
-                am1 = st_cur.s1;
-            }
-            float part = fmaf(u0s, am0, u1s * am1);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (t4 == 0) s_part[cur.j * 8 + g] = part;
 
-            if (cur.j < head) {
-                // this tile belongs to the row tile shared with the previous CTA: the warp that completes the head piece publishes
-                // its 8 partial sums (fixed order over the k tiles) for the owner
+            if (cur.i < head) {
+                // this slot belongs to the row group shared with the previous CTA: the warp that completes the head piece publishes
+                // its 32 partial sums (fixed order over the k tiles) for the owner
                 __syncwarp();
                 unsigned old = 0;
                 if (lane == 0) {
@@ -536,30 +667,27 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     old = atomicAdd(&s_misc[0], 1u);
                 }
                 old = __shfl_sync(0xffffffffu, old, 0);
-                if (old == (unsigned)head - 1u && lane < 8) {
+                if (old == (unsigned)(head * kWarpsPerSlot) - 1u) {
                     __threadfence_block();
                     float total = 0.0f;
-                    for (int j = 0; j < head; j++) total += reinterpret_cast<volatile float*>(s_part)[j * 8 + lane];
-                    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c.ws) + kWsFixOff) + (size_t)bx * 8 + lane;
+                    for (int j = 0; j < head; j++) total += reinterpret_cast<volatile float*>(s_part)[j * (kSub * 8) + lane];
+                    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c.ws) + kWsFixOff) + (size_t)bx * (kSub * 8) + lane;
                     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(total)), "r"(epoch) : "memory");
                 }
             }
 
             cur = nxt;
-            st_cur = st_nxt;
-            pos += d_pos;
-            ph ^= (uint32_t)d_wrap & 1u;
-            if (pos >= D) {
-                pos -= D;
-                ph ^= 1u;
-            }
+#pragma unroll
+            for (int q2 = 0; q2 < kSubPerWarp; q2++) st_cur[q2] = st_nxt[q2];
+            pos = pos_n;
+            ph = ph_n;
         }
         base_seq += nloc;
         if (tid == 0) mark(stage, 4);
         bar_sync(kConsumerBar, kCons);
 
-        // ---- fixed-order sum over the k tiles of every row tile this CTA owns (= holds the first k tile of), [the partner's
-        //      partials of a split row tile,] [all-reduce over tensor-parallel ranks,] bias / residual, store
+        // ---- fixed-order sum over the k tiles of every row group this CTA owns (= holds the first k tile of), [the partner's
+        //      partials of a split row group,] [all-reduce over tensor-parallel ranks,] bias / residual, store
         uint32_t ar_epoch = 0;
         if (a.ar_world > 1) {
             // exchanges are counted per CTA in the rank's own exchange area, by EVERY CTA whether or not it owns rows in this stage: all
@@ -574,26 +702,33 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             ar_epoch = s_misc[2];
         }
         if (nloc > 0) {
-            const int rt_own0 = (u0 + KT - 1) / KT;   // first row tile whose k tile 0 lies in [u0, u1)
-            const int rt_own1 = (u1 + KT - 1) / KT;   // one past the last
-            const int nrows_own = (rt_own1 - rt_own0) * 8;
-            const int row_lo = rt_own0 * 8;
+            constexpr int kRows = kSub * 8;           // rows per row group
+            const int rg_own0 = (S0 + KT - 1) / KT;   // first row group whose k tile 0 lies in [S0, S1)
+            const int rg_own1 = (S1 + KT - 1) / KT;   // one past the last
+            const int nrows_own = (rg_own1 - rg_own0) * kRows;
+            const int row_lo = rg_own0 * kRows;
             auto row_total = [&](int i) {  // i = row index relative to row_lo
-                const int rt = rt_own0 + (i >> 3), gg = i & 7;
-                const int j0 = rt * KT - u0;
+                const int rg = rg_own0 + i / kRows, v = i % kRows;
+                const int j0 = rg * KT - S0;
                 const int j1 = j0 + KT < nloc ? j0 + KT : nloc;
+                const bool cut = j0 + KT > nloc;  // split row group: its remaining k tiles are the head pieces of the following CTAs
+                const uint2* fix = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(c.ws) + kWsFixOff) + v;
+                uint32_t val = 0, e = 0;
+                if (cut)  // first probe of the next CTA's piece: in flight while the own partials are summed
+                    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(e) : "l"(fix + (size_t)(bx + 1) * kRows) : "memory");
                 float total = 0.0f;
-                for (int j = j0; j < j1; j++) total += s_part[j * 8 + gg];
-                if (j0 + KT > nloc) {
-                    // split row tile: its remaining k tiles are the head piece of CTA bx + 1
-                    const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(c.ws) + kWsFixOff) + (size_t)(bx + 1) * 8 + gg;
-                    uint32_t v, e;
-                    for (long long spin = 0;; spin++) {
-                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
-                        if (e == epoch) break;
-                        if (spin > (1ll << 26)) __trap();
+                for (int j = j0; j < j1; j++) total += s_part[j * kRows + v];
+                if (cut) {
+                    const int gend = (rg + 1) * KT;
+                    for (int b2 = bx + 1; b2 < a.active && range_start(a, b2) < gend; b2++) {  // pieces added in CTA order
+                        const uint2* src = fix + (size_t)b2 * kRows;
+                        for (long long spin = 0;; spin++) {
+                            if (spin || b2 != bx + 1) asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(e) : "l"(src) : "memory");
+                            if (e == epoch) break;
+                            if (spin > (1ll << 26)) __trap();
+                        }
+                        total += __uint_as_float(val);
                     }
-                    total += __uint_as_float(v);
                 }
                 return total;
             };
@@ -608,8 +743,8 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             if (a.ar_world > 1) {
                 // One-shot all-reduce in the epilogue (include/quantizations_b200.h: q4_allreduce_t): every partial travels as ONE 8-byte
                 // store {value, epoch} into every peer's exchange area; the owner of a row polls the W slots of that row until they
-                // carry the current epoch.  The same CTA owns the same rows on every rank (identical launch), launches are counted per
-                // CTA on the device, slots are double-buffered by epoch parity.
+                // carry the current epoch.  The same CTA owns the same rows on every rank (identical launch), slots are double-buffered
+                // by epoch parity (a fast peer may start its next exchange while this rank still reads the current one).
                 const int W = a.ar_world, me = a.ar_rank;
                 uint8_t* mine = reinterpret_cast<uint8_t*>(a.ar_peer_bases[me]);
                 const size_t halfsel = (size_t)(ar_epoch & 1) * W * a.ar_max_rows;
@@ -661,21 +796,36 @@ gemv_ring_kernel(const __grid_constant__ Args c)
 
 // ---------------------------------------------------------------------------------------------- host-side planning
 
-// how a stage's flat tile list is dealt to G CTAs.  split_ok (a workspace is available): tile granularity, a row tile may be cut
-// between two neighbouring CTAs -- never three: every active CTA gets at least KT tiles; else whole row tiles.
-inline void plan_stage(Stage& a, int rows, int K, int G, bool split_ok)
+// tensor map of a packed weight for the ring's slots: u8 [rows, K/2], box = one half (128 bytes) of a k tile x one row group
+inline bool make_weight_map(CUtensorMap* m, const void* B, int64_t rows, int64_t K)
+{
+    return make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, B, (uint64_t)K / 2, (uint64_t)rows, (uint64_t)K / 2, 128, kSub * 8,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// how a stage's flat slot list is dealt to G CTAs.  split_ok (a workspace is available): slot granularity, a row group may be cut
+// between neighbouring CTAs (each CTA publishes at most one head piece); else whole row groups.
+inline void plan_stage(Stage& a, int rows, int K, int G, bool split_ok, int np = 8)
 {
     a.rows = rows;
     a.K = K;
     a.KT = (K + 511) / 512;
-    const int RT = (rows + 7) / 8;
+    const int RT = (rows + kSub * 8 - 1) / (kSub * 8);  // row groups (one slot = a row group x one k tile)
     const long long units = (long long)RT * a.KT;
     long long Q;
+    // Splitting row groups between CTAs balances the bytes per SM, but the owner of a cut row group has to pick the other piece
+    // up.  That is free when the other CTA finishes the piece rounds before the owner needs it (it meets it first), and a memory
+    // round trip on the critical path when both CTAs are through after a single round of their consumer groups (np slots are in
+    // work at once): 4096 x 4096 on 148 SMs is 6.9 slots per CTA split, 8 unsplit -- one round either way -- so it stays whole.
+    if (split_ok) {
+        const long long whole = ((RT + G - 1) / G) * (long long)a.KT;  // longest slot list, whole row groups
+        const long long cut = (units + G - 1) / G;                     // ... cut at slot granularity
+        if (whole <= np || whole - cut < 2) split_ok = false;
+    }
     if (split_ok) {
         a.gran = 1;
         Q = units;
-        long long act = units / a.KT;  // = RT
-        a.active = (int)(act < G ? (act < 1 ? 1 : act) : G);
+        a.active = (int)(units < G ? units : G);
     } else {
         a.gran = a.KT;
         Q = RT;
@@ -686,21 +836,25 @@ inline void plan_stage(Stage& a, int rows, int K, int G, bool split_ok)
 }
 
 // shared-memory plan of a launch: fills x_bytes / part_bytes / slots, returns the dynamic shared-memory size (0: does not fit)
-inline size_t plan_launch(Args& c, size_t max_smem = 226 * 1024, int max_slots = 96)
+inline size_t plan_launch(Args& c, int np, size_t max_smem = 227 * 1024, int max_slots = 24)
 {
+    // ring depth: a multiple of the consumer groups and of the producer lanes (fixed ownership of ring positions, see the kernel)
+    int align = np;
+    while (align % kProdLanes) align += np;
     c.x_bytes = 0;
     c.part_bytes = 0;
     for (int i = 0; i < c.n; i++) {
         const Stage& a = c.st[i];
         if (a.KT * 1024 > c.x_bytes) c.x_bytes = a.KT * 1024;
         const int tiles = (a.per + (a.rem ? 1 : 0)) * a.gran;
-        if (tiles * 32 > c.part_bytes) c.part_bytes = tiles * 32;
+        if (tiles * kSub * 32 > c.part_bytes) c.part_bytes = tiles * kSub * 32;
     }
     c.part_bytes = (c.part_bytes + 127) & ~127;
     const size_t fixed = (size_t)kLutBytes + c.x_bytes + c.part_bytes + 128 /* s_red */ + 64 /* s_misc */ + 8 /* table barrier */;
-    if (fixed + 4 * (kSlotBytes + 16) > max_smem) return 0;
+    if (fixed + (size_t)align * (kSlotBytes + 16) > max_smem) return 0;
     int slots = (int)((max_smem - fixed) / (kSlotBytes + 16));
     if (slots > max_slots) slots = max_slots;
+    slots -= slots % align;
     c.slots = slots;
     return fixed + (size_t)slots * (kSlotBytes + 16);
 }

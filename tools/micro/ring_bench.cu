@@ -83,19 +83,19 @@ static const float kNf4[16] = {-1.0f, -0.6961928009986877f, -0.5250730514526367f
                                -0.18477343022823334f, -0.09105003625154495f, 0.0f, 0.07958029955625534f, 0.16093020141124725f,
                                0.24611230194568634f, 0.33791524171829224f, 0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
 
-template <int NC>
+template <int NC, int WPS>
 static cudaError_t launch_nc(const ring::Args& a, int grid, size_t smem, bool pdl, cudaStream_t s)
 {
-    auto kern = ring::gemv_ring_kernel<bf16, true, NC>;
+    auto kern = ring::gemv_ring_kernel<bf16, true, NC, WPS>;
     static bool set = false;
     if (!set) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3((NC + 1) * 32);
+    cfg.blockDim = dim3(ring::ring_threads(NC));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -106,25 +106,27 @@ static cudaError_t launch_nc(const ring::Args& a, int grid, size_t smem, bool pd
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
+static int g_wps = 2;
 static cudaError_t launch(int nc, const ring::Args& a, int grid, size_t smem, bool pdl, cudaStream_t s)
 {
-    switch (nc) {
-        case 8: return launch_nc<8>(a, grid, smem, pdl, s);
-        case 12: return launch_nc<12>(a, grid, smem, pdl, s);
-        case 16: return launch_nc<16>(a, grid, smem, pdl, s);
-        case 20: return launch_nc<20>(a, grid, smem, pdl, s);
-        case 24: return launch_nc<24>(a, grid, smem, pdl, s);
-        default: printf("unsupported --nc\n"); exit(1);
+    switch (nc * 10 + g_wps) {
+        case 81: return launch_nc<8, 1>(a, grid, smem, pdl, s);
+        case 161: return launch_nc<16, 1>(a, grid, smem, pdl, s);
+        case 162: return launch_nc<16, 2>(a, grid, smem, pdl, s);
+        case 164: return launch_nc<16, 4>(a, grid, smem, pdl, s);
+        case 82: return launch_nc<8, 2>(a, grid, smem, pdl, s);
+        default: printf("unsupported --nc / --wps\n"); exit(1);
     }
 }
 
 int main(int argc, char** argv)
 {
-    int nc = 16, chain = 4, layers = 32, pool = 6, iters = 20, slots_cap = 96;
+    int nc = 16, chain = 4, layers = 32, pool = 6, iters = 20, slots_cap = 24;
     bool split = true, pdl = true, trace = false, check_only = false;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--nc")) nc = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--chain")) chain = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--wps")) g_wps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--layers")) layers = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--pool")) pool = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
@@ -184,8 +186,8 @@ int main(int argc, char** argv)
     fill_bf16<<<16, 256>>>(x14336, 14336, 6);
     fill_bf16<<<16, 256>>>(bias, 28672, 7);
     unsigned* ws;
-    CK(cudaMalloc(&ws, 128 * 1024));
-    CK(cudaMemset(ws, 0, 128 * 1024));
+    CK(cudaMalloc(&ws, ring::kWsBytes));
+    CK(cudaMemset(ws, 0, ring::kWsBytes));
     unsigned long long* d_trace = nullptr;
     const size_t trace_n = (size_t)ring::kMaxStages * G * 8;
     if (trace) {
@@ -197,8 +199,7 @@ int main(int argc, char** argv)
 
     auto fill_stage = [&](ring::Stage& st, const Mat& m, bool with_bias) {
         memset(&st, 0, sizeof(st));
-        if (!make_map_2d(&st.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, m.B, (uint64_t)m.K / 2, (uint64_t)m.rows, (uint64_t)m.K / 2, 128, 8,
-                         CU_TENSOR_MAP_SWIZZLE_128B)) {
+        if (!ring::make_weight_map(&st.map, m.B, m.rows, m.K)) {
             printf("tensor map failed\n");
             exit(1);
         }
@@ -224,7 +225,7 @@ int main(int argc, char** argv)
         a.lut = d_lut;
         a.code = d_code;
         a.ws = ws;
-        smem = ring::plan_launch(a, 226 * 1024, slots_cap);
+        smem = ring::plan_launch(a, nc / g_wps, 227 * 1024, slots_cap);
         if (!smem) { printf("smem plan failed\n"); exit(1); }
     };
 
@@ -326,7 +327,7 @@ int main(int argc, char** argv)
         sum += ms;
         if (ms < best) best = ms;
     }
-    printf("RESULT nc %d chain %d split %d pdl %d slots %d: %.4f ms/step best, %.4f mean; %.1f GB/s (%.3f of 6531.6), %.2f us/stage\n", nc, chain,
+    printf("RESULT nc %d wps %d chain %d split %d pdl %d slots %d: %.4f ms/step best, %.4f mean; %.1f GB/s (%.3f of 6531.6), %.2f us/stage\n", nc, g_wps, chain,
            (int)split, (int)pdl, launches[0].slots, best, sum / 5, algo / best / 1e6, algo / best / 1e6 / 6531.6, best * 1e3 / (layers * 4));
 
     if (trace) {
