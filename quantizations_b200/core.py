@@ -16,6 +16,7 @@ There is no CPU path: a non-CUDA tensor raises NotImplementedError exactly where
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Optional, Tuple
 
@@ -45,6 +46,19 @@ _NF4_VALUES = [
 
 def _stream(t: Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_NO_GUARD = contextlib.nullcontext()
+
+
+def _on_device(dev: torch.device):
+    """Context for a launch whose pointers live on `dev`: the library sizes grids from, and sets kernel attributes on, the CURRENT
+    device, so a launch for another GPU of the same process (HF device_map sharding, multi-GPU tests) must switch to it first.
+    Free when `dev` is already current (the common case): no context manager is entered."""
+    idx = dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
 
 
 # Split-K workspace of the tcgen05 decode GEMV (include/quantizations_b200.h: q4_gemv_fused_t.workspace): zeroed once, one per
@@ -509,17 +523,19 @@ def gemv_4bit(
             None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
             state.lut(A.dtype).data_ptr(), *_ws_args(A.device), None, int(prefetch_k),
         )
-        rc = lib.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
+        with _on_device(A.device):
+            rc = lib.q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
         if rc != 0:
             check(rc, "gemv_4bit")
         return out
-    code = lib.q4_gemv_4bit(
+    with _on_device(A.device):
+      code = lib.q4_gemv_4bit(
         A.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
         None if bias is None else bias.data_ptr(), out.data_ptr(), bout, k, state.blocksize,
         _DTYPE_CODE[A.dtype], flags,
         None if prefetch is None else prefetch.data_ptr(), 0 if prefetch is None else prefetch.numel() * prefetch.element_size(),
         torch.cuda.current_stream(A.device).cuda_stream,
-    )
+      )
     if code != 0:
         check(code, "gemv_4bit")
     return out
@@ -711,7 +727,8 @@ def gemv_4bit_fused(
     if _defer is not None:  # gemv_4bit_chain collects the stage instead of launching it
         _defer.append((f, (A, gate, rms_weight, residual, out, lut, stats)))
         return out
-    rc = _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
+    with _on_device(A.device):
+        rc = _lib.lib().q4_gemv_4bit_fused(ctypes.byref(f), torch.cuda.current_stream(A.device).cuda_stream)
     if rc:
         check(rc, "gemv_4bit_fused")
     return out
@@ -731,7 +748,8 @@ def gemv_4bit_batch(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tens
     if out is None:
         out = torch.empty(A.shape[:-1] + (N,), dtype=A.dtype, device=A.device)
     ws = gemv_workspace(A.device)
-    rc = _lib.lib().q4_gemv_4bit_batch(A2.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
+    with _on_device(A.device):
+      rc = _lib.lib().q4_gemv_4bit_batch(A2.data_ptr(), B.data_ptr(), state.native_stats(), state.code.data_ptr(),
                                        None if bias is None else bias.data_ptr(), out.data_ptr(), M, N, K, state.blocksize,
                                        _DTYPE_CODE[A.dtype], flags, state.lut(A.dtype).data_ptr(), ws.data_ptr(), ws.numel(),
                                        torch.cuda.current_stream(A.device).cuda_stream)
@@ -781,12 +799,13 @@ class gemv_4bit_chain:
         if bar is None:
             bar = _chain_barriers[key] = torch.zeros(64, dtype=torch.int32, device=dev)
         lib = _lib.lib()
-        for i in range(0, len(self.stages), 4):
-            part = self.stages[i:i + 4]
-            arr = (_lib.GemvFused * len(part))(*[f for f, _ in part])
-            rc = lib.q4_gemv_4bit_chain(arr, len(part), bar.data_ptr(), stream.cuda_stream)
-            if rc:
-                check(rc, "gemv_4bit_chain")
+        with _on_device(dev):
+            for i in range(0, len(self.stages), 4):
+                part = self.stages[i:i + 4]
+                arr = (_lib.GemvFused * len(part))(*[f for f, _ in part])
+                rc = lib.q4_gemv_4bit_chain(arr, len(part), bar.data_ptr(), stream.cuda_stream)
+                if rc:
+                    check(rc, "gemv_4bit_chain")
         self.stages = []
 
 
@@ -805,7 +824,8 @@ def decode_attention(qkv: Tensor, cos: Tensor, sin: Tensor, k_cache: Tensor, v_c
         raise ValueError("pos must be a one-element int64 device tensor")
     if out is None:
         out = torch.empty(qkv.shape[:-1] + (nh * hd,), dtype=qkv.dtype, device=qkv.device)
-    rc = _lib.lib().q4_decode_attention(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+    with _on_device(qkv.device):
+      rc = _lib.lib().q4_decode_attention(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
                                         pos.data_ptr(), out.data_ptr(), nh, nkv, hd, k_cache.shape[-2], _DTYPE_CODE[qkv.dtype], flags,
                                         torch.cuda.current_stream(qkv.device).cuda_stream)
     if rc:

@@ -150,7 +150,8 @@ static int launch_mma(const MmaChainArgs& c, bool nested, bool compact, bool kta
     const bool swiglu = c.st[0].swiglu != 0;
     void* kern = nested ? mma_kernel_ptr<T, true>(compact, ktail, chain, swiglu) : mma_kernel_ptr<T, false>(compact, ktail, chain, swiglu);
     if (!kern) return Q4_ERR_SHAPE;  // the SwiGLU epilogue exists for the compact layout and whole tiles only
-    static bool attr_set[2][2][2][2][2] = {};
+    static bool attr_set_dev[kMaxDevices][2][2][2][2][2] = {};
+    auto& attr_set = attr_set_dev[device_slot()];
     if (!attr_set[nested][compact][ktail][chain][swiglu]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -268,7 +269,8 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                     auto kern = mt > 1 ? (nested ? gemv_tc_kernel<T, true, false, 16> : gemv_tc_kernel<T, false, false, 16>)
                                        : (nested ? (multi ? gemv_tc_kernel<T, true, true, 1> : gemv_tc_kernel<T, true, false, 1>)
                                                  : gemv_tc_kernel<T, false, false, 1>);
-                    static bool attr_set[2][2][2] = {};
+                    static bool attr_set_dev[kMaxDevices][2][2][2] = {};
+                    auto& attr_set = attr_set_dev[device_slot()];
                     if (!attr_set[nested][multi][mt > 1]) {
                         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
                         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -1,33 +1,42 @@
-// q4_gemv_ring.cuh -- the batch-1 decode GEMV as a persistent, warp-specialised streaming kernel (fp16 / bf16 activations,
-// blocksize 64, K % 128 == 0).
+// q4_gemv_ring.cuh -- the batch-1 decode GEMV as a persistent, warp-specialised streaming kernel over up to four DEPENDENT
+// GEMVs ("stages": o_proj -> gate/up -> down_proj -> next layer's q/k/v), fp16 / bf16 activations, blocksize 64, K % 128 == 0.
 //
 //   out[r] = sum_b absmax[r,b] * sum_{k in block b} x[k] * code[nib(r,k)]            (+ bias[r])
 //
 // Replaces reference csrc/kernels.cu:1061-1219 (kgemm_4bit_inference_naive), its launcher ops.cu:167-171 and the two launches
 // core.py:467-468 issues before every call.  HBM-bound: every packed byte is read once.
 //
-// One CTA per SM, (NC consumer warps + 1 producer warp):
+// One CTA per SM, (NC consumer warps + a producer warp):
 //
-//   producer   one elected thread streams the CTA's share of the packed weight HBM -> shared memory with 2-D TMA
-//              (cp.async.bulk.tensor, 128-byte swizzle) into a ring of 2-KB slots guarded by full / empty mbarriers.  The weight
-//              does not depend on the activation, so the producer never waits for anything but a free slot: it runs ahead
-//              ACROSS the dependent GEMVs ("stages") of a launch -- while the consumers sit at the grid barrier between o_proj and
-//              gate/up, the ring is already filling with gate/up's first tiles -- and it starts before griddepcontrol.wait under
-//              programmatic dependent launch.  The bytes in flight per SM are the ring (>= 100 KB), not registers.
-//   consumers  take slots round-robin.  A slot is an 8-row x 512-k tile (8 quantisation blocks per row); a lane copies its 64
-//              packed bytes out of the slot (4 conflict-free LDS.128, the swizzle spreads the 8 rows over the banks), releases the
-//              slot at once, then decodes ONE packed byte per shared-memory lookup (256-row table of lane-private
-//              {code[b>>4], code[b&15]} pairs, address spliced by one PRMT) and feeds the pairs to mma.sync.m16n8k16 as
-//              A-fragments: the tensor pipe does the multiply-accumulate and the k-reduction, its 8 B columns are used as 8
-//              quantisation blocks so that D holds the 64 per-(row, block) sums of the tile, each scaled by its decoded absmax
-//              (double-quant decode fused: code2[q] * absmax2 + offset, fp32 multiply then add as kernels.cu:552 + core.py:468).
+//   producer   a few lanes stream the CTA's share of the packed weight HBM -> shared memory with 2-D TMA (cp.async.bulk.tensor,
+//              128-byte swizzle) into a ring of 8-KB slots guarded by full / empty mbarriers.  The weight does not depend on the
+//              activation, so the producer never waits for anything but a free slot: it runs ahead ACROSS the stages of a launch
+//              -- while the consumers wait for the previous stage's output, the ring is already full of this stage's first tiles
+//              -- and it starts before griddepcontrol.wait under programmatic dependent launch.
+//   consumers  take slots round-robin.  A slot is a 32-row x 512-k tile; a warp takes 8-row sub-tiles of it: a lane copies its 64
+//              packed bytes out of the slot (4 conflict-free LDS.128, the swizzle spreads the 8 rows over the banks), decodes ONE
+//              packed byte per shared-memory lookup (256-row table of lane-private {code[b>>4], code[b&15]} pairs, address spliced
+//              by one PRMT) and feeds the pairs to mma.sync.m16n8k16 as A-fragments: the tensor pipe does the multiply-accumulate
+//              and the k-reduction, its 8 B columns are used as 8 quantisation blocks so that D holds the 64 per-(row, block) sums of
+//              the tile, each scaled by its decoded absmax (double-quant decode fused: code2[q] * absmax2 + offset, fp32 multiply
+//              then add as kernels.cu:552 + core.py:468).
 //
-// Work split ("inter-CTA split-K").  A stage's tiles form a flat list, k fastest; CTA b owns a contiguous range of it, so every
-// SM streams the same number of bytes (+-1 tile) whatever the row count -- 4096 rows are 4096 tiles over 148 CTAs = 27 or 28 each,
-// not 3 or 4 row tiles.  A row tile cut by a range boundary is finished by the CTA that holds its first k tile: the other CTA
-// meets that row tile FIRST in its own range, publishes the 8 partial sums (value + epoch tag, one 8-byte store each) as soon as
-// its warps are through with it, and the owner picks them up at the end of its range -- fixed order, no atomics on data, no
-// extra grid-wide step.  Between stages the consumers synchronise on one global counter (all CTAs are co-resident: grid = SMs).
+// Work split ("inter-CTA split-K").  A stage's slots form a flat list, k fastest; CTA b owns a contiguous range of it, so every SM
+// streams the same number of bytes (+-1 slot) whatever the row count.  A row group cut by a range boundary is finished by the CTA
+// that holds its first k tile: the other CTA meets that row group FIRST in its own range, publishes the 32 partial sums (value +
+// epoch tag, one 8-byte store each) as soon as its warps are through with it, and the owner picks them up at the end of its range
+// -- fixed order, no atomics on data, no extra grid-wide step.
+//
+// Stage boundaries ("one-hop exchange").  There is no grid barrier.  The epilogue of a stage whose output feeds the next stage stores
+// every pair of outputs ALSO as one 8-byte {2 x T, epoch tag} word into an exchange buffer (workspace); the next stage's staging
+// polls those words directly -- value and "it is there" arrive in the same load, so a boundary costs one store -> L2 -> load trip
+// instead of (stores, release, atomic, acquire-spin, loads).  Everything a stage needs to know about its share of the work (range,
+// first slot of every warp group, rows it owns) is computed once per launch into a shared-memory plan while the previous kernel is
+// still running, so a warp enters a stage with a handful of instructions.
+//
+// SwiGLU.  A gate/up stage followed by down_proj runs in PAIR mode: a slot holds 16 gate rows and the 16 up rows of the same
+// indices (four 16-row TMA boxes), so the CTA that owns a row group owns gate AND up of those rows, and its epilogue publishes
+// silu(gate) * up -- the down_proj stage stages 14336 activations instead of 2 x 14336 and computes no exp.
 #pragma once
 
 #include <cuda.h>
@@ -42,20 +51,24 @@ namespace q4 {
 namespace ring {
 
 constexpr int kSub = 4;                     // 8-row sub-tiles per ring slot
-constexpr int kSlotBytes = kSub * 2048;     // 32 rows x 256 packed bytes = two 128-byte-wide, 32-row TMA boxes
+constexpr int kSlotBytes = kSub * 2048;     // 32 rows x 256 packed bytes = two 128-byte-wide, 32-row TMA boxes (pair mode: four 16-row boxes)
+constexpr int kSlots = 16;                  // ring depth (a power of two: position / phase of a sequence number are a mask and a shift)
 constexpr int kProdLanes = 4;               // producer lanes issuing slots in lockstep
 constexpr int kMaxStages = 4;
-constexpr int kConsumerBar = 1;    // named barrier of the consumer warps
+constexpr int kConsumerBar = 1;             // named barrier of the consumer warps
+constexpr int kTraceSlots = 16;             // developer trace: globaltimer marks per (stage, CTA)
 // workspace layout (Q4_GEMV_RING_WS_BYTES, zeroed once by the caller, owned by one stream at a time)
-constexpr int kWsEpochOff = 1024;  // u32 [kWsMaxCtas]: stages run so far, per CTA (tags of the split-tile hand-over)
-constexpr int kWsFixOff = 8192;    // {f32, u32} [kWsMaxCtas][32]: partial sums of the row group a CTA shares with its predecessor
+constexpr int kWsEpochOff = 1024;           // u32 [kWsMaxCtas]: stages run so far, per CTA (the tags of both exchanges)
+constexpr int kWsFixOff = 8192;             // {f32, u32} [kWsMaxCtas][32]: partial sums of the row group a CTA shares with its predecessor
 constexpr int kWsMaxCtas = 256;
-constexpr int kWsBytes = kWsFixOff + kWsMaxCtas * kSub * 8 * 8;
+constexpr int kWsXchOff = kWsFixOff + kWsMaxCtas * kSub * 8 * 8;  // {2 x T, u32 tag} [kMaxStages][kXchMaxRows / 2]: stage outputs
+constexpr int kXchMaxRows = 32768;
+constexpr int kWsBytes = kWsXchOff + kMaxStages * kXchMaxRows * 4;
 
 struct Stage {
-    alignas(64) CUtensorMap map;  // packed weight as u8 [rows, K/2], box {128 bytes, 32 rows}, SWIZZLE_128B
+    alignas(64) CUtensorMap map;  // packed weight as u8 [rows, K/2], box {128 bytes, 32 rows (pair mode: 16)}, SWIZZLE_128B
     const void* x;
-    const void* x_gate;      // optional: effective activation = silu(x_gate[k]) * x[k]
+    const void* x_gate;      // optional (plain staging only): effective activation = silu(x_gate[k]) * x[k]
     const void* rms_weight;  // optional: effective activation = x * rsqrt(mean(x^2) + eps) * rms_weight
     AbsmaxView s;
     const float* offsets[kMaxMats];  // nested: per-matrix offset scalars (device pointers)
@@ -64,8 +77,14 @@ struct Stage {
     const void* bias;        // [rows] or nullptr (may alias out: residual stream updated in place)
     float rms_eps;
     int rows, K;
-    int KT;                  // ceil(K / 512): k tiles per row tile
+    int bias_stage;          // >= 0: bias is the output of that EARLIER stage of this launch -- read from its tagged copy (other CTAs wrote it)
+    int KT;                  // ceil(K / 512): k tiles per row group
+    int units;               // row groups x KT: length of the flat slot list
     int multi;               // grouped launch with per-matrix offsets
+    int pair;                // PAIR mode: rows = 2 * half; a row group is gate rows [16 rg, +16) and up rows half + [16 rg, +16)
+    int half;                // pair mode: rows of one member
+    int x_tagged;            // the activation is the previous stage's tagged output (exchange buffer stage - 1), not x
+    int publish;             // 0: out only; 1: out + tagged out; 2 (pair mode): out + tagged silu(gate) * up
     int gran;                // slots per assignment quantum: 1 (a row group may be split between two CTAs) or KT (never split)
     int active, per, rem;    // CTA b < active owns quanta [b*per + min(b, rem), +per + (b < rem)); the others idle in this stage
     // fused one-shot all-reduce over tensor-parallel ranks (q4_allreduce_t), ar_world <= 1: off
@@ -79,10 +98,19 @@ struct Args {
     const void* lut;      // prebuilt 64-KB table image, or nullptr: built in the kernel from code / code2
     const float* code;
     unsigned* ws;         // workspace (see above); required when n > 1 or any stage has gran == 1
-    int slots;            // ring depth
     int x_bytes;          // shared-memory bytes reserved for the activation vector: max over the stages of KT * 1024
-    int part_bytes;       // ... for the per-tile partial sums: max over the stages of (tiles per CTA) * 32
-    unsigned long long* trace;  // developer: [stage][cta][8] globaltimer marks
+    int part_bytes;       // ... for the per-slot partial sums: max over the stages of (slots per CTA) * 128
+    unsigned long long* trace;  // developer: [stage][cta][kTraceSlots] globaltimer marks
+};
+
+// what a CTA needs to know about its share of a stage; computed once per launch (consumer warp `stage`), read by everybody
+struct Plan {
+    int S0, nloc;            // the CTA's range of the flat slot list: [S0, S0 + nloc)
+    int head;                // its first `head` slots belong to a row group that began in the previous CTA
+    int base_seq;            // ring sequence number of its first slot (slots taken in earlier stages)
+    int rg_own0, nrows_own;  // row groups it owns (= holds the first k tile of): [rg_own0, rg_own0 + nrows_own / 32)
+    int pad0, pad1;
+    unsigned short i0[16], rg[16], kt[16];  // per consumer warp group: local index, row group and k tile of its first slot
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,6 +166,7 @@ __device__ __forceinline__ unsigned long long gtime()
     return t;
 }
 
+
 __device__ __forceinline__ int range_start(const Stage& a, int b) { return (b * a.per + (b < a.rem ? b : a.rem)) * a.gran; }
 
 // the CTA's range of a stage's flat slot list
@@ -151,8 +180,58 @@ __device__ __forceinline__ void cta_range(const Stage& a, int b, int& u0, int& u
     const int q1 = q0 + a.per + (b < a.rem ? 1 : 0);
     u0 = q0 * a.gran;
     u1 = q1 * a.gran;
-    const int total = ((a.rows + kSub * 8 - 1) / (kSub * 8)) * a.KT;
-    if (u1 > total) u1 = total;  // gran == KT never overshoots; kept for safety
+    if (u1 > a.units) u1 = a.units;  // gran == KT never overshoots; kept for safety
+}
+
+// first weight row of sub-tile `sub` of row group `rg`
+__device__ __forceinline__ int sub_row(const Stage& a, int rg, int sub)
+{
+    return a.pair ? ((sub >> 1) * a.half + rg * 16 + (sub & 1) * 8) : (rg * (kSub * 8) + sub * 8);
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ld_relaxed_2xu64(const unsigned long long* p, unsigned long long& a, unsigned long long& b)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// second half of the RMSNorm glue: `ss` is the thread's sum of squares over the chunks it staged itself (c = tid, tid + nthr, ...);
+// x_eff = x * rsqrt(mean(x^2) + eps) * weight in fp32, rounded to T once
+template <typename T>
+__device__ __noinline__ void rms_rescale(const void* rms_weight, float rms_eps, int K, uint4* s_x, float* s_red, int nchunk, float ss,
+                                         int tid, int nthr)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    auto slot = [](int c) { return (c & ~7) | ((c ^ (c >> 3)) & 7); };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) s_red[warp] = ss;
+    bar_sync(kConsumerBar, nthr);
+    ss = 0.0f;
+    for (int i = 0; i < (nthr >> 5); i++) ss += s_red[i];
+    const float rs = rsqrtf(ss / (float)K + rms_eps);
+#pragma unroll 1
+    for (int c = tid; c < nchunk; c += nthr) {  // each thread rescales the chunks it wrote itself
+        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(rms_weight) + c);
+        const uint4 v = s_x[slot(c)];
+        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+        uint32_t xw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q2 = 0; q2 < 4; q2++) {
+            const float2 f = unpack2<T>(xw[q2]), gm = unpack2<T>(ww[q2]);
+            xw[q2] = pack2<T>(f.x * rs * gm.x, f.y * rs * gm.y);
+        }
+        s_x[slot(c)] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+    }
 }
 
 // Activation staging by the consumer threads, decode glue fused in (see q4_gemv_fused_t):
@@ -193,27 +272,7 @@ __device__ __noinline__ void stage_x_glue(const void* x, const void* x_gate, con
         }
         s_x[slot(c)] = v;
     }
-    if (!rms_weight) return;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) s_red[warp] = ss;
-    bar_sync(kConsumerBar, nthr);
-    ss = 0.0f;
-    for (int i = 0; i < (nthr >> 5); i++) ss += s_red[i];
-    const float rs = rsqrtf(ss / (float)K + rms_eps);
-#pragma unroll 1
-    for (int c = tid; c < nchunk; c += nthr) {  // each thread rescales the chunks it wrote itself
-        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(rms_weight) + c);
-        const uint4 v = s_x[slot(c)];
-        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
-        uint32_t xw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q2 = 0; q2 < 4; q2++) {
-            const float2 f = unpack2<T>(xw[q2]), gm = unpack2<T>(ww[q2]);
-            xw[q2] = pack2<T>(f.x * rs * gm.x, f.y * rs * gm.y);
-        }
-        s_x[slot(c)] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
-    }
+    if (rms_weight) rms_rescale<T>(rms_weight, rms_eps, K, s_x, s_red, nchunk, ss, tid, nthr);
 }
 
 // NC consumer warps; WPS of them share a ring slot (each takes kSub / WPS of its sub-tiles)
@@ -226,26 +285,28 @@ __global__ void __launch_bounds__(ring_threads(NC), 1)
 gemv_ring_kernel(const __grid_constant__ Args c)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // Shared-memory plan: [table 64 KB][ring: slots x 8 KB][x][partials][barriers][scratch].  The PRMT splice of the lookups needs
-    // the table at (64-KB aligned window address) + (compile-time immediate): it is the first thing in dynamic shared memory,
+    // Shared-memory plan: [table 64 KB][ring: kSlots x 8 KB][x][partials][barriers][scratch][plans].  The PRMT splice of the lookups
+    // needs the table at (64-KB aligned window address) + (compile-time immediate): it is the first thing in dynamic shared memory,
     // which starts kDynBase into the CTA's window (probed on the host, trapped here if violated).  kDynBase + 64 KB is a multiple
     // of 1024, which the 128-byte TMA swizzle of the ring slots needs.
     constexpr int kImm = kDynBase;
     constexpr int kCons = NC * 32;
     constexpr int kWarpsPerSlot = WPS;
     constexpr int NP = NC / kWarpsPerSlot;  // slots in work at once: ring sequence number q goes to warp group q % NP
+    constexpr int D = kSlots;
     static_assert(NC % kWarpsPerSlot == 0 && kSub % kWarpsPerSlot == 0, "warps per slot");
+    static_assert(NP <= 16 && D % NP == 0 && D % kProdLanes == 0 && (D & (D - 1)) == 0, "ring depth / consumer groups");
     constexpr int kSubPerWarp = kSub / kWarpsPerSlot;
     const uint32_t smem_saddr = smem_u32(smem);
     if (smem_saddr != kDynBase) __trap();
     uint8_t* lut = smem;
     uint8_t* ringp = smem + kLutBytes;
-    const int D = c.slots;
     uint4* s_x = reinterpret_cast<uint4*>(ringp + (size_t)D * kSlotBytes);
     float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_x) + c.x_bytes);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_part) + c.part_bytes);  // [0] table, [1 + i] full, [1 + D + i] empty
-    float* s_red = reinterpret_cast<float*>(s_bar + 1 + 2 * D);                                          // 32 floats
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_red + 32);  // [0] head-piece counter, [1] epoch base, [2] all-reduce epoch
+    float* s_red = reinterpret_cast<float*>(s_bar + 1 + 2 * D);                                          // 16 floats (one per consumer warp)
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_red + 16);  // [0] head-piece counter, [1] epoch base, [2] all-reduce epoch
+    Plan* s_plan = reinterpret_cast<Plan*>(s_misc + 8);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -255,7 +316,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
     auto full = [&](int i) { return bar0 + 8u * (uint32_t)(1 + i); };
     auto empty = [&](int i) { return bar0 + 8u * (uint32_t)(1 + D + i); };
     auto mark = [&](int stage, int slot) {
-        if (c.trace) c.trace[((size_t)stage * G + bx) * 8 + slot] = gtime();
+        if (c.trace) c.trace[((size_t)stage * G + bx) * kTraceSlots + slot] = gtime();
     };
 
     pdl_launch_dependents();
@@ -268,6 +329,37 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_misc[0] = 0;
         mark(0, 0);
+    }
+    if (warp < c.n) {
+        // ---- the plan of stage `warp` (all the integer divisions of the launch happen here, once, off the critical path)
+        const Stage& a = c.st[warp];
+        int base = 0;
+        for (int s = 0; s < warp; s++) {
+            int u0, u1;
+            cta_range(c.st[s], bx, u0, u1);
+            base += u1 - u0;
+        }
+        int S0, S1;
+        cta_range(a, bx, S0, S1);
+        const int nloc = S1 - S0, KT = a.KT;
+        Plan& p = s_plan[warp];
+        if (lane == 0) {
+            p.S0 = S0;
+            p.nloc = nloc;
+            p.base_seq = base;
+            p.head = (nloc > 0 && (S0 % KT) != 0) ? (KT - S0 % KT < nloc ? KT - S0 % KT : nloc) : 0;
+            const int rg_own0 = (S0 + KT - 1) / KT, rg_own1 = (S1 + KT - 1) / KT;
+            p.rg_own0 = rg_own0;
+            p.nrows_own = nloc > 0 ? (rg_own1 - rg_own0) * (kSub * 8) : 0;
+        }
+        if (lane < NP) {
+            int i0 = lane - (base % NP);
+            if (i0 < 0) i0 += NP;
+            const int S = S0 + i0;
+            p.i0[lane] = (unsigned short)i0;
+            p.rg[lane] = (unsigned short)(S / KT);
+            p.kt[lane] = (unsigned short)(S - (S / KT) * KT);
+        }
     }
     __syncthreads();
 
@@ -287,38 +379,41 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         }
         if (lane < kProdLanes) {
             // kProdLanes lanes in lockstep, lane l taking slots l, l + kProdLanes, ... of the CTA's sequence: the latency of the
-            // empty-barrier probe and the issue cost of the copies are paid once per kProdLanes slots
-            int base = 0;
+            // empty-barrier probe and the issue cost of the copies are paid once per kProdLanes slots.  D is a multiple of kProdLanes,
+            // so a ring position is always filled by the same lane, fill after fill: its parity wait can never alias an older phase.
             for (int s = 0; s < c.n; s++) {
                 const Stage& a = c.st[s];
-                int S0, S1;
-                cta_range(a, bx, S0, S1);
-                const int n = S1 - S0, KT = a.KT, half = a.K >> 1;
+                const int S0 = s_plan[s].S0, n = s_plan[s].nloc, base = s_plan[s].base_seq;
+                const int KT = a.KT, half = a.K >> 1;
                 if (lane == 0) {
                     asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map) : "memory");
                     mark(s, 6);
                 }
-                // lane l fills the ring sequence numbers q = l (mod kProdLanes); D is a multiple of kProdLanes, so a ring position is
-                // always filled by the same lane, fill after fill: its parity wait can never alias an older phase
                 int i = lane - base % kProdLanes;
                 if (i < 0) i += kProdLanes;
                 int rg = (S0 + i) / KT, kt = (S0 + i) - rg * KT;
-                int pos;
-                uint32_t ph;
-                {
-                    const int q = base + i, w = q / D;
-                    pos = q - w * D;
-                    ph = (uint32_t)w & 1u;
-                }
                 const int d_rg = kProdLanes / KT, d_kt = kProdLanes - d_rg * KT;
-                const int d_wrap = kProdLanes / D, d_pos = kProdLanes - d_wrap * D;
+                const bool pair = a.pair != 0;
+                const int hrows = a.half;
                 while (i < n) {
+                    const int q = base + i;
+                    const int pos = q & (D - 1);
+                    const uint32_t ph = (uint32_t)(q / D) & 1u;
                     mbar_wait(empty(pos), ph ^ 1u);
                     const uint32_t dst = ring_saddr + (uint32_t)pos * kSlotBytes;
                     const bool two = kt * 256 + 128 < half;  // a ragged last k tile may hold one box only
                     mbar_expect_tx(full(pos), two ? kSlotBytes : kSlotBytes / 2);
-                    tma_load_2d(dst, &a.map, kt * 256, rg * 32, full(pos));
-                    if (two) tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 32, full(pos));
+                    if (!pair) {
+                        tma_load_2d(dst, &a.map, kt * 256, rg * 32, full(pos));
+                        if (two) tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 32, full(pos));
+                    } else {  // 16 gate rows then the 16 up rows of the same indices, per 128-byte half
+                        tma_load_2d(dst, &a.map, kt * 256, rg * 16, full(pos));
+                        tma_load_2d(dst + kSlotBytes / 4, &a.map, kt * 256, hrows + rg * 16, full(pos));
+                        if (two) {
+                            tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 16, full(pos));
+                            tma_load_2d(dst + 3 * kSlotBytes / 4, &a.map, kt * 256 + 128, hrows + rg * 16, full(pos));
+                        }
+                    }
                     i += kProdLanes;
                     rg += d_rg;
                     kt += d_kt;
@@ -326,14 +421,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                         kt -= KT;
                         rg++;
                     }
-                    pos += d_pos;
-                    ph ^= (uint32_t)d_wrap & 1u;
-                    if (pos >= D) {
-                        pos -= D;
-                        ph ^= 1u;
-                    }
                 }
-                base += n;
                 if (lane == 0) mark(s, 7);
             }
         }
@@ -351,15 +439,14 @@ gemv_ring_kernel(const __grid_constant__ Args c)
     const bool xrole = t4 == (g & 3);  // this lane feeds column g of the B operand: x of the tile's block g
     const uint32_t x_saddr = smem_u32(s_x), xswz = (uint32_t)(g * 16);
     uint32_t epoch_base = 0;  // stages this CTA ran in earlier launches (workspace counter): read after griddepcontrol.wait
-    int base_seq = 0;         // slots this CTA has taken from the ring in earlier stages
+    uint2* const xch0 = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c.ws) + kWsXchOff);
 
     for (int stage = 0; stage < c.n; stage++) {
         const Stage& a = c.st[stage];
+        const Plan& pl = s_plan[stage];
         const int K = a.K, R = a.rows, KT = a.KT;
         const int bpr = K >> 6;
-        int S0, S1;
-        cta_range(a, bx, S0, S1);
-        const int nloc = S1 - S0;
+        const int S0 = pl.S0, nloc = pl.nloc, head = pl.head;
         const bool MULTI = a.multi != 0;
         float off[kMaxMats];
 #pragma unroll
@@ -369,14 +456,9 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         // parity wait can never alias an older phase.  Within a stage the group's k tile is constant whenever NP % KT == 0.
         struct Cursor { int i, rg, kt; };
         Cursor cur;
-        {
-            int i0 = grp - (base_seq % NP);
-            if (i0 < 0) i0 += NP;
-            const int S = S0 + i0;
-            cur.i = i0;
-            cur.rg = S / KT;
-            cur.kt = S - cur.rg * KT;
-        }
+        cur.i = pl.i0[grp];
+        cur.rg = pl.rg[grp];
+        cur.kt = pl.kt[grp];
         const int d_rg = NP / KT, d_kt = NP - d_rg * KT;
         auto advance = [&](Cursor& q) {
             q.i += NP;
@@ -390,20 +472,26 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         int pos;
         uint32_t ph;
         {
-            const int seq = base_seq + cur.i;
-            const int w = seq / D;
-            pos = seq - w * D;
-            ph = (uint32_t)w & 1u;
+            const int seq = pl.base_seq + cur.i;
+            pos = seq & (D - 1);
+            ph = (uint32_t)(seq / D) & 1u;
         }
-        const int d_wrap = NP / D, d_pos = NP - d_wrap * D;
 
         // absmax of the lane's two blocks (2*t4, 2*t4+1 of row g of a sub-tile), fetched one slot ahead
         struct Stat { uint32_t q; float s0; };  // nested: two 8-bit codes + their second-level absmax; else the two fp32 absmax values
-        auto load_stat = [&](const Cursor& q, int sub) {
+        const int row_mul = a.pair ? kSub * 4 : kSub * 8;
+        int sub_off[kSubPerWarp];  // first row of the warp's sub-tiles relative to rg * row_mul
+#pragma unroll
+        for (int q2 = 0; q2 < kSubPerWarp; q2++) {
+            const int sub = wh * kSubPerWarp + q2;
+            sub_off[q2] = (a.pair ? ((sub >> 1) * a.half + (sub & 1) * 8) : sub * 8) + g;
+        }
+        const int re0 = a.row_end[0], re1 = a.row_end[1], re2 = a.row_end[2];
+        auto load_stat = [&](const Cursor& q, int q2) {
             Stat r;
             r.q = 0;
             r.s0 = 0.0f;
-            const int row = (q.rg * kSub + sub) * 8 + g;
+            const int row = q.rg * row_mul + sub_off[q2];
             const int blk = q.kt * 8 + 2 * t4;
             if (blk < bpr) {  // bpr is even: the pair is valid together
                 const int sb = (row < R ? row : R - 1) * bpr + blk;  // rows past the end read a valid row and are never stored
@@ -423,57 +511,85 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         for (int q2 = 0; q2 < kSubPerWarp; q2++) {
             st_cur[q2].q = 0;
             st_cur[q2].s0 = 0.0f;
-            if (cur.i < nloc) st_cur[q2] = load_stat(cur, wh * kSubPerWarp + q2);  // statistics do not depend on the previous stage: before the barrier
+            if (cur.i < nloc) st_cur[q2] = load_stat(cur, q2);  // statistics do not depend on the previous stage: before the exchange
         }
 
         // ---- everything below may read the previous kernel's (stage 0) or the previous stage's output
-        // A plain activation whose k tile is the same for all of a warp group's slots (NP % KT == 0: K = 4096 with 16 consumer warps)
-        // is not staged at all: the lanes that feed the B operand read their 64 activations straight from global memory (L2) into
-        // registers -- no shared-memory pass, no CTA-wide barrier after the grid barrier.
-        const bool private_x = false;  // measured: 16 warps x 148 CTAs hammering the same 8 KB of L2 costs ~3 us per stage; staged once per CTA instead
-        if (tid == 0) mark(stage, 1);
+        if (tid == 0) {
+            mark(stage, 1);
+            s_misc[0] = 0;  // head-piece counter of this stage (its last use was before the previous stage's closing barrier)
+        }
         if (stage == 0) {
             pdl_wait();
             if (tid == 0) s_misc[1] = c.ws ? __ldcg(c.ws + kWsEpochOff / 4 + bx) : 0u;  // written by this CTA index of the previous launch
-        } else {
-            // grid-wide barrier of the consumers: every CTA's stores of the previous stage are visible afterwards
-            bar_sync(kConsumerBar, kCons);
-            if (tid == 0) {
-                // release at gpu scope: cumulative over what the bar.sync above ordered before this thread, i.e. every store of the CTA
-                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.ws), "r"(1u) : "memory");
-                const unsigned target = (unsigned)stage * (unsigned)G;
-                unsigned v;
-                for (long long spin = 0;; spin++) {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.ws) : "memory");
-                    if (v >= target) break;
-                    if (spin > (1ll << 27)) __trap();  // a CTA never arrived: fail loudly instead of hanging the GPU
-                }
-                s_misc[0] = 0;  // head-piece counter of this stage
-            }
-            bar_sync(kConsumerBar, kCons);
         }
-        if (tid == 0) mark(stage, 2);
-
-        if (!private_x) {
-            const int nchunk = K >> 3;  // 16-byte chunks of x
-            const int npad = KT * 64;   // staged chunks (zero tail up to whole tiles)
-            if (a.x_gate || a.rms_weight) {
-                stage_x_glue<T>(a.x, a.x_gate, a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, npad, tid, kCons);
-            } else {
-                constexpr int kU = NC >= 16 ? 4 : 8;  // loads in flight per thread: the whole vector in one round trip
-                for (int cb = tid; cb < npad; cb += kU * kCons) {
-                    uint4 v[kU];
+        const int nchunk = K >> 3;  // 16-byte chunks of x
+        const int npad = KT * 64;   // staged chunks (zero tail up to whole tiles)
+        if (a.x_tagged) {
+            // One-hop exchange: the previous stage's epilogue stored every pair of its outputs as one 64-bit word {2 x T, tag}; value
+            // and arrival are one load.  All of a thread's loads are issued before the first is examined: one round trip when the data
+            // is there.  A thread owns whole 16-byte chunks (8 activations), exactly as in the plain staging, so the sum of squares of
+            // the RMSNorm is accumulated in the same order.
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xch0) + (size_t)(stage - 1) * (kXchMaxRows / 2);
+            const uint32_t tag = epoch_base + (uint32_t)stage;  // the previous stage's epoch
+            constexpr int kU = 4;
+            float ss = 0.0f;
+            for (int cb = tid; cb < npad; cb += kU * kCons) {
+                unsigned long long w[kU][4];
 #pragma unroll
-                    for (int j = 0; j < kU; j++) {
-                        const int cc = cb + j * kCons;
-                        v[j] = make_uint4(0, 0, 0, 0);
-                        if (cc < nchunk) v[j] = __ldcg(reinterpret_cast<const uint4*>(a.x) + cc);  // coherent: may be a previous stage's output
-                    }
+                for (int j = 0; j < kU; j++) {
+                    const int cc = cb + j * kCons;
 #pragma unroll
-                    for (int j = 0; j < kU; j++) {
-                        const int cc = cb + j * kCons;
-                        if (cc < npad) s_x[(cc & ~7) | ((cc ^ (cc >> 3)) & 7)] = v[j];
+                    for (int q2 = 0; q2 < 4; q2++) w[j][q2] = (unsigned long long)tag << 32;
+                    if (cc < nchunk) {
+                        ld_relaxed_2xu64(src + (size_t)cc * 4, w[j][0], w[j][1]);
+                        ld_relaxed_2xu64(src + (size_t)cc * 4 + 2, w[j][2], w[j][3]);
                     }
+                }
+#pragma unroll
+                for (int j = 0; j < kU; j++) {
+                    const int cc = cb + j * kCons;
+                    if (cc < npad) {
+                        // a chunk is one 32-byte sector written by one store instruction of one CTA: its four words arrive together.
+                        // Not there yet: back off before asking again -- 75 000 threads polling flat out keep the L2 slices busier
+                        // than the stores they are waiting for.
+                        unsigned ns = 32;
+                        for (long long spin = 0; (uint32_t)(w[j][0] >> 32) != tag || (uint32_t)(w[j][1] >> 32) != tag ||
+                                                 (uint32_t)(w[j][2] >> 32) != tag || (uint32_t)(w[j][3] >> 32) != tag; spin++) {
+                            __nanosleep(ns);
+                            if (ns < 256) ns *= 2;
+                            ld_relaxed_2xu64(src + (size_t)cc * 4, w[j][0], w[j][1]);
+                            ld_relaxed_2xu64(src + (size_t)cc * 4 + 2, w[j][2], w[j][3]);
+                            if (spin > (1ll << 24)) __trap();  // a CTA never published: fail loudly instead of hanging the GPU
+                        }
+                        uint32_t v[4];
+#pragma unroll
+                        for (int q2 = 0; q2 < 4; q2++) {
+                            v[q2] = (uint32_t)w[j][q2];
+                            const float2 f = unpack2<T>(v[q2]);
+                            ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+                        }
+                        s_x[(cc & ~7) | ((cc ^ (cc >> 3)) & 7)] = make_uint4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+            }
+            if (a.rms_weight) rms_rescale<T>(a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, ss, tid, kCons);
+        } else if (a.x_gate || a.rms_weight) {
+            stage_x_glue<T>(a.x, a.x_gate, a.rms_weight, a.rms_eps, K, s_x, s_red, nchunk, npad, tid, kCons);
+        } else {
+            constexpr int kU = NC >= 16 ? 4 : 8;  // loads in flight per thread: the whole vector in one round trip
+            for (int cb = tid; cb < npad; cb += kU * kCons) {
+                uint4 v[kU];
+#pragma unroll
+                for (int j = 0; j < kU; j++) {
+                    const int cc = cb + j * kCons;
+                    v[j] = make_uint4(0, 0, 0, 0);
+                    if (cc < nchunk) v[j] = __ldcg(reinterpret_cast<const uint4*>(a.x) + cc);  // coherent: the previous kernel's output
+                }
+#pragma unroll
+                for (int j = 0; j < kU; j++) {
+                    const int cc = cb + j * kCons;
+                    if (cc < npad) s_x[(cc & ~7) | ((cc ^ (cc >> 3)) & 7)] = v[j];
                 }
             }
         }
@@ -487,14 +603,12 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 *reinterpret_cast<uint4*>(lut + cc * 16) = make_uint4(word, word, word, word);
             }
         }
-        if (stage == 0 || !private_x) bar_sync(kConsumerBar, kCons);
+        if (tid == 0) mark(stage, 2);
+        bar_sync(kConsumerBar, kCons);
         if (stage == 0 && c.lut) mbar_wait(bar0, 0);  // table landed?
         if (stage == 0) epoch_base = s_misc[1];
-        const uint32_t epoch = epoch_base + (uint32_t)stage + 1u;  // tag of this stage's split-row-group hand-over
+        const uint32_t epoch = epoch_base + (uint32_t)stage + 1u;  // tag of this stage's exchanges
         if (tid == 0) mark(stage, 3);
-
-        // split row groups of this CTA's range: the first `head` slots belong to a row group that began in the previous CTA
-        const int head = (nloc > 0 && (S0 % KT) != 0) ? (KT - S0 % KT < nloc ? KT - S0 % KT : nloc) : 0;
 
         // ---- main loop: the warp's sub-tiles as ONE continuous stream.  The table lookups run kAhead MMAs ahead of the tensor pipe
         // and keep running across sub-tile and slot boundaries: the next sub-tile's packed bytes replace the current one's in the
@@ -507,6 +621,8 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         constexpr int kAhead = 3;
         uint32_t wa[8], wb[8];        // packed bytes of (row g, block t4) and (row g, block 4 + t4) of the sub-tile in work
         uint32_t f[kAhead + 1][4];    // looked-up A fragments in flight
+#pragma unroll
+        for (int i = 0; i < 8; i++) wa[i] = wb[i] = 0;
         auto fetch = [&](uint32_t (&d)[4], int j) {
             const uint32_t va = wa[j >> 1], vb = wb[j >> 1];
 #ifdef Q4_RING_EXPERIMENT_SKIPLOOKUP  // developer experiment (wrong results): every 4th MMA step decodes without shared-memory lookups
@@ -551,19 +667,15 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         while (cur.i < nloc) {
             Cursor nxt = cur;
             advance(nxt);
-            int pos_n = pos + d_pos;
-            uint32_t ph_n = ph ^ ((uint32_t)d_wrap & 1u);
-            if (pos_n >= D) {
-                pos_n -= D;
-                ph_n ^= 1u;
-            }
+            const int pos_n = (pos + NP) & (D - 1);
+            const uint32_t ph_n = ph ^ (uint32_t)(pos + NP >= D);
             const bool has_next = nxt.i < nloc;
             Stat st_nxt[kSubPerWarp];
 #pragma unroll
             for (int q2 = 0; q2 < kSubPerWarp; q2++) {
                 st_nxt[q2].q = 0;
                 st_nxt[q2].s0 = 0.0f;
-                if (has_next) st_nxt[q2] = load_stat(nxt, wh * kSubPerWarp + q2);
+                if (has_next) st_nxt[q2] = load_stat(nxt, q2);
             }
 
             if (cur.kt != kt_loaded) {  // warp-uniform; the lookups in flight do not depend on it
@@ -637,13 +749,14 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 const float u1s = t4 < 2 ? ce[1] + co[1] : ce[3] + co[3];
                 float am0, am1;
                 if (NESTED) {
-                    float o = off[0];
-                    if (MULTI) {
-                        const int row = (cur.rg * kSub + sub) * 8 + g;
-                        o = row < a.row_end[0] ? off[0] : (row < a.row_end[1] ? off[1] : (row < a.row_end[2] ? off[2] : off[3]));
-                    }
                     const float q0 = __uint_as_float(lut_lookup<0, kImm + 128>(st_cur[q2].q, lane_base));
                     const float q1 = __uint_as_float(lut_lookup<1, kImm + 128>(st_cur[q2].q, lane_base));
+                    // (measured: carrying the offset in the prefetched statistics instead of selecting it here costs 16 %)
+                    float o = off[0];
+                    if (MULTI) {
+                        const int row = cur.rg * row_mul + sub_off[q2];
+                        o = row < re0 ? off[0] : (row < re1 ? off[1] : (row < re2 ? off[2] : off[3]));
+                    }
                     am0 = __fadd_rn(__fmul_rn(q0, st_cur[q2].s0), o);  // reference: kernels.cu:552 then core.py:468
                     am1 = __fadd_rn(__fmul_rn(q1, st_cur[q2].s0), o);
                     if (cur.kt * 8 + 2 * t4 >= bpr) am0 = am1 = 0.0f;  // ragged k tile: blocks past the row's end
@@ -682,12 +795,37 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             pos = pos_n;
             ph = ph_n;
         }
-        base_seq += nloc;
         if (tid == 0) mark(stage, 4);
+        // ---- what the epilogue needs from L2 is requested BEFORE the closing barrier (the wait for the CTA's slowest warp hides the
+        //      round trip): the neighbour's piece of a cut row group, published long ago, and the residual / bias of the thread's row
+        const int nrows_own = pl.nrows_own;
+        constexpr int kRows = kSub * 8;  // rows per row group
+        uint32_t pre_val = 0, pre_e = 0;
+        unsigned long long pre_bias = 0;  // bias_stage >= 0: the tagged word; else the value's bits
+        if (tid < nrows_own) {
+            const int rg = pl.rg_own0 + tid / kRows, v = tid % kRows;
+            if (rg * KT - S0 + KT > nloc) {
+                const uint2* fix = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(c.ws) + kWsFixOff) + v;
+                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(pre_val), "=r"(pre_e) : "l"(fix + (size_t)(bx + 1) * kRows) : "memory");
+            }
+            if (a.bias) {
+                const int r = sub_row(a, rg, v >> 3) + (v & 7);
+                if (a.bias_stage >= 0) pre_bias = ld_relaxed_u64(reinterpret_cast<const unsigned long long*>(xch0) + (size_t)a.bias_stage * (kXchMaxRows / 2) + (r >> 1));
+                else if (r < R) pre_bias = __ldcg(reinterpret_cast<const unsigned short*>(a.bias) + r);
+            }
+        }
         bar_sync(kConsumerBar, kCons);
+        if (tid == 0) {
+            mark(stage, 8);
+            if (c.trace) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                c.trace[((size_t)stage * G + bx) * kTraceSlots + 9] = smid;
+            }
+        }
 
         // ---- fixed-order sum over the k tiles of every row group this CTA owns (= holds the first k tile of), [the partner's
-        //      partials of a split row group,] [all-reduce over tensor-parallel ranks,] bias / residual, store
+        //      partials of a split row group,] [all-reduce over tensor-parallel ranks,] bias / residual, store, publish
         uint32_t ar_epoch = 0;
         if (a.ar_world > 1) {
             // exchanges are counted per CTA in the rank's own exchange area, by EVERY CTA whether or not it owns rows in this stage: all
@@ -701,23 +839,27 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             bar_sync(kConsumerBar, kCons);
             ar_epoch = s_misc[2];
         }
-        if (nloc > 0) {
-            constexpr int kRows = kSub * 8;           // rows per row group
-            const int rg_own0 = (S0 + KT - 1) / KT;   // first row group whose k tile 0 lies in [S0, S1)
-            const int rg_own1 = (S1 + KT - 1) / KT;   // one past the last
-            const int nrows_own = (rg_own1 - rg_own0) * kRows;
-            const int row_lo = rg_own0 * kRows;
-            auto row_total = [&](int i) {  // i = row index relative to row_lo
+        if (nrows_own > 0) {
+            const int rg_own0 = pl.rg_own0;
+            auto row_of = [&](int i) { return sub_row(a, rg_own0 + i / kRows, (i % kRows) >> 3) + (i & 7); };
+            auto row_total = [&](int i) {  // i = row index relative to the first owned row group
                 const int rg = rg_own0 + i / kRows, v = i % kRows;
                 const int j0 = rg * KT - S0;
                 const int j1 = j0 + KT < nloc ? j0 + KT : nloc;
                 const bool cut = j0 + KT > nloc;  // split row group: its remaining k tiles are the head pieces of the following CTAs
                 const uint2* fix = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(c.ws) + kWsFixOff) + v;
-                uint32_t val = 0, e = 0;
-                if (cut)  // first probe of the next CTA's piece: in flight while the own partials are summed
+                uint32_t val = pre_val, e = pre_e;  // the thread's first row: requested before the closing barrier
+                if (cut && i != tid)
                     asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(e) : "l"(fix + (size_t)(bx + 1) * kRows) : "memory");
                 float total = 0.0f;
-                for (int j = j0; j < j1; j++) total += s_part[j * kRows + v];
+                for (int j = j0; j < j1; j += 4) {  // the partials of four k tiles are fetched together, added in k order
+                    float p4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) p4[u] = j + u < j1 ? s_part[(j + u) * kRows + v] : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (j + u < j1) total += p4[u];
+                }
                 if (cut) {
                     const int gend = (rg + 1) * KT;
                     for (int b2 = bx + 1; b2 < a.active && range_start(a, b2) < gend; b2++) {  // pieces added in CTA order
@@ -732,13 +874,47 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 }
                 return total;
             };
-            auto finish = [&](int i, float total) {
-                const int r = row_lo + i;
-                if (r >= R) return;
+            // y = T(total) (+ bias), stored; published for the next stage when it consumes this output (whole warps: shuffles inside)
+            auto emit = [&](int i, float total) {
+                const int r = row_of(i);
+                const bool valid = r < R;
                 T y = Elem<T>::from_f32(total);
-                const T* bias = reinterpret_cast<const T*>(a.bias);
-                if (bias) y = Elem<T>::from_f32(Elem<T>::to_f32(y) + Elem<T>::to_f32(__ldcg(bias + r)));  // torch `out += bias`
-                reinterpret_cast<T*>(a.out)[r] = y;
+                if (a.bias && valid) {  // torch `out += bias`
+                    float bv;
+                    if (a.bias_stage >= 0) {
+                        // written by other CTAs in an earlier stage of this launch: its tagged copy says when it is there
+                        const unsigned long long* bsrc = reinterpret_cast<const unsigned long long*>(xch0) + (size_t)a.bias_stage * (kXchMaxRows / 2) + (r >> 1);
+                        unsigned long long w = i == tid ? pre_bias : ld_relaxed_u64(bsrc);
+                        const uint32_t btag = epoch_base + (uint32_t)a.bias_stage + 1u;
+                        for (long long spin = 0; (uint32_t)(w >> 32) != btag; spin++) {
+                            w = ld_relaxed_u64(bsrc);
+                            if (spin > (1ll << 26)) __trap();
+                        }
+                        const float2 f = unpack2<T>((uint32_t)w);
+                        bv = (r & 1) ? f.y : f.x;
+                    } else {
+                        const unsigned short bits = i == tid ? (unsigned short)pre_bias : __ldcg(reinterpret_cast<const unsigned short*>(a.bias) + r);
+                        bv = Elem<T>::to_f32(*reinterpret_cast<const T*>(&bits));
+                    }
+                    y = Elem<T>::from_f32(Elem<T>::to_f32(y) + bv);
+                }
+                if (valid) reinterpret_cast<T*>(a.out)[r] = y;
+                if (a.publish) {
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(xch0) + (size_t)stage * (kXchMaxRows / 2);
+                    const float yf = Elem<T>::to_f32(y);
+                    if (a.publish == 1) {
+                        const float yo = __shfl_xor_sync(0xffffffffu, yf, 1);
+                        if (!(lane & 1)) st_relaxed_u64(dst + (r >> 1), ((unsigned long long)epoch << 32) | pack2<T>(yf, yo));
+                    } else {
+                        // pair mode: lanes 0-15 hold gate rows, lanes 16-31 the up rows of the same indices.  F.silu rounded to T,
+                        // then the product rounded to T -- the arithmetic of the staging glue (stage_x_glue), done once instead of per CTA
+                        const float up = __shfl_xor_sync(0xffffffffu, yf, 16);
+                        const float sg = Elem<T>::to_f32(Elem<T>::from_f32(__fdividef(yf, 1.0f + __expf(-yf))));
+                        const float h = sg * up;
+                        const float ho = __shfl_xor_sync(0xffffffffu, h, 1);
+                        if (lane < 16 && !(lane & 1)) st_relaxed_u64(dst + (r >> 1), ((unsigned long long)epoch << 32) | pack2<T>(h, ho));
+                    }
+                }
             };
             if (a.ar_world > 1) {
                 // One-shot all-reduce in the epilogue (include/quantizations_b200.h: q4_allreduce_t): every partial travels as ONE 8-byte
@@ -749,57 +925,51 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 uint8_t* mine = reinterpret_cast<uint8_t*>(a.ar_peer_bases[me]);
                 const size_t halfsel = (size_t)(ar_epoch & 1) * W * a.ar_max_rows;
                 for (int i = tid; i < nrows_own; i += kCons) {
-                    if (row_lo + i >= R) continue;
+                    const int r = row_of(i);
+                    if (r >= R) continue;
                     const float total = row_total(i);
                     for (int p = 0; p < W; p++) {
                         uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.ar_peer_bases[p]) + kArDataOffset) + halfsel +
-                                     (size_t)me * a.ar_max_rows + row_lo + i;
+                                     (size_t)me * a.ar_max_rows + r;
                         asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(total)), "r"(ar_epoch) : "memory");
                     }
                 }
                 const uint2* slots = reinterpret_cast<const uint2*>(mine + kArDataOffset) + halfsel;
                 for (int i = tid; i < nrows_own; i += kCons) {
-                    if (row_lo + i >= R) continue;
+                    const int r = row_of(i);
                     float total = 0.0f;
-                    for (int p = 0; p < W; p++) {  // rank order: every rank computes the same sum
-                        const uint2* src = slots + (size_t)p * a.ar_max_rows + row_lo + i;
-                        uint32_t v, e;
-                        for (long long spin = 0;; spin++) {
-                            asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
-                            if (e == ar_epoch) break;
-                            if (spin > (1ll << 26)) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
+                    if (r < R) {
+                        for (int p = 0; p < W; p++) {  // rank order: every rank computes the same sum
+                            const uint2* src = slots + (size_t)p * a.ar_max_rows + r;
+                            uint32_t v, e;
+                            for (long long spin = 0;; spin++) {
+                                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
+                                if (e == ar_epoch) break;
+                                if (spin > (1ll << 26)) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
+                            }
+                            total += __uint_as_float(v);
                         }
-                        total += __uint_as_float(v);
                     }
-                    finish(i, total);
+                    emit(i, total);
                 }
             } else {
-                for (int i = tid; i < nrows_own; i += kCons) finish(i, row_total(i));
+                for (int i = tid; i < nrows_own; i += kCons) emit(i, row_total(i));
             }
         }
         if (tid == 0) mark(stage, 5);
     }  // stage loop
 
-    // ---- leave the workspace ready for the next launch: the grid-barrier counter back at zero (last CTA), this CTA's epoch advanced
-    if (c.ws) {
-        bar_sync(kConsumerBar, kCons);
-        if (tid == 0) {
-            c.ws[kWsEpochOff / 4 + bx] = epoch_base + (uint32_t)c.n;
-            if (c.n > 1) {
-                __threadfence();
-                const unsigned old = atomicAdd(c.ws, 1u);
-                if (old == (unsigned)c.n * (unsigned)G - 1u) c.ws[0] = 0;
-            }
-        }
-    }
+    // ---- leave the workspace ready for the next launch: this CTA's epoch advanced
+    if (c.ws && tid == 0) c.ws[kWsEpochOff / 4 + bx] = epoch_base + (uint32_t)c.n;
 }
 
 // ---------------------------------------------------------------------------------------------- host-side planning
 
 // tensor map of a packed weight for the ring's slots: u8 [rows, K/2], box = one half (128 bytes) of a k tile x one row group
-inline bool make_weight_map(CUtensorMap* m, const void* B, int64_t rows, int64_t K)
+// (pair mode: the gate or the up half of a row group, 16 rows)
+inline bool make_weight_map(CUtensorMap* m, const void* B, int64_t rows, int64_t K, bool pair = false)
 {
-    return make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, B, (uint64_t)K / 2, (uint64_t)rows, (uint64_t)K / 2, 128, kSub * 8,
+    return make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, B, (uint64_t)K / 2, (uint64_t)rows, (uint64_t)K / 2, 128, pair ? kSub * 4 : kSub * 8,
                        CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -810,8 +980,9 @@ inline void plan_stage(Stage& a, int rows, int K, int G, bool split_ok, int np =
     a.rows = rows;
     a.K = K;
     a.KT = (K + 511) / 512;
-    const int RT = (rows + kSub * 8 - 1) / (kSub * 8);  // row groups (one slot = a row group x one k tile)
+    const int RT = a.pair ? a.half / (kSub * 4) : (rows + kSub * 8 - 1) / (kSub * 8);  // row groups (one slot = a row group x one k tile)
     const long long units = (long long)RT * a.KT;
+    a.units = (int)units;
     long long Q;
     // Splitting row groups between CTAs balances the bytes per SM, but the owner of a cut row group has to pick the other piece
     // up.  That is free when the other CTA finishes the piece rounds before the owner needs it (it meets it first), and a memory
@@ -835,12 +1006,9 @@ inline void plan_stage(Stage& a, int rows, int K, int G, bool split_ok, int np =
     a.rem = (int)(Q % a.active);
 }
 
-// shared-memory plan of a launch: fills x_bytes / part_bytes / slots, returns the dynamic shared-memory size (0: does not fit)
-inline size_t plan_launch(Args& c, int np, size_t max_smem = 227 * 1024, int max_slots = 24)
+// shared-memory plan of a launch: fills x_bytes / part_bytes, returns the dynamic shared-memory size (0: does not fit)
+inline size_t plan_launch(Args& c, size_t max_smem = 227 * 1024)
 {
-    // ring depth: a multiple of the consumer groups and of the producer lanes (fixed ownership of ring positions, see the kernel)
-    int align = np;
-    while (align % kProdLanes) align += np;
     c.x_bytes = 0;
     c.part_bytes = 0;
     for (int i = 0; i < c.n; i++) {
@@ -850,13 +1018,9 @@ inline size_t plan_launch(Args& c, int np, size_t max_smem = 227 * 1024, int max
         if (tiles * kSub * 32 > c.part_bytes) c.part_bytes = tiles * kSub * 32;
     }
     c.part_bytes = (c.part_bytes + 127) & ~127;
-    const size_t fixed = (size_t)kLutBytes + c.x_bytes + c.part_bytes + 128 /* s_red */ + 64 /* s_misc */ + 8 /* table barrier */;
-    if (fixed + (size_t)align * (kSlotBytes + 16) > max_smem) return 0;
-    int slots = (int)((max_smem - fixed) / (kSlotBytes + 16));
-    if (slots > max_slots) slots = max_slots;
-    slots -= slots % align;
-    c.slots = slots;
-    return fixed + (size_t)slots * (kSlotBytes + 16);
+    const size_t total = (size_t)kLutBytes + (size_t)kSlots * kSlotBytes + c.x_bytes + c.part_bytes + (1 + 2 * kSlots) * 8 /* barriers */ +
+                         64 /* s_red */ + 32 /* s_misc */ + kMaxStages * sizeof(Plan);
+    return total <= max_smem ? total : 0;
 }
 
 }  // namespace ring

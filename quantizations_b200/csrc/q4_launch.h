@@ -42,6 +42,16 @@ int gemm_4bit(const void* X, const uint8_t* B, const q4_absmax_t* stats, const f
 
 int sm_count();  // cached multiprocessor count of the current device
 
+// Index of the current device, clamped to [0, kMaxDevices): cudaFuncSetAttribute and the dynamic-shared-memory probe apply per
+// DEVICE, so "already done" flags are kept per device, not per process (a process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+inline int device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
 inline int ilog2(int v)
 {
     int s = 0;

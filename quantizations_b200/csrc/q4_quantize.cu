@@ -247,7 +247,8 @@ static int launch_quantize(const float* code, const T* A, float* absmax, uint8_t
             const unsigned grid = (unsigned)(want < cap ? want : cap);
 #define Q4_LUT_LAUNCH(BS, EPT)                                                                                            \
     {                                                                                                                     \
-        static bool attr = false;                                                                                         \
+        static bool attr_dev[kMaxDevices] = {};                                                                           \
+        bool& attr = attr_dev[device_slot()];                                                                             \
         if (!attr) {                                                                                                      \
             cudaError_t e = cudaFuncSetAttribute(quantize_4bit_lut_kernel<T, BS, QT, EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncLutBytes); \
             if (e != cudaSuccess) return (int)e;                                                                          \

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .core import Params4bit, QuantState, _dequantize_4bit_into, fused_gemm_supported, gemm_4bit, gemv_4bit
+from .core import Params4bit, QuantState, _dequantize_4bit_into, _on_device, fused_gemm_supported, gemm_4bit, gemv_4bit
 
 
 def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: torch.Tensor = None, bias=None,
@@ -166,7 +166,8 @@ def _linear4bit_decode(self, x, weight, bias):
         f.prefetch, f.prefetch_bytes, f.prefetch_K = t.data_ptr(), t.numel() * t.element_size(), k
     else:
         f.prefetch, f.prefetch_bytes, f.prefetch_K = None, 0, 0
-    rc = c[4](c[2], torch.cuda.current_stream(x.device).cuda_stream)
+    with _on_device(x.device):
+        rc = c[4](c[2], torch.cuda.current_stream(x.device).cuda_stream)
     if rc:
         _lib.check(rc, "gemv_4bit")
     return out

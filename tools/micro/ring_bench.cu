@@ -70,6 +70,16 @@ __global__ void ref_gemv(const bf16* x, const uint8_t* B, const uint8_t* qabs, c
     if (lane == 0) out[r] = acc + (bias ? __bfloat162float(bias[r]) : 0.0f);
 }
 
+// h = silu(gate) * up with the staging glue's arithmetic (F.silu rounded to bf16, then the product rounded to bf16)
+__global__ void swiglu_ref(const bf16* gate, const bf16* up, bf16* h, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = __bfloat162float(gate[i]), u = __bfloat162float(up[i]);
+    const float sg = __bfloat162float(__float2bfloat16(__fdividef(g, 1.0f + __expf(-g))));
+    h[i] = __float2bfloat16(sg * u);
+}
+
 struct Mat {
     int rows, K;
     uint8_t* B;
@@ -121,7 +131,7 @@ static cudaError_t launch(int nc, const ring::Args& a, int grid, size_t smem, bo
 
 int main(int argc, char** argv)
 {
-    int nc = 16, chain = 4, layers = 32, pool = 6, iters = 20, slots_cap = 24;
+    int nc = 16, chain = 4, layers = 32, pool = 6, iters = 20;
     bool split = true, pdl = true, trace = false, check_only = false;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--nc")) nc = atoi(argv[++i]);
@@ -130,7 +140,6 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--layers")) layers = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--pool")) pool = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
-        else if (!strcmp(argv[i], "--slots")) slots_cap = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--no-split")) split = false;
         else if (!strcmp(argv[i], "--no-pdl")) pdl = false;
         else if (!strcmp(argv[i], "--trace")) trace = true;
@@ -189,7 +198,7 @@ int main(int argc, char** argv)
     CK(cudaMalloc(&ws, ring::kWsBytes));
     CK(cudaMemset(ws, 0, ring::kWsBytes));
     unsigned long long* d_trace = nullptr;
-    const size_t trace_n = (size_t)ring::kMaxStages * G * 8;
+    const size_t trace_n = (size_t)ring::kMaxStages * G * ring::kTraceSlots;
     if (trace) {
         CK(cudaMalloc(&d_trace, trace_n * 8 * 64));
         CK(cudaMemset(d_trace, 0, trace_n * 8 * 64));
@@ -197,9 +206,19 @@ int main(int argc, char** argv)
     CK(cudaDeviceSynchronize());
     printf("pool: %zu MB packed\n", packed_total >> 20);
 
-    auto fill_stage = [&](ring::Stage& st, const Mat& m, bool with_bias) {
+    // stage `pos` of a launch over mats[idx[..]]: stages after the first consume the previous stage's (tagged) output; a gate/up
+    // stage followed by a K = rows / 2 stage runs in pair mode and publishes silu(gate) * up
+    auto fill_stage = [&](ring::Stage& st, const std::vector<int>& idx, int pos, bool with_bias) {
+        const Mat& m = mats[idx[pos]];
         memset(&st, 0, sizeof(st));
-        if (!ring::make_weight_map(&st.map, m.B, m.rows, m.K)) {
+        const bool has_next = pos + 1 < (int)idx.size();
+        const Mat* nx = has_next ? &mats[idx[pos + 1]] : nullptr;
+        st.pair = (nx && nx->K * 2 == m.rows) ? 1 : 0;
+        st.half = m.rows / 2;
+        st.publish = !nx ? 0 : (st.pair ? 2 : 1);
+        if (nx && !st.pair && nx->K > m.rows) { printf("chain: stage %d needs %d activations, the previous one has %d rows\n", pos + 1, nx->K, m.rows); exit(1); }
+        st.x_tagged = pos > 0 ? 1 : 0;
+        if (!ring::make_weight_map(&st.map, m.B, m.rows, m.K, st.pair != 0)) {
             printf("tensor map failed\n");
             exit(1);
         }
@@ -216,43 +235,59 @@ int main(int argc, char** argv)
         st.offsets[0] = m.offset;
         st.out = m.out;
         st.bias = with_bias ? bias : nullptr;
-        ring::plan_stage(st, m.rows, m.K, G, split);
+        st.bias_stage = -1;
+        ring::plan_stage(st, m.rows, m.K, G, split, nc / g_wps);
     };
     auto make_args = [&](ring::Args& a, const std::vector<int>& idx, bool with_bias, size_t& smem) {
         memset(&a, 0, sizeof(a));
         a.n = (int)idx.size();
-        for (int i = 0; i < a.n; i++) fill_stage(a.st[i], mats[idx[i]], with_bias);
+        for (int i = 0; i < a.n; i++) fill_stage(a.st[i], idx, i, with_bias);
         a.lut = d_lut;
         a.code = d_code;
         a.ws = ws;
-        smem = ring::plan_launch(a, nc / g_wps, 227 * 1024, slots_cap);
+        smem = ring::plan_launch(a, 227 * 1024);
         if (!smem) { printf("smem plan failed\n"); exit(1); }
     };
 
     // ---- correctness: every stage kind, alone and chained, against the naive kernel
     {
         float* d_ref;
+        bf16* d_h;
         CK(cudaMalloc(&d_ref, 28672 * 4));
+        CK(cudaMalloc(&d_h, 28672 * 2));
         std::vector<float> ref(28672);
         std::vector<bf16> got(28672);
-        for (int pass = 0; pass < 2; pass++) {
+        for (int pass = 0; pass < 3; pass++) {
             ring::Args a;
             size_t smem;
             std::vector<int> idx;
             if (pass == 0) idx = {0, 1, 2, 3};
-            else idx = {3, 1};
+            else if (pass == 1) idx = {3, 1};
+            else idx = {1, 2, 3};  // o -> gate/up -> down, down's residual = o's output through its tagged copy
             if ((int)idx.size() > chain) idx.resize(chain);
             make_args(a, idx, pass == 1, smem);
+            if (pass == 2 && a.n == 3) {
+                a.st[2].bias = mats[idx[0]].out;
+                a.st[2].bias_stage = 0;
+            }
             for (int i = 0; i < a.n; i++) CK(cudaMemset(mats[idx[i]].out, 0xff, mats[idx[i]].rows * 2));
             CK(launch(nc, a, G, smem, false, 0));
             CK(cudaDeviceSynchronize());
-            printf("check pass %d: slots %d smem %zu x_bytes %d part_bytes %d\n", pass, a.slots, smem, a.x_bytes, a.part_bytes);
+            printf("check pass %d: smem %zu x_bytes %d part_bytes %d\n", pass, smem, a.x_bytes, a.part_bytes);
             for (int i = 0; i < a.n; i++) {
                 const Mat& m = mats[idx[i]];
                 float off;
                 CK(cudaMemcpy(&off, m.offset, 4, cudaMemcpyDeviceToHost));
-                ref_gemv<<<(m.rows + 7) / 8, 256>>>(m.K == 4096 ? x4096 : x14336, m.B, m.qabs, d_code2, m.absmax2, off, d_code,
-                                                    pass == 1 ? bias : nullptr, d_ref, m.rows, m.K);
+                const bf16* xin = m.K == 4096 ? x4096 : x14336;
+                if (i > 0) {  // the stage consumed the previous stage's output as the kernel stored it
+                    const Mat& pm = mats[idx[i - 1]];
+                    if (a.st[i - 1].pair) {
+                        swiglu_ref<<<(m.K + 255) / 256, 256>>>(pm.out, pm.out + pm.rows / 2, d_h, m.K);
+                        xin = d_h;
+                    } else xin = pm.out;
+                }
+                ref_gemv<<<(m.rows + 7) / 8, 256>>>(xin, m.B, m.qabs, d_code2, m.absmax2, off, d_code,
+                                                    pass == 1 ? bias : (pass == 2 && i == 2 ? mats[idx[0]].out : nullptr), d_ref, m.rows, m.K);
                 CK(cudaMemcpy(ref.data(), d_ref, m.rows * 4, cudaMemcpyDeviceToHost));
                 CK(cudaMemcpy(got.data(), m.out, m.rows * 2, cudaMemcpyDeviceToHost));
                 double worst = 0, scale = 0;
@@ -262,8 +297,8 @@ int main(int argc, char** argv)
                     if (!(d <= worst)) { worst = d; bad = r; }
                     if (fabs(ref[r]) > scale) scale = fabs(ref[r]);
                 }
-                printf("  stage %d (%dx%d, active %d per %d rem %d gran %d): max err %.3g / scale %.3g = %.3g at row %d %s\n", i, m.rows, m.K,
-                       a.st[i].active, a.st[i].per, a.st[i].rem, a.st[i].gran, worst, scale, worst / scale, bad, worst / scale < 8e-3 ? "ok" : "FAIL");
+                printf("  stage %d (%dx%d, pair %d publish %d, active %d per %d rem %d gran %d): max err %.3g / scale %.3g = %.3g at row %d %s\n", i, m.rows, m.K,
+                       a.st[i].pair, a.st[i].publish, a.st[i].active, a.st[i].per, a.st[i].rem, a.st[i].gran, worst, scale, worst / scale, bad, worst / scale < 8e-3 ? "ok" : "FAIL");
             }
         }
         CK(cudaFree(d_ref));
@@ -327,8 +362,8 @@ int main(int argc, char** argv)
         sum += ms;
         if (ms < best) best = ms;
     }
-    printf("RESULT nc %d wps %d chain %d split %d pdl %d slots %d: %.4f ms/step best, %.4f mean; %.1f GB/s (%.3f of 6531.6), %.2f us/stage\n", nc, g_wps, chain,
-           (int)split, (int)pdl, launches[0].slots, best, sum / 5, algo / best / 1e6, algo / best / 1e6 / 6531.6, best * 1e3 / (layers * 4));
+    printf("RESULT nc %d wps %d chain %d split %d pdl %d: %.4f ms/step best, %.4f mean; %.1f GB/s (%.3f of 6531.6), %.2f us/stage\n", nc, g_wps, chain,
+           (int)split, (int)pdl, best, sum / 5, algo / best / 1e6, algo / best / 1e6 / 6531.6, best * 1e3 / (layers * 4));
 
     if (trace) {
         // one eager step with the marks on (first `launches` entries only need their own buffers)
@@ -337,27 +372,38 @@ int main(int argc, char** argv)
         const size_t nl = launches.size() < 64 ? launches.size() : 64;
         std::vector<unsigned long long> h(trace_n * nl);
         CK(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
-        const char* names[8] = {"start", "stage in", "barrier", "x staged", "loop end", "epi end", "tma first", "tma last"};
+        const char* names[9] = {"start", "stage in", "x loaded", "x staged", "loop end", "epi end", "tma first", "tma last", "all warps"};
         // launches in the middle of the step
         for (size_t li = nl / 2; li < nl / 2 + 2 && li < nl; li++) {
             unsigned long long t0 = ~0ull;
             for (int st = 0; st < launches[li].n; st++)
                 for (int b = 0; b < G; b++) {
-                    const unsigned long long v = h[li * trace_n + ((size_t)st * G + b) * 8 + 1];
+                    const unsigned long long v = h[li * trace_n + ((size_t)st * G + b) * ring::kTraceSlots + 1];
                     if (v && v < t0) t0 = v;
                 }
             printf("launch %zu (relative to its first 'stage in'), us: min / median / max over CTAs\n", li);
             for (int st = 0; st < launches[li].n; st++) {
                 printf("  stage %d (%dx%d)\n", st, launches[li].st[st].rows, launches[li].st[st].K);
-                for (int m = (st == 0 ? 0 : 1); m < 8; m++) {
+                for (int m = (st == 0 ? 0 : 1); m < 9; m++) {
                     std::vector<double> v;
                     for (int b = 0; b < G; b++) {
-                        const unsigned long long t = h[li * trace_n + ((size_t)st * G + b) * 8 + m];
+                        const unsigned long long t = h[li * trace_n + ((size_t)st * G + b) * ring::kTraceSlots + m];
                         if (t) v.push_back(((double)t - (double)t0) / 1e3);
                     }
                     if (v.empty()) continue;
                     std::sort(v.begin(), v.end());
                     printf("    %-9s %8.2f %8.2f %8.2f\n", names[m], v.front(), v[v.size() / 2], v.back());
+                }
+            }
+            if (li == nl / 2 && launches[li].n > 2) {
+                const int st = 2;
+                printf("  per CTA, stage %d: cta smid slots | stage-in staged loop-end all-warps epi-end\n", st);
+                for (int b = 0; b < G; b++) {
+                    const unsigned long long* t = &h[li * trace_n + ((size_t)st * G + b) * ring::kTraceSlots];
+                    auto us = [&](int m) { return t[m] ? ((double)t[m] - (double)t0) / 1e3 : 0.0; };
+                    const ring::Stage& sg = launches[li].st[st];
+                    const int nsl = b < sg.active ? (sg.per + (b < sg.rem ? 1 : 0)) * sg.gran : 0;
+                    printf("   cta %3d sm %3llu slots %3d | %7.2f %7.2f %7.2f %7.2f %7.2f\n", b, t[9], nsl, us(1), us(3), us(4), us(8), us(5));
                 }
             }
         }
