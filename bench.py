@@ -132,10 +132,12 @@ def build_stack(cfg, tp, rank, device, dtype, quant_type, layers, q):
         for j, (name, N, K, par) in enumerate(layer_shapes(cfg, tp)):
             g.manual_seed(1000 * layer + j)
             fullN, fullK = (N * tp, K) if par == "col" else (N, K * tp)
+            # N(0, 1/in_features): every GEMV keeps the activation's scale, so the outputs of a step that really feeds each Linear's
+            # output into the next stay finite over 128 dependent GEMVs
             if tp == 1:
-                W = torch.randn(N, K, device=device, dtype=torch.float32, generator=g).mul_(0.02).to(dtype)
+                W = torch.randn(N, K, device=device, dtype=torch.float32, generator=g).mul_(fullK ** -0.5).to(dtype)
             else:
-                Wf = torch.randn(fullN, fullK, device=device, dtype=torch.float32, generator=g).mul_(0.02).to(dtype)
+                Wf = torch.randn(fullN, fullK, device=device, dtype=torch.float32, generator=g).mul_(fullK ** -0.5).to(dtype)
                 W = (Wf[rank * N:(rank + 1) * N] if par == "col" else Wf[:, rank * K:(rank + 1) * K]).contiguous()
                 del Wf
             lin = q.Linear4bit(K, N, bias=False, compute_dtype=dtype, compress_statistics=True, quant_type=quant_type,
@@ -174,7 +176,7 @@ def run_ours(args, rank, world, device):
 
     h, inter = cfg["hidden"], cfg["inter"]
     torch.manual_seed(1)
-    x_in = {K: torch.randn(1, 1, K, device=device, dtype=dtype) for K in {m.in_features for m in mods}}
+    x_in = {h: torch.randn(1, 1, h, device=device, dtype=dtype)}  # the token's hidden state entering layer 0; everything else is produced by the step
     outs = {}
     for m in units:
         outs.setdefault((m.name_, m.out_features), torch.empty(1, 1, m.out_features, device=device, dtype=dtype))
@@ -213,6 +215,27 @@ def run_ours(args, rank, world, device):
         tp_check = {"status": "ok", "units": len(picked), "max_rel_err_vs_nccl": worst, "bit_identical_across_ranks": True}
 
     pdl = _lib.Q4_GEMV_PDL if args.pdl else 0
+    # ---- data flow of a step: a decode token's Linear4bit forwards are DEPENDENT -- every Linear consumes what the previous one
+    #      produced (q/k/v <- the previous layer's down_proj, o_proj <- the first in_features values of q/k/v [attention is not part
+    #      of this stack], gate/up <- o_proj, down_proj <- the first in_features values of gate/up), so a launch can never start its
+    #      arithmetic before its predecessor's last row exists.  All launch paths below run this same flow.
+    per_layer = len(units) // layers
+    first_in = {"qkv_proj", "q_proj", "k_proj", "v_proj"}
+    qkey = ("qkv_proj", (h + 2 * cfg["kv"]) // tp) if args.group else ("q_proj", h // tp)
+    gkey = ("gate_up_proj", 2 * inter // tp) if args.group else ("gate_proj", inter // tp)
+
+    def source_of(i, m, bufs, x0):
+        """the tensor unit i reads: its first in_features values"""
+        if m.name_ in first_in:
+            t = x0 if i // per_layer == 0 else bufs[("down_proj", h)]
+        elif m.name_ == "o_proj":
+            t = bufs[qkey]
+        elif m.name_ in ("gate_up_proj", "gate_proj", "up_proj"):
+            t = bufs[("o_proj", h)]
+        else:
+            t = bufs[gkey]
+        return t[..., :m.in_features]
+
     # A decoder layer's Linear4bit calls form a small DAG: q/k/v share their input and are independent of each other, so do
     # gate/up; o_proj and down_proj each depend on what precedes them.  The step is launched exactly like that: independent
     # GEMVs go to parallel streams (parallel branches of the CUDA graph) with Q4_GEMV_SHARE_SM so they are co-resident on
@@ -260,13 +283,13 @@ def run_ours(args, rank, world, device):
             npt, nby = (None, 0) if nxt is None else (nxt.data_ptr(), nxt.numel())
             nk = units[(i + 1) % len(units)].in_features if args.prefetch else 0  # exact hint: the next launch's in_features
             if isinstance(m, q.Linear4bitGroup):
-                f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.packed.data_ptr(), ctypes.pointer(m._stats), m._offsets,
+                f = _lib.GemvFused(source_of(i, m, outs, x_in[h]).data_ptr(), None, None, 0.0, m.packed.data_ptr(), ctypes.pointer(m._stats), m._offsets,
                                    m._row_end, len(m.splits), m.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, 64,
                                    _lib.Q4_BF16, flags, npt, nby, m.lut(dtype).data_ptr(), ws_ptr, ws_bytes, prefetch_K=nk)
             else:
                 st = m.weight.quant_state
                 ar = ctypes.pointer(fused_ar.struct) if (fused_ar is not None and m.parallel == "row") else None
-                f = _lib.GemvFused(x_in[m.in_features].data_ptr(), None, None, 0.0, m.weight.data_ptr(), ctypes.pointer(st.native_stats()), None,
+                f = _lib.GemvFused(source_of(i, m, outs, x_in[h]).data_ptr(), None, None, 0.0, m.weight.data_ptr(), ctypes.pointer(st.native_stats()), None,
                                    None, 1, st.code.data_ptr(), None, out.data_ptr(), m.out_features, m.in_features, st.blocksize,
                                    _lib.Q4_BF16, flags, npt, nby, st.lut(dtype).data_ptr(), ws_ptr, ws_bytes, ar, nk)
             fused_args[key] = f
@@ -310,10 +333,39 @@ def run_ours(args, rank, world, device):
                 _lib.check(rc, "q4_gemv_4bit_chain")
 
     use_chain = args.chain and args.group and not side and (comm is None or fused_ar is not None) and len(units) % 4 == 0
+    # the persistent ring kernel (q4_gemv_4bit_ring): up to eight dependent GEMVs (two decoder layers) per launch
+    use_ring = args.ring and not use_chain and args.group and not side and comm is None
+    ring_arrays = []
+    ring_state = {"launches": 0, "fallbacks": 0}
+
+    def build_rings():
+        ws = q.core.ring_workspace(device)
+        n_max = _lib.Q4_GEMV_RING_MAX_STAGES
+        for c0 in range(0, len(units), n_max):
+            idx = list(range(c0, min(c0 + n_max, len(units))))
+            arr = (_lib.GemvFused * len(idx))(*[launch_struct(i, units[i], pdl) for i in idx])
+            ring_arrays.append((arr, idx, ws))
+
+    def step_ring():
+        stream = torch.cuda.current_stream().cuda_stream
+        for arr, idx, ws in ring_arrays:
+            rc = L.q4_gemv_4bit_ring(arr, len(idx), ws.data_ptr(), ws.numel(), stream)
+            if rc in (_lib.Q4_ERR_SHAPE, _lib.Q4_ERR_ALIGN):  # nothing was launched: the single-GEMV kernel takes these stages
+                ring_state["fallbacks"] += 1
+                for i in idx:
+                    launch_cabi(i, units[i], pdl)
+            elif rc:
+                _lib.check(rc, "q4_gemv_4bit_ring")
+            else:
+                ring_state["launches"] += 1
 
     def step_cabi():
         """one decode token's worth of Linear4bit GEMVs straight through the C ABI"""
-        if use_chain:
+        if use_ring:
+            if not ring_arrays:
+                build_rings()
+            step_ring()
+        elif use_chain:
             if not chain_arrays:
                 build_chains()
             step_chained()
@@ -370,16 +422,31 @@ def run_ours(args, rank, world, device):
     def launch_api(i, m, flags):
         m.gemv_flags = flags
         m.prefetch_next = (packed_of(units[(i + 1) % len(units)]), units[(i + 1) % len(units)].in_features) if args.prefetch else None
+        x = source_of(i, m, y_static, x_static[h])
         if fused_ar is not None and m.parallel == "row":
-            y = q.gemv_4bit_fused(x_static[m.in_features], m.weight.data, m.weight.quant_state, flags=flags, allreduce=fused_ar)
+            y = q.gemv_4bit_fused(x, m.weight.data, m.weight.quant_state, flags=flags, allreduce=fused_ar)
         else:
-            y = m.forward_fused(x_static[m.in_features]) if isinstance(m, q.Linear4bitGroup) else m(x_static[m.in_features])
+            y = m.forward_fused(x) if isinstance(m, q.Linear4bitGroup) else m(x)
             if comm is not None and m.parallel == "row":
                 comm.all_reduce(y)
         y_static[(m.name_, m.out_features)] = y
 
+    y_ring = {k: torch.empty_like(v) for k, v in outs.items()} if use_ring else {}
+
     def step_api():
-        run_stack(launch_api)
+        if not use_ring:
+            return run_stack(launch_api)
+        # the public chain API: quantizations_b200.gemv_4bit_chain collects dependent Linear4bit forwards and issues them as
+        # persistent ring launches (eight stages each)
+        y_static.update(y_ring)
+        with q.gemv_4bit_chain(flags=pdl) as ch:
+            for i, m in enumerate(units):
+                x = source_of(i, m, y_ring, x_static[h])
+                out = y_ring[(m.name_, m.out_features)]
+                if isinstance(m, q.Linear4bitGroup):
+                    ch.add(x, None, group=m, out=out)
+                else:
+                    ch.add(x, m.weight.data, m.weight.quant_state, out=out)
 
     step_api()
     torch.cuda.synchronize()
@@ -412,6 +479,8 @@ def run_ours(args, rank, world, device):
     for k in out_keys:
         if not torch.equal(y_host[k].to(device), outs[k]):
             raise RuntimeError(f"e2e output {k} differs from the C-ABI output")
+        if not torch.isfinite(outs[k].float()).all():
+            raise RuntimeError(f"output {k} of the chained step is not finite")
 
     if rank != 0:
         if not args.no_decode:  # the tensor-parallel decode leg runs on every rank
@@ -436,7 +505,10 @@ def run_ours(args, rank, world, device):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, layers, len(mods) if world == 1 else 7 * layers),
                    "parallelism": f"tp{world}" if world > 1 else "single GPU"},
-        "launch": (f"{len(units)} launches/step" + (" (q/k/v and gate/up grouped: they share their input)" if args.group else "")
+        "launch": ((f"{launches_per_step} persistent ring launches/step ({len(units)} dependent GEMV stages, <= {_lib.Q4_GEMV_RING_MAX_STAGES} per launch: "
+                    "TMA weight ring streaming across stage boundaries, inter-CTA split-K, tagged activation exchange instead of grid barriers)"
+                    if use_ring and ring_state["fallbacks"] == 0 else f"{len(units)} launches/step")
+                   + (" (q/k/v and gate/up grouped: they share their input)" if args.group else "")
                    + (", CUDA graph replay" if graph is not None else ", eager") + (" + programmatic dependent launch" if args.pdl else "")
                    + (", chained: 1 + layers persistent launches per step (o -> gate/up -> down -> next q/k/v per launch)" if use_chain else "")
                    + (", q/k/v and gate/up as parallel graph branches (co-resident CTAs)" if args.branches else "")
@@ -455,9 +527,11 @@ def run_ours(args, rank, world, device):
                 "api": "quantizations_b200.Linear4bit / Linear4bitGroup forward x%d under quantizations_b200.graphs.capture, pinned-host x in / y out" % len(units)},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk.summary(),
-        "roofline": {"bound": "hbm", "kernel": "q4::gemv_mma_kernel<bf16, nested>", "achieved": round(value / world, 1), "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": ("q4::ring::gemv_ring_kernel<bf16, nested, 16, 2>" if use_ring and ring_state["fallbacks"] == 0
+                                                else "q4::gemv_mma_kernel<bf16, nested>"), "achieved": round(value / world, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(value / world / peak, 4), "peak_source": peak_src,
                      "avg_launch_us": round(per_launch_us, 3), "algorithmic_bytes_per_launch": step_bytes_local // launches_per_step,
+                     "gemv_stages_per_step": len(units), "avg_stage_us": round(ms_per_step * 1e3 / len(units), 3),
                      "traffic": traffic, "timed_blocks_ms": [round(t, 3) for t in times[:5]]},
     }
     if tp_check is not None:
@@ -543,6 +617,8 @@ def decode_tok_s(args, device, impl, rank=0, world=1):
             from quantizations_b200 import tp as tpmod
 
             model.fused_ar = None if args.nccl_allreduce else tpmod.FusedAllReduce(cfg.hidden, device=device)
+        elif getattr(args, "ring", True) or getattr(args, "chain", False):
+            model.chain = True  # o -> gate/up -> down -> next q/k/v as one persistent launch per layer (ring kernel, else the older chain)
         ctx, graph = torch.cuda.stream(torch.cuda.Stream(device=device)), True
     else:
         from oracle import ref_linear
@@ -745,6 +821,9 @@ def main():
     ap.add_argument("--chain", action="store_true",
                     help="one persistent launch per layer (q4_gemv_4bit_chain: o -> gate/up -> down -> next q/k/v) instead of one "
                          "launch per (grouped) Linear; measured SLOWER on B200 (1.65 vs 1.47 ms/step: DESIGN.md 4.1c), hence opt-in")
+    ap.add_argument("--no-ring", dest="ring", action="store_false",
+                    help="single GPU: one launch per (grouped) Linear (q4_gemv_4bit_fused) instead of the persistent ring kernel "
+                         "(q4_gemv_4bit_ring: eight dependent GEMVs per launch, weights streamed through a TMA ring across stage boundaries)")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="tensor-parallel runs: NCCL all-reduce after the row-parallel GEMVs (the baseline) instead of the fused epilogue exchange")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",

@@ -200,6 +200,27 @@ int q4_gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats
  * flags of stage 0 apply to the launch. */
 int q4_gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, void* stream);
 
+/* `n` (<= Q4_GEMV_RING_MAX_STAGES) DEPENDENT decode GEMVs in one launch of the persistent ring kernel (csrc/q4_gemv_ring.cuh): one
+ * CTA per SM; a producer warp streams every stage's packed weight through a shared-memory ring with TMA and never stops at a stage
+ * boundary (the weight does not depend on the activation); rows are split across CTAs at k-tile granularity (inter-CTA split-K,
+ * fixed-order combine); between stages there is no grid barrier -- a stage's epilogue stores its outputs as tagged words that the next
+ * stage's staging polls directly.  The dependencies must be expressed through the pointers:
+ *   - stage i+1's x == stage i's out (the first K values are consumed), or
+ *   - stage i is a grouped gate/up pair (nmat == 2, equal halves) and stage i+1 has x_gate == stage i's out and x == out + rows/2:
+ *     the gate/up epilogue then publishes silu(gate) * up itself (stage i's out is still written in full);
+ *   - a stage's bias may be memory the PREVIOUS kernel wrote, or exactly the out of an earlier stage (the residual stream);
+ *   - stage 0's x / x_gate, and any stage's rms_weight, are memory the previous kernel wrote.
+ * Any other aliasing between stages, tensor-parallel stages, ragged shapes (K % 512, rows % 32, grouped members not ending on
+ * 32-row boundaries), K > 16384, a missing table image or mixed types return Q4_ERR_SHAPE / Q4_ERR_ALIGN WITHOUT launching: the caller
+ * falls back to q4_gemv_4bit_chain / q4_gemv_4bit_fused.  Results agree with those within the GEMV tolerance (same per-tile
+ * arithmetic, same fixed summation order over k tiles).  `workspace`: Q4_GEMV_RING_WS_BYTES of 16-byte aligned device memory, zeroed
+ * ONCE by the caller, owned by one stream at a time (it carries the exchange words and the per-CTA launch epochs, so replayed CUDA
+ * graphs stay in step).  flags of stage 0 apply to the launch (Q4_GEMV_PDL).  The grid is one CTA per SM and its CTAs wait for each
+ * other: it must not be launched while a kernel that waits for IT holds SMs. */
+#define Q4_GEMV_RING_MAX_STAGES 8
+#define Q4_GEMV_RING_WS_BYTES (73728 + 8 * 131072)
+int q4_gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* The decode GEMV decodes one packed BYTE per shared-memory lookup through a 64-KB table derived from the 16-entry 4-bit code
  * and the 256-entry absmax code (reference: `T quant_map[16]` in kernels.cu:1115-1121 and `code[q]` in kernels.cu:552).  The
  * table depends only on (code, code2, dtype), i.e. it is the same for every Linear4bit of a model: build it once into

@@ -24,7 +24,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import AbsmaxStats, check
+from ._lib import AbsmaxStats, Q4Error, check
 
 name2qmap = {}
 
@@ -794,19 +794,52 @@ class gemv_4bit_chain:
             return
         dev = self.stages[0][1][0].device
         stream = torch.cuda.current_stream(dev)
-        key = (dev.index, stream.cuda_stream)
-        bar = _chain_barriers.get(key)
-        if bar is None:
-            bar = _chain_barriers[key] = torch.zeros(64, dtype=torch.int32, device=dev)
         lib = _lib.lib()
+        stages, self.stages = self.stages, []
         with _on_device(dev):
-            for i in range(0, len(self.stages), 4):
-                part = self.stages[i:i + 4]
+            i = 0
+            while i < len(stages):
+                # the persistent ring kernel takes up to eight dependent stages; what it does not support (Q4_ERR_SHAPE / Q4_ERR_ALIGN,
+                # nothing launched) goes to the older chained launch, four stages at a time
+                if _USE_RING:
+                    part = stages[i:i + _lib.Q4_GEMV_RING_MAX_STAGES]
+                    ws = ring_workspace(dev)
+                    arr = (_lib.GemvFused * len(part))(*[f for f, _ in part])
+                    rc = lib.q4_gemv_4bit_ring(arr, len(part), ws.data_ptr(), ws.numel(), stream.cuda_stream)
+                    if rc == 0:
+                        i += len(part)
+                        continue
+                    if rc not in (_lib.Q4_ERR_SHAPE, _lib.Q4_ERR_ALIGN):
+                        check(rc, "gemv_4bit_ring")
+                part = stages[i:i + 4]
+                key = (dev.index, stream.cuda_stream)
+                bar = _chain_barriers.get(key)
+                if bar is None:
+                    bar = _chain_barriers[key] = torch.zeros(64, dtype=torch.int32, device=dev)
                 arr = (_lib.GemvFused * len(part))(*[f for f, _ in part])
                 rc = lib.q4_gemv_4bit_chain(arr, len(part), bar.data_ptr(), stream.cuda_stream)
                 if rc:
                     check(rc, "gemv_4bit_chain")
-        self.stages = []
+                i += len(part)
+
+
+_USE_RING = os.environ.get("Q4_GEMV_RING", "1") != "0"
+_ring_workspaces = {}
+
+
+def ring_workspace(device) -> Tensor:
+    """Workspace of the persistent ring GEMV (include/quantizations_b200.h: q4_gemv_4bit_ring): zeroed ONCE, one per device -- it
+    carries the exchange words and the per-CTA launch epochs, so it must neither be re-zeroed by a replayed CUDA graph nor be used
+    by two streams at once.  Allocate it (one eager call) before capturing a graph that contains ring launches."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    ws = _ring_workspaces.get(idx)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise Q4Error("the ring GEMV workspace must exist before stream capture: run the step once eagerly first")
+        ws = _ring_workspaces[idx] = torch.zeros(_lib.Q4_GEMV_RING_WS_BYTES, dtype=torch.uint8, device=torch.device("cuda", idx))
+    return ws
 
 
 def decode_attention(qkv: Tensor, cos: Tensor, sin: Tensor, k_cache: Tensor, v_cache: Tensor, pos: Tensor, nh: int, nkv: int,

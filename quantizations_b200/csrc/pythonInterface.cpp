@@ -124,6 +124,11 @@ int q4_gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, v
     return q4::gemv_4bit_chain(stages, n, barrier_ws, (cudaStream_t)stream);
 }
 
+int q4_gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    return q4::gemv_4bit_ring(stages, n, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int q4_gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
                        int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, void* workspace,
                        int64_t workspace_bytes, void* stream)

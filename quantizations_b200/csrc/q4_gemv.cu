@@ -166,7 +166,26 @@ static int launch_mma(const MmaChainArgs& c, bool nested, bool compact, bool kta
     return launch_pdl((void (*)(const MmaSingleArgs))kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, one);
 }
 
-static int g_dyn_base = -1;  // where dynamic shared memory starts in a CTA's window (probed once, see gemv_dispatch)
+static int g_dyn_base = -1;  // where dynamic shared memory starts in a CTA's window (probed once)
+
+// A property of the architecture / driver, not of a device: probed once per process (outside stream capture) and shared by the
+// kernels whose table address is a compile-time constant (q4_gemv_mma.cuh compact layout, q4_gemv_ring.cuh).
+int g_dyn_base_probed(cudaStream_t stream)
+{
+    if (g_dyn_base < 0) {
+        uint32_t* d = nullptr;
+        uint32_t h = 0;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cap);
+        if (cap == cudaStreamCaptureStatusNone && cudaMalloc(&d, 4) == cudaSuccess) {
+            probe_dyn_smem_base_kernel<<<1, 32, 1024, stream>>>(d);
+            if (cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess)
+                g_dyn_base = (int)h;
+            cudaFree(d);
+        }
+    }
+    return g_dyn_base;
+}
 
 template <typename T>
 static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, const float* code, const T* bias, T* out,
@@ -188,20 +207,7 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                             (!nested || ((reinterpret_cast<uintptr_t>(st->qabsmax) & 1) == 0 && st->blocksize2 >= 128)) &&
                             (nested || (reinterpret_cast<uintptr_t>(st->absmax) & 7) == 0);
         // where does dynamic shared memory start in the CTA's window?  (probed once; the compact table layout depends on it)
-        static int dyn_base = -1;
-        if (dyn_base < 0) {
-            uint32_t* d = nullptr;
-            uint32_t h = 0;
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            cudaStreamIsCapturing(stream, &cap);
-            if (cap == cudaStreamCaptureStatusNone && cudaMalloc(&d, 4) == cudaSuccess) {
-                probe_dyn_smem_base_kernel<<<1, 32, 1024, stream>>>(d);
-                if (cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess)
-                    dyn_base = (int)h;
-                cudaFree(d);
-            }
-            g_dyn_base = dyn_base;
-        }
+        const int dyn_base = g_dyn_base_probed(stream);
         static const int env_impl = getenv("Q4_GEMV_IMPL") ? atoi(getenv("Q4_GEMV_IMPL")) : 0;  // 1: force the mma.sync kernel
         // tcgen05 kernel (q4_gemv_tc.cuh): needs the prebuilt table image and the split-K workspace
         if (fast && env_impl != 1 && !stage_out && !(flags & Q4_GEMV_SWIGLU) && pro && pro->lut && pro->workspace && !pro->ar && dyn_base == kDynBase && K <= 65536 && (K % 256) == 0 &&

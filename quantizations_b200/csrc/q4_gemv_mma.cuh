@@ -172,7 +172,7 @@ __device__ __forceinline__ void mma_trace_x(const MmaGemvArgs& a, int k)
     }
 }
 
-__device__ __noinline__ void prefetch_next_share(const uint8_t* next, int64_t next_bytes, int lane)
+static __device__ __noinline__ void prefetch_next_share(const uint8_t* next, int64_t next_bytes, int lane)
 {
     const int64_t share = ((next_bytes / gridDim.x) + 15) & ~(int64_t)15;
     const int64_t lo = share * blockIdx.x;
@@ -185,7 +185,7 @@ __device__ __noinline__ void prefetch_next_share(const uint8_t* next, int64_t ne
 // CTA's first instructions 1.287 ms, after its loop 1.312 ms, right after griddepcontrol.wait 1.357 ms; two / four times the head
 // 1.32 / 1.39 ms; additionally the CTA's OWN range beyond its first tiles 1.38 ms -- bulk L2 prefetch only pays for bytes that
 // are on the critical path of a cold start.
-__device__ __noinline__ void prefetch_next_heads(const uint8_t* next, int nx_grid, int nx_rt_q, int nx_rt_r, int nx_head,
+static __device__ __noinline__ void prefetch_next_heads(const uint8_t* next, int nx_grid, int nx_rt_q, int nx_rt_r, int nx_head,
                                                  long long nx_tile_bytes, int lane)
 {
     for (int j = blockIdx.x; j < nx_grid; j += gridDim.x) {
@@ -681,7 +681,7 @@ gemv_mma_kernel(const __grid_constant__ typename std::conditional<CHAIN, MmaChai
     }
 }
 
-__global__ void probe_dyn_smem_base_kernel(uint32_t* out)
+static __global__ void probe_dyn_smem_base_kernel(uint32_t* out)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     out[0] = (uint32_t)__cvta_generic_to_shared(smem);

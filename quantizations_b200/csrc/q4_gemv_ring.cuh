@@ -1,5 +1,6 @@
 // q4_gemv_ring.cuh -- the batch-1 decode GEMV as a persistent, warp-specialised streaming kernel over up to four DEPENDENT
-// GEMVs ("stages": o_proj -> gate/up -> down_proj -> next layer's q/k/v), fp16 / bf16 activations, blocksize 64, K % 128 == 0.
+// GEMVs ("stages": o_proj -> gate/up -> down_proj -> next layer's q/k/v), fp16 / bf16 activations, blocksize 64, whole tiles only
+// (K % 512 == 0, rows % 32 == 0, grouped matrices end on 32-row boundaries; other shapes stay on q4_gemv_mma.cuh).
 //
 //   out[r] = sum_b absmax[r,b] * sum_{k in block b} x[k] * code[nib(r,k)]            (+ bias[r])
 //
@@ -54,7 +55,7 @@ constexpr int kSub = 4;                     // 8-row sub-tiles per ring slot
 constexpr int kSlotBytes = kSub * 2048;     // 32 rows x 256 packed bytes = two 128-byte-wide, 32-row TMA boxes (pair mode: four 16-row boxes)
 constexpr int kSlots = 16;                  // ring depth (a power of two: position / phase of a sequence number are a mask and a shift)
 constexpr int kProdLanes = 4;               // producer lanes issuing slots in lockstep
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;               // stages per launch (the argument struct must stay under the 4-KB parameter limit)
 constexpr int kConsumerBar = 1;             // named barrier of the consumer warps
 constexpr int kTraceSlots = 16;             // developer trace: globaltimer marks per (stage, CTA)
 // workspace layout (Q4_GEMV_RING_WS_BYTES, zeroed once by the caller, owned by one stream at a time)
@@ -85,6 +86,8 @@ struct Stage {
     int half;                // pair mode: rows of one member
     int x_tagged;            // the activation is the previous stage's tagged output (exchange buffer stage - 1), not x
     int publish;             // 0: out only; 1: out + tagged out; 2 (pair mode): out + tagged silu(gate) * up
+    int skip_out;            // a later stage of this launch overwrites the same `out` (in-place residual stream): only the tagged copy is stored
+    int d_rg, d_kt;          // consumer groups per launch configuration: NP / KT, NP % KT (plan_stage)
     int gran;                // slots per assignment quantum: 1 (a row group may be split between two CTAs) or KT (never split)
     int active, per, rem;    // CTA b < active owns quanta [b*per + min(b, rem), +per + (b < rem)); the others idle in this stage
     // fused one-shot all-reduce over tensor-parallel ranks (q4_allreduce_t), ar_world <= 1: off
@@ -104,13 +107,15 @@ struct Args {
 };
 
 // what a CTA needs to know about its share of a stage; computed once per launch (consumer warp `stage`), read by everybody
-struct Plan {
-    int S0, nloc;            // the CTA's range of the flat slot list: [S0, S0 + nloc)
-    int head;                // its first `head` slots belong to a row group that began in the previous CTA
-    int base_seq;            // ring sequence number of its first slot (slots taken in earlier stages)
-    int rg_own0, nrows_own;  // row groups it owns (= holds the first k tile of): [rg_own0, rg_own0 + nrows_own / 32)
-    int pad0, pad1;
-    unsigned short i0[16], rg[16], kt[16];  // per consumer warp group: local index, row group and k tile of its first slot
+struct Plan {                 // 48 bytes: eight of them have to fit beside the table, the ring and a 14336-element activation
+    int S0;                   // the CTA's range of the flat slot list: [S0, S0 + nloc)
+    int base_seq;             // ring sequence number of its first slot (slots taken in earlier stages)
+    unsigned short nloc;
+    unsigned short head;      // its first `head` slots belong to a row group that began in the previous CTA
+    unsigned short rg_own0;   // row groups it owns (= holds the first k tile of): [rg_own0, rg_own0 + nrows_own / 32)
+    unsigned short nrows_own;
+    unsigned short rg[8];     // per consumer warp group: row group, k tile and local index of its first slot
+    unsigned char kt[8], i0[8];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +149,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         if (ok) return;
         if (spin > (1u << 25)) __trap();
     }
+}
+// the common case -- the phase has completed -- is one probe and a branch; the bounded spin lives out of line
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
 {
@@ -295,7 +316,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
     constexpr int NP = NC / kWarpsPerSlot;  // slots in work at once: ring sequence number q goes to warp group q % NP
     constexpr int D = kSlots;
     static_assert(NC % kWarpsPerSlot == 0 && kSub % kWarpsPerSlot == 0, "warps per slot");
-    static_assert(NP <= 16 && D % NP == 0 && D % kProdLanes == 0 && (D & (D - 1)) == 0, "ring depth / consumer groups");
+    static_assert(NP <= 8 && D % NP == 0 && D % kProdLanes == 0 && (D & (D - 1)) == 0, "ring depth / consumer groups");
     constexpr int kSubPerWarp = kSub / kWarpsPerSlot;
     const uint32_t smem_saddr = smem_u32(smem);
     if (smem_saddr != kDynBase) __trap();
@@ -330,7 +351,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         s_misc[0] = 0;
         mark(0, 0);
     }
-    if (warp < c.n) {
+    if (warp < c.n) {  // kMaxStages <= consumer warps
         // ---- the plan of stage `warp` (all the integer divisions of the launch happen here, once, off the critical path)
         const Stage& a = c.st[warp];
         int base = 0;
@@ -345,20 +366,20 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         Plan& p = s_plan[warp];
         if (lane == 0) {
             p.S0 = S0;
-            p.nloc = nloc;
+            p.nloc = (unsigned short)nloc;
             p.base_seq = base;
-            p.head = (nloc > 0 && (S0 % KT) != 0) ? (KT - S0 % KT < nloc ? KT - S0 % KT : nloc) : 0;
+            p.head = (unsigned short)((nloc > 0 && (S0 % KT) != 0) ? (KT - S0 % KT < nloc ? KT - S0 % KT : nloc) : 0);
             const int rg_own0 = (S0 + KT - 1) / KT, rg_own1 = (S1 + KT - 1) / KT;
-            p.rg_own0 = rg_own0;
-            p.nrows_own = nloc > 0 ? (rg_own1 - rg_own0) * (kSub * 8) : 0;
+            p.rg_own0 = (unsigned short)rg_own0;
+            p.nrows_own = (unsigned short)(nloc > 0 ? (rg_own1 - rg_own0) * (kSub * 8) : 0);
         }
         if (lane < NP) {
             int i0 = lane - (base % NP);
             if (i0 < 0) i0 += NP;
             const int S = S0 + i0;
-            p.i0[lane] = (unsigned short)i0;
+            p.i0[lane] = (unsigned char)i0;
             p.rg[lane] = (unsigned short)(S / KT);
-            p.kt[lane] = (unsigned short)(S - (S / KT) * KT);
+            p.kt[lane] = (unsigned char)(S - (S / KT) * KT);
         }
     }
     __syncthreads();
@@ -384,7 +405,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             for (int s = 0; s < c.n; s++) {
                 const Stage& a = c.st[s];
                 const int S0 = s_plan[s].S0, n = s_plan[s].nloc, base = s_plan[s].base_seq;
-                const int KT = a.KT, half = a.K >> 1;
+                const int KT = a.KT;
                 if (lane == 0) {
                     asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map) : "memory");
                     mark(s, 6);
@@ -401,18 +422,15 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     const uint32_t ph = (uint32_t)(q / D) & 1u;
                     mbar_wait(empty(pos), ph ^ 1u);
                     const uint32_t dst = ring_saddr + (uint32_t)pos * kSlotBytes;
-                    const bool two = kt * 256 + 128 < half;  // a ragged last k tile may hold one box only
-                    mbar_expect_tx(full(pos), two ? kSlotBytes : kSlotBytes / 2);
+                    mbar_expect_tx(full(pos), kSlotBytes);
                     if (!pair) {
                         tma_load_2d(dst, &a.map, kt * 256, rg * 32, full(pos));
-                        if (two) tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 32, full(pos));
+                        tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 32, full(pos));
                     } else {  // 16 gate rows then the 16 up rows of the same indices, per 128-byte half
                         tma_load_2d(dst, &a.map, kt * 256, rg * 16, full(pos));
                         tma_load_2d(dst + kSlotBytes / 4, &a.map, kt * 256, hrows + rg * 16, full(pos));
-                        if (two) {
-                            tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 16, full(pos));
-                            tma_load_2d(dst + 3 * kSlotBytes / 4, &a.map, kt * 256 + 128, hrows + rg * 16, full(pos));
-                        }
+                        tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 16, full(pos));
+                        tma_load_2d(dst + 3 * kSlotBytes / 4, &a.map, kt * 256 + 128, hrows + rg * 16, full(pos));
                     }
                     i += kProdLanes;
                     rg += d_rg;
@@ -441,6 +459,8 @@ gemv_ring_kernel(const __grid_constant__ Args c)
     uint32_t epoch_base = 0;  // stages this CTA ran in earlier launches (workspace counter): read after griddepcontrol.wait
     uint2* const xch0 = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c.ws) + kWsXchOff);
 
+    // (Instantiating the stage body once per stage index -- every parameter a constant-bank operand at a fixed address -- was
+    // measured: 1 % faster with 16 x 2 warps, 30 % slower with the other layouts; the code no longer fits the instruction cache.)
     for (int stage = 0; stage < c.n; stage++) {
         const Stage& a = c.st[stage];
         const Plan& pl = s_plan[stage];
@@ -454,55 +474,49 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         // ---- the warp's slots: ring sequence numbers q = base_seq + i with q % NP == grp, i.e. local index i = i0, i0 + NP, ...
         // D is a multiple of NP: a ring position always belongs to the same warp group, which meets every fill of it in order -- a
         // parity wait can never alias an older phase.  Within a stage the group's k tile is constant whenever NP % KT == 0.
-        struct Cursor { int i, rg, kt; };
-        Cursor cur;
-        cur.i = pl.i0[grp];
-        cur.rg = pl.rg[grp];
-        cur.kt = pl.kt[grp];
-        const int d_rg = NP / KT, d_kt = NP - d_rg * KT;
-        auto advance = [&](Cursor& q) {
-            q.i += NP;
-            q.rg += d_rg;
-            q.kt += d_kt;
-            if (q.kt >= KT) {
-                q.kt -= KT;
-                q.rg++;
-            }
-        };
+        // Everything that moves from slot to slot is a running value advanced by per-stage constants (no multiplications, no
+        // parameter reads in the loop): the flat index i, its row group / k tile, and the index `sb` of the lane's absmax pair.
+        int ci = pl.i0[grp], crg = pl.rg[grp], ckt = pl.kt[grp];
+        int left = ci < nloc ? (nloc - ci + NP - 1) / NP : 0;  // slots this warp group still takes in this stage
+        const int d_rg = a.d_rg, d_kt = a.d_kt;                // NP / KT, NP % KT (host)
+        const int row_mul = a.pair ? kSub * 4 : kSub * 8;
+        // first row of the warp's first sub-tile relative to rg * row_mul (its sub-tiles are consecutive 8-row groups)
+        const int sub0 = wh * kSubPerWarp;
+        const int row_off = (a.pair ? ((sub0 >> 1) * a.half + (sub0 & 1) * 8) : sub0 * 8) + g;
+        int sb_sub[kSubPerWarp];  // absmax index of the warp's sub-tile q2 relative to its first one
+#pragma unroll
+        for (int q2 = 0; q2 < kSubPerWarp; q2++) {
+            const int sub = sub0 + q2;
+            sb_sub[q2] = ((a.pair ? ((sub >> 1) * a.half + (sub & 1) * 8) : sub * 8) + g - row_off) * bpr;
+        }
+        const int sb_step = d_rg * row_mul * bpr + d_kt * 8;        // ... between consecutive slots of the warp group
+        const int sb_wrap = row_mul * bpr - KT * 8;                 // ... extra when the k tile wraps into the next row group
+        int sb = (crg * row_mul + row_off) * bpr + ckt * 8 + 2 * t4;
         int pos;
         uint32_t ph;
         {
-            const int seq = pl.base_seq + cur.i;
+            const int seq = pl.base_seq + ci;
             pos = seq & (D - 1);
             ph = (uint32_t)(seq / D) & 1u;
         }
+        const uint8_t* const qabs = a.s.qabsmax;
+        const float* const am2 = NESTED ? a.s.absmax2 : a.s.absmax;
+        const int shift2 = a.s.shift2;
+        // grouped launch: the matrix (= offset) a row group belongs to; boundaries are whole row groups (host).  Pair mode: the
+        // warp's sub-tiles are all gate rows or all up rows.
+        const int mb0 = a.row_end[0] / (kSub * 8), mb1 = a.row_end[1] / (kSub * 8), mb2 = a.row_end[2] / (kSub * 8);
 
         // absmax of the lane's two blocks (2*t4, 2*t4+1 of row g of a sub-tile), fetched one slot ahead
         struct Stat { uint32_t q; float s0; };  // nested: two 8-bit codes + their second-level absmax; else the two fp32 absmax values
-        const int row_mul = a.pair ? kSub * 4 : kSub * 8;
-        int sub_off[kSubPerWarp];  // first row of the warp's sub-tiles relative to rg * row_mul
-#pragma unroll
-        for (int q2 = 0; q2 < kSubPerWarp; q2++) {
-            const int sub = wh * kSubPerWarp + q2;
-            sub_off[q2] = (a.pair ? ((sub >> 1) * a.half + (sub & 1) * 8) : sub * 8) + g;
-        }
-        const int re0 = a.row_end[0], re1 = a.row_end[1], re2 = a.row_end[2];
-        auto load_stat = [&](const Cursor& q, int q2) {
+        auto load_stat = [&](int sbi) {
             Stat r;
-            r.q = 0;
-            r.s0 = 0.0f;
-            const int row = q.rg * row_mul + sub_off[q2];
-            const int blk = q.kt * 8 + 2 * t4;
-            if (blk < bpr) {  // bpr is even: the pair is valid together
-                const int sb = (row < R ? row : R - 1) * bpr + blk;  // rows past the end read a valid row and are never stored
-                if (NESTED) {
-                    r.q = __ldg(reinterpret_cast<const unsigned short*>(a.s.qabsmax + sb));
-                    r.s0 = __ldg(a.s.absmax2 + (sb >> a.s.shift2));
-                } else {
-                    const float2 f2 = __ldg(reinterpret_cast<const float2*>(a.s.absmax + sb));
-                    r.q = __float_as_uint(f2.x);
-                    r.s0 = f2.y;
-                }
+            if (NESTED) {
+                r.q = __ldg(reinterpret_cast<const unsigned short*>(qabs + sbi));
+                r.s0 = __ldg(am2 + (sbi >> shift2));
+            } else {
+                const float2 f2 = __ldg(reinterpret_cast<const float2*>(am2 + sbi));
+                r.q = __float_as_uint(f2.x);
+                r.s0 = f2.y;
             }
             return r;
         };
@@ -511,7 +525,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         for (int q2 = 0; q2 < kSubPerWarp; q2++) {
             st_cur[q2].q = 0;
             st_cur[q2].s0 = 0.0f;
-            if (cur.i < nloc) st_cur[q2] = load_stat(cur, q2);  // statistics do not depend on the previous stage: before the exchange
+            if (left > 0) st_cur[q2] = load_stat(sb + sb_sub[q2]);  // statistics do not depend on the previous stage: before the exchange
         }
 
         // ---- everything below may read the previous kernel's (stage 0) or the previous stage's output
@@ -651,8 +665,8 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         };
         auto sub_addr = [&](int p, int q2) { return ring_saddr + (uint32_t)p * kSlotBytes + (uint32_t)((wh * kSubPerWarp + q2) * 1024); };
 
-        if (cur.i < nloc) {  // prologue: the first sub-tile's bytes and its first lookups
-            mbar_wait(full(pos), ph);
+        if (left > 0) {  // prologue: the first sub-tile's bytes and its first lookups
+            mbar_wait_fast(full(pos), ph);
             const uint32_t sa = sub_addr(pos, 0);
             load_lo(sa);
             load_hi(sa);
@@ -664,31 +678,38 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             for (int j = 0; j < kAhead; j++) fetch(f[j], j);
         }
 
-        while (cur.i < nloc) {
-            Cursor nxt = cur;
-            advance(nxt);
+        while (left > 0) {
+            // the warp group's next slot
+            int nrg = crg + d_rg, nkt = ckt + d_kt, nsb = sb + sb_step;
+            if (nkt >= KT) {
+                nkt -= KT;
+                nrg++;
+                nsb += sb_wrap;
+            }
             const int pos_n = (pos + NP) & (D - 1);
             const uint32_t ph_n = ph ^ (uint32_t)(pos + NP >= D);
-            const bool has_next = nxt.i < nloc;
+            const bool has_next = left > 1;
             Stat st_nxt[kSubPerWarp];
 #pragma unroll
             for (int q2 = 0; q2 < kSubPerWarp; q2++) {
                 st_nxt[q2].q = 0;
                 st_nxt[q2].s0 = 0.0f;
-                if (has_next) st_nxt[q2] = load_stat(nxt, q2);
+                if (has_next) st_nxt[q2] = load_stat(nsb + sb_sub[q2]);
             }
+            float o_slot = off[0];
+            if (MULTI && !a.pair) o_slot = crg < mb0 ? off[0] : (crg < mb1 ? off[1] : (crg < mb2 ? off[2] : off[3]));
 
-            if (cur.kt != kt_loaded) {  // warp-uniform; the lookups in flight do not depend on it
+            if (ckt != kt_loaded) {  // warp-uniform; the lookups in flight do not depend on it
                 if (xrole) {
                     // chunk i of block kt*8+g sits at piece i ^ g: byte offset (kt*1024 + g*128 + i*16) ^ (g*16)
-                    const uint32_t xb = x_saddr + (uint32_t)(cur.kt * 1024 + g * 128);
+                    const uint32_t xb = x_saddr + (uint32_t)(ckt * 1024 + g * 128);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const uint4 v = lds128((xb | (uint32_t)(i * 16)) ^ xswz);
                         xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
                     }
                 }
-                kt_loaded = cur.kt;
+                kt_loaded = ckt;
             }
 
 #pragma unroll
@@ -706,7 +727,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     for (int j = 0; j < 8; j++) acc ^= wa[j] ^ wb[j];
                     ce[0] = __uint_as_float(acc & 0x3fffffffu);
                     if (follows) {
-                        if (last_sub) mbar_wait(full(pos_n), ph_n);
+                        if (last_sub) mbar_wait_fast(full(pos_n), ph_n);
                         load_lo(sa_next);
                         load_hi(sa_next);
                         const bool rel = last_sub ? kSubPerWarp == 1 : q2 + 1 == kSubPerWarp - 1;
@@ -730,7 +751,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     else Hmma<T>::run(ce, a4[0], a4[1], a4[2], a4[3], xr[2 * j], xr[2 * j + 1]);
 #endif
                     if (j == 8 && follows) {  // words 0-3 are dead (last used by the lookups of MMA 7, issued at j == 4)
-                        if (last_sub) mbar_wait(full(pos_n), ph_n);
+                        if (last_sub) mbar_wait_fast(full(pos_n), ph_n);
                         load_lo(sa_next);
                     }
                     if (j == 12 && follows) {  // words 4-7 are dead (the lookups of MMA 15 were issued above)
@@ -751,15 +772,9 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 if (NESTED) {
                     const float q0 = __uint_as_float(lut_lookup<0, kImm + 128>(st_cur[q2].q, lane_base));
                     const float q1 = __uint_as_float(lut_lookup<1, kImm + 128>(st_cur[q2].q, lane_base));
-                    // (measured: carrying the offset in the prefetched statistics instead of selecting it here costs 16 %)
-                    float o = off[0];
-                    if (MULTI) {
-                        const int row = cur.rg * row_mul + sub_off[q2];
-                        o = row < re0 ? off[0] : (row < re1 ? off[1] : (row < re2 ? off[2] : off[3]));
-                    }
+                    const float o = (MULTI && a.pair) ? (((sub0 + q2) >> 1) ? off[1] : off[0]) : o_slot;  // pair mode: gate / up sub-tile
                     am0 = __fadd_rn(__fmul_rn(q0, st_cur[q2].s0), o);  // reference: kernels.cu:552 then core.py:468
                     am1 = __fadd_rn(__fmul_rn(q1, st_cur[q2].s0), o);
-                    if (cur.kt * 8 + 2 * t4 >= bpr) am0 = am1 = 0.0f;  // ragged k tile: blocks past the row's end
                 } else {
                     am0 = __uint_as_float(st_cur[q2].q);
                     am1 = st_cur[q2].s0;
@@ -767,10 +782,10 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 float part = fmaf(u0s, am0, u1s * am1);
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
-                if (t4 == 0) s_part[(cur.i * kSub + sub) * 8 + g] = part;
+                if (t4 == 0) s_part[(ci * kSub + sub) * 8 + g] = part;
             }
 
-            if (cur.i < head) {
+            if (ci < head) {
                 // this slot belongs to the row group shared with the previous CTA: the warp that completes the head piece publishes
                 // its 32 partial sums (fixed order over the k tiles) for the owner
                 __syncwarp();
@@ -789,7 +804,11 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 }
             }
 
-            cur = nxt;
+            ci += NP;
+            crg = nrg;
+            ckt = nkt;
+            sb = nsb;
+            left--;
 #pragma unroll
             for (int q2 = 0; q2 < kSubPerWarp; q2++) st_cur[q2] = st_nxt[q2];
             pos = pos_n;
@@ -898,7 +917,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     }
                     y = Elem<T>::from_f32(Elem<T>::to_f32(y) + bv);
                 }
-                if (valid) reinterpret_cast<T*>(a.out)[r] = y;
+                if (valid && !a.skip_out) reinterpret_cast<T*>(a.out)[r] = y;
                 if (a.publish) {
                     unsigned long long* dst = reinterpret_cast<unsigned long long*>(xch0) + (size_t)stage * (kXchMaxRows / 2);
                     const float yf = Elem<T>::to_f32(y);
@@ -1004,6 +1023,8 @@ inline void plan_stage(Stage& a, int rows, int K, int G, bool split_ok, int np =
     }
     a.per = (int)(Q / a.active);
     a.rem = (int)(Q % a.active);
+    a.d_rg = np / a.KT;
+    a.d_kt = np % a.KT;
 }
 
 // shared-memory plan of a launch: fills x_bytes / part_bytes, returns the dynamic shared-memory size (0: does not fit)

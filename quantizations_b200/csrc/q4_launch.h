@@ -30,6 +30,7 @@ int gemv_4bit_grouped(const void* x, const uint8_t* B, const q4_absmax_t* stats,
                       int flags, const void* next, int64_t next_bytes, cudaStream_t stream);
 int gemv_4bit_fused(const q4_gemv_fused_t* f, cudaStream_t stream);
 int gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, cudaStream_t stream);
+int gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
                     int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, void* workspace,
                     int64_t workspace_bytes, cudaStream_t stream);

@@ -1,0 +1,132 @@
+"""The persistent ring GEMV (q4_gemv_4bit_ring, csrc/q4_gemv_ring.cuh) against separate launches of the single-GEMV kernel on the
+same inputs: the decoder-layer chain at Llama-3-8B sizes (o + residual -> norm + gate/up -> SwiGLU + down + residual -> norm + q/k/v),
+plain chains, fp16 / non-nested statistics, CUDA-graph replay, and the refusals that make callers fall back.
+
+Reference path replaced: core.py:467-499 (three launches per Linear) x the layer's Linears, modules.py:124-151."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+TDT = {"bfloat16": torch.bfloat16, "float16": torch.float16}
+
+
+@pytest.fixture(scope="module")
+def q():
+    import quantizations_b200 as q
+
+    return q
+
+
+def _close(a, b, tol=1e-2):
+    a, b = a.float(), b.float()
+    return (a - b).abs().max().item() <= tol * max(b.abs().max().item(), 1e-6)
+
+
+def _ring_launch(q, stages):
+    """stages: list of GemvFused structs (already chained through their pointers); returns the ABI's return code"""
+    L = q._lib.lib()
+    ws = q.core.ring_workspace(DEV)
+    arr = (q._lib.GemvFused * len(stages))(*stages)
+    return L.q4_gemv_4bit_ring(arr, len(stages), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+@pytest.mark.parametrize("compress", [True, False])
+def test_ring_decoder_layer_chain_matches_separate_launches(q, dtype, compress):
+    """Llama-3-8B sizes.  The ring kernel splits rows across CTAs along K and sums the per-(row, k tile) partials in k order, the
+    arithmetic of the single-launch kernel: results must agree to the GEMV tolerance (they are in fact expected bit-identical)."""
+    torch.manual_seed(5)
+    dt = TDT[dtype]
+    H, I, KV = 4096, 14336, 1024
+    mk = lambda n, k: q.Linear4bit(k, n, bias=False, compute_dtype=dt, compress_statistics=compress, quant_type="nf4").to(DEV)
+    o, gate, up, down, qp, kp, vp = mk(H, H), mk(I, H), mk(I, H), mk(H, I), mk(H, H), mk(KV, H), mk(KV, H)
+    gu, qkv = q.Linear4bitGroup([gate, up]), q.Linear4bitGroup([qp, kp, vp])
+    ln2 = (1 + 0.1 * torch.randn(H, device=DEV)).to(dt)
+    ln1 = (1 + 0.1 * torch.randn(H, device=DEV)).to(dt)
+    a = torch.randn(1, 1, H, device=DEV, dtype=dt)
+    h0 = torch.randn(1, 1, H, device=DEV, dtype=dt)
+
+    h = h0.clone()
+    q.gemv_4bit_fused(a, o.weight.data, o.weight.quant_state, residual=h, out=h)
+    g_ref = q.gemv_4bit_fused(h, None, group=gu, rms_weight=ln2)
+    q.gemv_4bit_fused(g_ref[..., I:], down.weight.data, down.weight.quant_state, gate=g_ref[..., :I], residual=h, out=h)
+    h_ref, qkv_ref = h, q.gemv_4bit_fused(h, None, group=qkv, rms_weight=ln1)
+
+    h = h0.clone()
+    g_u = torch.empty(1, 1, 2 * I, device=DEV, dtype=dt)
+    out_qkv = torch.empty(1, 1, H + 2 * KV, device=DEV, dtype=dt)
+    stages = []
+    q.gemv_4bit_fused(a, o.weight.data, o.weight.quant_state, residual=h, out=h, _defer=stages)
+    q.gemv_4bit_fused(h, None, group=gu, rms_weight=ln2, out=g_u, _defer=stages)
+    q.gemv_4bit_fused(g_u[..., I:], down.weight.data, down.weight.quant_state, gate=g_u[..., :I], residual=h, out=h, _defer=stages)
+    q.gemv_4bit_fused(h, None, group=qkv, rms_weight=ln1, out=out_qkv, _defer=stages)
+    n0 = q._lib.launch_count()
+    for rep in range(3):  # the epochs of the exchange advance from call to call
+        h.copy_(h0)
+        g_u.fill_(float("nan"))
+        out_qkv.fill_(float("nan"))
+        rc = _ring_launch(q, [f for f, _ in stages])
+        assert rc == 0, q._lib.lib().q4_error_string(rc)
+        torch.cuda.synchronize()
+        assert _close(g_u, g_ref) and _close(h, h_ref) and _close(out_qkv, qkv_ref)
+    assert q._lib.launch_count() - n0 == 3
+    exact = torch.equal(g_u, g_ref) and torch.equal(h, h_ref) and torch.equal(out_qkv, qkv_ref)
+    print("ring vs single-launch kernel bit-identical:", exact)
+
+
+def test_ring_plain_chain_and_eight_stages(q):
+    """Eight plainly chained stages (x of stage i+1 = the first K outputs of stage i), weights scaled so that magnitudes stay O(1)."""
+    torch.manual_seed(9)
+    dt = torch.bfloat16
+    shapes = [(6144, 4096), (4096, 4096), (8192, 4096), (4096, 8192), (4096, 4096), (2048, 4096), (1024, 2048), (512, 1024)]
+    lins = []
+    for n, k in shapes:
+        lin = q.Linear4bit(k, n, bias=False, compute_dtype=dt, quant_type="nf4", device="meta")
+        W = (torch.randn(n, k, device=DEV) / k ** 0.5).to(dt)
+        lin.weight = q.Params4bit(W, requires_grad=False, quant_type="nf4", module=lin).to(DEV)
+        lins.append(lin)
+    x0 = torch.randn(1, 1, 4096, device=DEV, dtype=dt)
+    ref, x = [], x0
+    for lin, (n, k) in zip(lins, shapes):
+        y = q.gemv_4bit(x[..., :k].contiguous(), lin.weight.data, state=lin.weight.quant_state)
+        ref.append(y)
+        x = y
+    outs = [torch.full((1, 1, n), float("nan"), device=DEV, dtype=dt) for n, _ in shapes]
+    stages, x = [], x0
+    for lin, (n, k), out in zip(lins, shapes, outs):
+        q.gemv_4bit_fused(x[..., :k] if x is not x0 else x, lin.weight.data, lin.weight.quant_state, out=out, _defer=stages)
+        x = out
+    rc = _ring_launch(q, [f for f, _ in stages])
+    assert rc == 0, q._lib.lib().q4_error_string(rc)
+    torch.cuda.synchronize()
+    for i, (y, r) in enumerate(zip(outs, ref)):
+        assert _close(y, r), f"stage {i}"
+
+
+def test_ring_refuses_what_it_does_not_support(q):
+    """Ragged shapes, a later stage reading an earlier out in an unsupported way, too many stages: Q4_ERR_SHAPE and nothing
+    launched -- the Python chain then falls back to the older launches with the same results."""
+    dt = torch.bfloat16
+    torch.manual_seed(2)
+    mk = lambda n, k: q.Linear4bit(k, n, bias=False, compute_dtype=dt, quant_type="nf4").to(DEV)
+    x = torch.randn(1, 1, 1024, device=DEV, dtype=dt)
+    a, c, d = mk(1000, 1024), mk(1024, 1024), mk(512, 1024)  # a: rows % 32 != 0
+    q.core.ring_workspace(DEV)
+    n0 = q._lib.launch_count()
+    st = []
+    q.gemv_4bit_fused(x, a.weight.data, a.weight.quant_state, _defer=st)
+    assert _ring_launch(q, [f for f, _ in st]) == q._lib.Q4_ERR_SHAPE
+    st = []
+    y1 = q.gemv_4bit_fused(x, c.weight.data, c.weight.quant_state, _defer=st)
+    q.gemv_4bit_fused(x, d.weight.data, d.weight.quant_state, _defer=st)
+    q.gemv_4bit_fused(y1, d.weight.data, d.weight.quant_state, _defer=st)  # reads stage 0's out, but is not its successor
+    assert _ring_launch(q, [f for f, _ in st]) == q._lib.Q4_ERR_SHAPE
+    assert q._lib.launch_count() == n0
+    # the context manager hides the difference
+    with q.gemv_4bit_chain() as ch:
+        y = ch.add(x, a.weight.data, a.weight.quant_state)
+    assert _close(y, q.gemv_4bit(x, a.weight.data, state=a.weight.quant_state), 0.0) or torch.equal(y, q.gemv_4bit(x, a.weight.data, state=a.weight.quant_state))
