@@ -811,6 +811,13 @@ class gemv_4bit_chain:
                         continue
                     if rc not in (_lib.Q4_ERR_SHAPE, _lib.Q4_ERR_ALIGN):
                         check(rc, "gemv_4bit_ring")
+                if not _USE_OLD_CHAIN:  # measured: single launches under programmatic dependent launch beat the older chained kernel
+                    f = stages[i][0]
+                    rc = lib.q4_gemv_4bit_fused(ctypes.byref(f), stream.cuda_stream)
+                    if rc:
+                        check(rc, "gemv_4bit_fused")
+                    i += 1
+                    continue
                 part = stages[i:i + 4]
                 key = (dev.index, stream.cuda_stream)
                 bar = _chain_barriers.get(key)
@@ -824,6 +831,7 @@ class gemv_4bit_chain:
 
 
 _USE_RING = os.environ.get("Q4_GEMV_RING", "1") != "0"
+_USE_OLD_CHAIN = os.environ.get("Q4_GEMV_OLD_CHAIN", "0") == "1"  # fall back to q4_gemv_4bit_chain instead of single launches
 _ring_workspaces = {}
 
 

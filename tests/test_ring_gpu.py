@@ -130,3 +130,24 @@ def test_ring_refuses_what_it_does_not_support(q):
     with q.gemv_4bit_chain() as ch:
         y = ch.add(x, a.weight.data, a.weight.quant_state)
     assert _close(y, q.gemv_4bit(x, a.weight.data, state=a.weight.quant_state), 0.0) or torch.equal(y, q.gemv_4bit(x, a.weight.data, state=a.weight.quant_state))
+
+
+def test_older_chained_launch_still_matches_through_the_abi(q):
+    """q4_gemv_4bit_chain (grid-barrier kernel) is no longer what gemv_4bit_chain() issues -- the ring kernel took over, single
+    launches are the fallback -- but the export stays: called directly it must still equal the separate launches bit for bit."""
+    torch.manual_seed(4)
+    dt = torch.bfloat16
+    mk = lambda n, k: q.Linear4bit(k, n, bias=False, compute_dtype=dt, quant_type="nf4").to(DEV)
+    a, b = mk(1024, 1024), mk(512, 1024)
+    x = torch.randn(1, 1, 1024, device=DEV, dtype=dt)
+    y1 = q.gemv_4bit(x, a.weight.data, state=a.weight.quant_state)
+    y2 = q.gemv_4bit(y1, b.weight.data, state=b.weight.quant_state)
+    st = []
+    o1 = q.gemv_4bit_fused(x, a.weight.data, a.weight.quant_state, _defer=st)
+    o2 = q.gemv_4bit_fused(o1, b.weight.data, b.weight.quant_state, _defer=st)
+    bar = torch.zeros(64, dtype=torch.int32, device=DEV)
+    arr = (q._lib.GemvFused * 2)(*[f for f, _ in st])
+    rc = q._lib.lib().q4_gemv_4bit_chain(arr, 2, bar.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(o1, y1) and torch.equal(o2, y2) and int(bar.abs().sum()) == 0
