@@ -334,7 +334,8 @@ def run_ours(args, rank, world, device):
 
     use_chain = args.chain and args.group and not side and (comm is None or fused_ar is not None) and len(units) % 4 == 0
     # the persistent ring kernel (q4_gemv_4bit_ring): up to eight dependent GEMVs (two decoder layers) per launch
-    use_ring = args.ring and not use_chain and args.group and not side and comm is None
+    # (tensor-parallel: measured slower than single launches at tp2 -- 1.03 vs 0.94 ms/step -- so there it is opt-in: --ring-tp)
+    use_ring = args.ring and not use_chain and args.group and not side and (comm is None or (fused_ar is not None and args.ring_tp))
     ring_arrays = []
     ring_state = {"launches": 0, "fallbacks": 0}
 
@@ -377,6 +378,21 @@ def run_ours(args, rank, world, device):
     step_cabi()
     launches_per_step = _lib.launch_count() - n0
     torch.cuda.synchronize()
+    ring_check = None
+    if use_ring and ring_state["fallbacks"] == 0:
+        # the ring launches against one single-GEMV launch per stage on the same data flow (all ranks, before anything is timed)
+        got = {k: v.clone() for k, v in outs.items()}
+        run_stack(launch_cabi)
+        torch.cuda.synchronize()
+        worst = 0.0
+        for k, v in outs.items():
+            ref = v.float()
+            worst = max(worst, ((got[k].float() - ref).abs().max() / ref.abs().max().clamp_min(1e-20)).item())
+        # the two paths round identically per tile, but a cut row group adds its pieces in a different association: over 128 DEPENDENT
+        # stages single bf16 rounding flips propagate, so the bound here is loose -- the per-stage checks are tests/test_ring_gpu.py
+        if not worst <= 6e-2:
+            raise RuntimeError(f"ring_check: the ring kernel's step differs from the single-launch step by {worst} (rank {rank})")
+        ring_check = {"status": "ok", "max_rel_err_vs_single_launches": worst, "stages": len(units)}
     graph = None
     if not args.no_graph:
         graph = graphs.capture(step_cabi)
@@ -446,7 +462,8 @@ def run_ours(args, rank, world, device):
                 if isinstance(m, q.Linear4bitGroup):
                     ch.add(x, None, group=m, out=out)
                 else:
-                    ch.add(x, m.weight.data, m.weight.quant_state, out=out)
+                    kw = {"allreduce": fused_ar} if (fused_ar is not None and m.parallel == "row") else {}
+                    ch.add(x, m.weight.data, m.weight.quant_state, out=out, **kw)
 
     step_api()
     torch.cuda.synchronize()
@@ -536,6 +553,8 @@ def run_ours(args, rank, world, device):
     }
     if tp_check is not None:
         res["tp_check"] = tp_check
+    if ring_check is not None:
+        res["ring_check"] = ring_check
     if world == 1 and not args.no_blockwise:
         res["blockwise"] = blockwise_rates(device, peak)
     if world == 1 and not args.no_sweep:
@@ -680,6 +699,8 @@ def decode_tok_s(args, device, impl, rank=0, world=1):
             from quantizations_b200 import tp as tpmod
 
             model.fused_ar = None if args.nccl_allreduce else tpmod.FusedAllReduce(cfg.hidden, device=device)
+            if model.fused_ar is not None and getattr(args, "ring", True) and getattr(args, "ring_tp", False) and cfg.inter // world <= 16384:
+                model.chain = True  # the all-reduces run in the epilogues of the ring kernel's row-parallel stages
         elif (getattr(args, "ring", True) and cfg.inter <= 16384) or getattr(args, "chain", False):
             model.chain = True  # o -> gate/up -> down -> next q/k/v as one persistent launch per layer (ring kernel, else the older chain)
         ctx, graph = torch.cuda.stream(torch.cuda.Stream(device=device)), True
@@ -888,6 +909,7 @@ def main():
     ap.add_argument("--no-ring", dest="ring", action="store_false",
                     help="single GPU: one launch per (grouped) Linear (q4_gemv_4bit_fused) instead of the persistent ring kernel "
                          "(q4_gemv_4bit_ring: eight dependent GEMVs per launch, weights streamed through a TMA ring across stage boundaries)")
+    ap.add_argument("--ring-tp", action="store_true", help="tensor-parallel runs: the ring kernel with the all-reduce in its row-parallel stages' epilogues")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="tensor-parallel runs: NCCL all-reduce after the row-parallel GEMVs (the baseline) instead of the fused epilogue exchange")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",

@@ -210,7 +210,9 @@ int q4_gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, v
  *     the gate/up epilogue then publishes silu(gate) * up itself (stage i's out is still written in full);
  *   - a stage's bias may be memory the PREVIOUS kernel wrote, or exactly the out of an earlier stage (the residual stream);
  *   - stage 0's x / x_gate, and any stage's rms_weight, are memory the previous kernel wrote.
- * Any other aliasing between stages, tensor-parallel stages, ragged shapes (K % 512, rows % 32, grouped members not ending on
+ * Row-parallel stages may carry q4_allreduce_t: the sum over the tensor-parallel ranks then runs in the stage's epilogue, before bias
+ * and before the outputs are handed to the next stage.
+ * Any other aliasing between stages, ragged shapes (K % 256, rows % 32, grouped members not ending on
  * 32-row boundaries), K > 16384, a missing table image or mixed types return Q4_ERR_SHAPE / Q4_ERR_ALIGN WITHOUT launching: the caller
  * falls back to q4_gemv_4bit_chain / q4_gemv_4bit_fused.  Results agree with those within the GEMV tolerance (same per-tile
  * arithmetic, same fixed summation order over k tiles).  `workspace`: Q4_GEMV_RING_WS_BYTES of 16-byte aligned device memory, zeroed

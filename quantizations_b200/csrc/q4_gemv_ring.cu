@@ -122,8 +122,7 @@ int gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_
         ring::Stage& st = c.st[i];
         if (!f.x || !f.B || !f.out || !f.stats || !f.code) return Q4_ERR_NULL;
         if (f.dtype != f0.dtype || f.lut != f0.lut || (f.stats->qabsmax != nullptr) != nested) return Q4_ERR_SHAPE;  // one table image = one (code, code2, dtype)
-        if (f.blocksize != 64 || f.rows <= 0 || f.K <= 0 || (f.K % 512) != 0 || (f.rows % 32) != 0 || f.K > 16384 || f.rows > (1 << 20)) return Q4_ERR_SHAPE;
-        if (f.allreduce && f.allreduce->world > 1) return Q4_ERR_SHAPE;  // tensor-parallel stages stay on the single-launch kernel
+        if (f.blocksize != 64 || f.rows <= 0 || f.K <= 0 || (f.K % 256) != 0 || (f.rows % 32) != 0 || f.K > 16384 || f.rows > (1 << 20)) return Q4_ERR_SHAPE;
         if (f.flags & (Q4_GEMV_SWIGLU | Q4_GEMV_EXACT_F32)) return Q4_ERR_SHAPE;
         if (nested) {
             if (!f.stats->code2 || !f.stats->absmax2 || f.stats->blocksize2 < 128 ||
@@ -202,6 +201,17 @@ int gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_
         }
         st.rows = (int)f.rows;
         st.K = (int)f.K;
+        // ---- tensor-parallel row-parallel stage: the all-reduce over the ranks runs in the epilogue (q4_allreduce_t), before bias /
+        //      residual and before the outputs are published to the next stage
+        if (f.allreduce && f.allreduce->world > 1) {
+            const q4_allreduce_t* ar = f.allreduce;
+            if (!ar->peer_bases) return Q4_ERR_NULL;
+            if (ar->world > kArMaxWorld || ar->rank < 0 || ar->rank >= ar->world || f.rows != ar->max_rows || G > kArMaxCtas || nmat > 1) return Q4_ERR_SHAPE;
+            st.ar_peer_bases = ar->peer_bases;
+            st.ar_world = ar->world;
+            st.ar_rank = ar->rank;
+            st.ar_max_rows = ar->max_rows;
+        }
     }
     // publishing stages need their tagged copy even when only a later bias reads it
     for (int i = 0; i < n; i++)

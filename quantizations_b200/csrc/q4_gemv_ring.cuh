@@ -1,6 +1,6 @@
 // q4_gemv_ring.cuh -- the batch-1 decode GEMV as a persistent, warp-specialised streaming kernel over up to four DEPENDENT
 // GEMVs ("stages": o_proj -> gate/up -> down_proj -> next layer's q/k/v), fp16 / bf16 activations, blocksize 64, whole tiles only
-// (K % 512 == 0, rows % 32 == 0, grouped matrices end on 32-row boundaries; other shapes stay on q4_gemv_mma.cuh).
+// (K % 256 == 0, rows % 32 == 0, grouped matrices end on 32-row boundaries; other shapes stay on q4_gemv_mma.cuh).
 //
 //   out[r] = sum_b absmax[r,b] * sum_{k in block b} x[k] * code[nib(r,k)]            (+ bias[r])
 //
@@ -405,7 +405,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             for (int s = 0; s < c.n; s++) {
                 const Stage& a = c.st[s];
                 const int S0 = s_plan[s].S0, n = s_plan[s].nloc, base = s_plan[s].base_seq;
-                const int KT = a.KT;
+                const int KT = a.KT, halfK = a.K >> 1;
                 if (lane == 0) {
                     asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map) : "memory");
                     mark(s, 6);
@@ -422,15 +422,20 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     const uint32_t ph = (uint32_t)(q / D) & 1u;
                     mbar_wait(empty(pos), ph ^ 1u);
                     const uint32_t dst = ring_saddr + (uint32_t)pos * kSlotBytes;
-                    mbar_expect_tx(full(pos), kSlotBytes);
+                    // K % 512 == 256 (tensor-parallel shards): the last k tile holds one 128-byte box only; the other half of the slot
+                    // keeps stale bytes, which meet zero activations (the staging pads x with zeros up to whole tiles)
+                    const bool two = kt * 256 + 128 < halfK;
+                    mbar_expect_tx(full(pos), two ? kSlotBytes : kSlotBytes / 2);
                     if (!pair) {
                         tma_load_2d(dst, &a.map, kt * 256, rg * 32, full(pos));
-                        tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 32, full(pos));
+                        if (two) tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 32, full(pos));
                     } else {  // 16 gate rows then the 16 up rows of the same indices, per 128-byte half
                         tma_load_2d(dst, &a.map, kt * 256, rg * 16, full(pos));
                         tma_load_2d(dst + kSlotBytes / 4, &a.map, kt * 256, hrows + rg * 16, full(pos));
-                        tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 16, full(pos));
-                        tma_load_2d(dst + 3 * kSlotBytes / 4, &a.map, kt * 256 + 128, hrows + rg * 16, full(pos));
+                        if (two) {
+                            tma_load_2d(dst + kSlotBytes / 2, &a.map, kt * 256 + 128, rg * 16, full(pos));
+                            tma_load_2d(dst + 3 * kSlotBytes / 4, &a.map, kt * 256 + 128, hrows + rg * 16, full(pos));
+                        }
                     }
                     i += kProdLanes;
                     rg += d_rg;
@@ -508,8 +513,10 @@ gemv_ring_kernel(const __grid_constant__ Args c)
 
         // absmax of the lane's two blocks (2*t4, 2*t4+1 of row g of a sub-tile), fetched one slot ahead
         struct Stat { uint32_t q; float s0; };  // nested: two 8-bit codes + their second-level absmax; else the two fp32 absmax values
-        auto load_stat = [&](int sbi) {
+        const int sb_max = R * bpr - 2;  // a ragged last k tile asks for block pairs past its row's end: they meet zero activations, but
+        auto load_stat = [&](int sbi) {  // the index must stay inside the array
             Stat r;
+            sbi = sbi < sb_max ? sbi : sb_max;
             if (NESTED) {
                 r.q = __ldg(reinterpret_cast<const unsigned short*>(qabs + sbi));
                 r.s0 = __ldg(am2 + (sbi >> shift2));

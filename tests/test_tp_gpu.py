@@ -59,6 +59,62 @@ def _worker(rank, world, port, ret):
         gathered = [torch.empty_like(out) for _ in range(world)]
         dist.all_gather(gathered, out)
         assert all(torch.equal(gathered[0], t) for t in gathered)
+        # ---- the same exchange inside the persistent ring kernel: a tensor-parallel decoder-layer chain (row-parallel o_proj and
+        #      down_proj shards with the all-reduce in their epilogues, column-parallel gate/up shard with SwiGLU in pair mode) in ONE
+        #      launch against the same stages as single launches, repeated and replayed
+        I2 = inter // world
+        mk = lambda n, k, seed: q.Linear4bit(k, n, bias=False, compute_dtype=torch.bfloat16, quant_type="nf4", device="meta")
+        def shard_lin(N, K, kind, seed):
+            gg = torch.Generator(device=dev).manual_seed(seed)
+            W = (torch.randn(N, K, device=dev, generator=gg) * K ** -0.5).to(torch.bfloat16)
+            sh = tp.shard_weight(W, kind, rank, world)
+            lin = mk(sh.shape[0], sh.shape[1], seed)
+            lin.weight = q.Params4bit(sh, requires_grad=False, quant_type="nf4", module=lin).to(dev)
+            return lin
+        o_l, gate_l, up_l, down_l = shard_lin(hidden, hidden, "row", 31), shard_lin(inter, hidden, "col", 32), shard_lin(inter, hidden, "col", 33), shard_lin(hidden, inter, "row", 34)
+        gu = q.Linear4bitGroup([gate_l, up_l])
+        ln2 = (1 + 0.1 * torch.randn(hidden, device=dev, generator=torch.Generator(device=dev).manual_seed(5))).to(torch.bfloat16)
+        a_in = torch.randn(1, 1, hidden // world, device=dev, dtype=torch.bfloat16, generator=torch.Generator(device=dev).manual_seed(50 + rank))
+        h0 = torch.randn(1, 1, hidden, device=dev, dtype=torch.bfloat16, generator=torch.Generator(device=dev).manual_seed(51))
+
+        h = h0.clone()
+        q.gemv_4bit_fused(a_in, o_l.weight.data, o_l.weight.quant_state, residual=h, out=h, allreduce=ar)
+        g_ref = q.gemv_4bit_fused(h, None, group=gu, rms_weight=ln2)
+        q.gemv_4bit_fused(g_ref[..., I2:], down_l.weight.data, down_l.weight.quant_state, gate=g_ref[..., :I2], residual=h, out=h, allreduce=ar)
+        h_ref = h.clone()
+
+        h = h0.clone()
+        g_u = torch.empty(1, 1, 2 * I2, device=dev, dtype=torch.bfloat16)
+
+        def ring_chain():
+            st = []
+            q.gemv_4bit_fused(a_in, o_l.weight.data, o_l.weight.quant_state, residual=h, out=h, allreduce=ar, _defer=st)
+            q.gemv_4bit_fused(h, None, group=gu, rms_weight=ln2, out=g_u, _defer=st)
+            q.gemv_4bit_fused(g_u[..., I2:], down_l.weight.data, down_l.weight.quant_state, gate=g_u[..., :I2], residual=h, out=h, allreduce=ar, _defer=st)
+            ws = q.core.ring_workspace(dev)
+            arr = (q._lib.GemvFused * len(st))(*[f for f, _ in st])
+            rc = q._lib.lib().q4_gemv_4bit_ring(arr, len(st), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, rc
+            return st
+
+        for rep in range(3):
+            h.copy_(h0)
+            keep = ring_chain()
+            torch.cuda.synchronize()
+            err = ((h.float() - h_ref.float()).abs().max() / h_ref.float().abs().max()).item()
+            assert err <= 1e-2, ("ring tp chain", rep, err)
+            assert ((g_u.float() - g_ref.float()).abs().max() / g_ref.float().abs().max()).item() <= 1e-2
+        gathered = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(gathered, h)
+        assert all(torch.equal(gathered[0], t) for t in gathered), "ring: ranks hold different bits"
+        h.copy_(h0)
+        gr = graphs.capture(ring_chain)
+        for _ in range(3):
+            h.copy_(h0)
+            gr.replay()
+            torch.cuda.synchronize()
+            err = ((h.float() - h_ref.float()).abs().max() / h_ref.float().abs().max()).item()
+            assert err <= 1e-2, ("ring tp chain replay", err)
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback
