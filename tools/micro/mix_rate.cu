@@ -21,7 +21,7 @@ template <int SEL> __device__ __forceinline__ uint32_t lookup(uint32_t w, uint32
 }
 
 // MODE bit 0: 4 x LDS.128 per sub-tile (packed bytes from a 2-KB shared-memory tile); bit 1: no HMMA (xor instead); bit 2: no lookups
-template <int MODE, int AHEAD>
+template <int MODE, int AHEAD, int U = 1>
 __global__ void __launch_bounds__(512) k(unsigned* out, long long* cyc, int subtiles, unsigned seed)
 {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(512) k(unsigned* out, long long* cyc, int subt
     for (int j = 0; j < AHEAD; j++) fetch(f[j], j);
     float acc = 0.0f;
     const long long t0 = clock64();
-    for (int s = 0; s < subtiles; s++) {
+    for (int s0 = 0; s0 < subtiles; s0 += U) {
+#pragma unroll
+      for (int us = 0; us < U; us++) {
+        const int s = s0 + us;
         float ce[4] = {0, 0, 0, 0}, co[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(512) k(unsigned* out, long long* cyc, int subt
             }
         }
         acc += ce[0] + co[0] + ce[1] + co[1] + ce[2] + co[2] + ce[3] + co[3];
+      }
     }
     const long long t1 = clock64();
     uint32_t r = __float_as_uint(acc);
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(512) k(unsigned* out, long long* cyc, int subt
     if (tid == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-template <int MODE, int AHEAD>
+template <int MODE, int AHEAD, int U = 1>
 static int run(const char* name, int threads)
 {
     unsigned* out;
@@ -97,10 +101,10 @@ static int run(const char* name, int threads)
     CK(cudaMalloc(&out, 148 * 512 * 4));
     CK(cudaMalloc(&cyc, 148 * 8));
     const int smem = 65536 + 16 * 2048;
-    CK(cudaFuncSetAttribute(k<MODE, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k<MODE, AHEAD, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int subtiles = 400;
-    k<MODE, AHEAD><<<148, threads, smem>>>(out, cyc, subtiles, 1);
-    k<MODE, AHEAD><<<148, threads, smem>>>(out, cyc, subtiles, 2);
+    k<MODE, AHEAD, U><<<148, threads, smem>>>(out, cyc, subtiles, 1);
+    k<MODE, AHEAD, U><<<148, threads, smem>>>(out, cyc, subtiles, 2);
     CK(cudaDeviceSynchronize());
     long long h[148];
     CK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
@@ -117,7 +121,12 @@ static int run(const char* name, int threads)
 
 int main()
 {
-    for (int threads : {256, 512}) {
+    run<1, 3, 1>("lookups + HMMA + packed, body x1 (~2.5 KB)", 512);
+    run<1, 3, 2>("lookups + HMMA + packed, body x2 (~5 KB)", 512);
+    run<1, 3, 4>("lookups + HMMA + packed, body x4 (~10 KB)", 512);
+    run<1, 3, 8>("lookups + HMMA + packed, body x8 (~20 KB)", 512);
+    run<1, 3, 16>("lookups + HMMA + packed, body x16 (~40 KB)", 512);
+    for (int threads : {512}) {
         run<0, 3>("lookups + HMMA", threads);
         run<1, 3>("lookups + HMMA + packed LDS.128", threads);
         run<3, 3>("lookups + packed LDS.128, no HMMA", threads);
