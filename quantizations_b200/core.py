@@ -157,6 +157,13 @@ class QuantState:
         self._stats = None  # cached C struct of pointers (see native_stats)
         self._luts = {}     # decode-GEMV table image per activation dtype (see gemv_lut)
 
+    def __getstate__(self):
+        """copy / pickle: the tensors travel, the caches (C struct of raw pointers, table images) are rebuilt on first use"""
+        state = self.__dict__.copy()
+        state["_stats"] = None
+        state["_luts"] = {}
+        return state
+
     def to(self, device):
         """Move the statistics to `device` (reference core.py:78-88; also handles a non-nested state)."""
         self.absmax = self.absmax.to(device)
@@ -318,6 +325,43 @@ class Params4bit(torch.nn.Parameter):
             module.quant_state = self.quant_state
         return self
 
+    # ---- copying / pickling keep the quantisation state (upstream bitsandbytes semantics; the reference has neither: a deepcopy or
+    # pickle of its parameter silently drops quant_state and re-quantises nothing) ------------------------------------------------
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["data"] = self.data
+        state["requires_grad"] = self.requires_grad
+        state["module"] = None  # the owning module is re-attached by whoever rebuilds it
+        return state
+
+    def __setstate__(self, state):
+        self.requires_grad = state["requires_grad"]
+        self.blocksize = state["blocksize"]
+        self.compress_statistics = state["compress_statistics"]
+        self.quant_type = state["quant_type"]
+        self.quant_state = state["quant_state"]
+        self.data = state["data"]
+        self.quant_storage = state["quant_storage"]
+        self.bnb_quantized = state["bnb_quantized"]
+        self.module = state.get("module")
+
+    def __reduce_ex__(self, proto):
+        return (_rebuild_params4bit, (self.__getstate__(),))
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        state = self.__getstate__()
+        state["data"] = copy.deepcopy(state["data"], memo)
+        state["quant_state"] = copy.deepcopy(state["quant_state"], memo)
+        new = _rebuild_params4bit(state)
+        new.module = memo.get(id(self.module)) if self.module is not None else None
+        return new
+
+    def __copy__(self):
+        return _rebuild_params4bit(self.__getstate__())
+
     def _quantize(self, device):
         """reference core.py:139-161"""
         w = self.data.contiguous().cuda(device)
@@ -358,6 +402,12 @@ class Params4bit(torch.nn.Parameter):
             compress_statistics=self.compress_statistics,
         )
         return new_param
+
+
+def _rebuild_params4bit(state: dict) -> "Params4bit":
+    p = Tensor._make_subclass(Params4bit, state["data"], state["requires_grad"])
+    p.__setstate__(state)
+    return p
 
 
 def get_4bit_type(typename, device=None, blocksize=64):

@@ -417,7 +417,15 @@ static int gemv_dispatch(const T* x, const uint8_t* B, const q4_absmax_t* st, co
                     a.nx_tile_bytes = 4 * nK;  // 8 rows x K/2 bytes
                 }
             }
-            if (a.ar_world > 1 && grid > kArMaxCtas) return Q4_ERR_SHAPE;
+            if (a.ar_world > 1) {
+                // The fused all-reduce addresses a peer's slots by ROW and tags them with per-CTA epochs: every launch that shares an
+                // exchange area must map rows to CTAs identically on all ranks, launch after launch.  That holds when the grid follows
+                // from the row count alone; a grid changed by the shared-memory fit loop (depends on K) or by a developer override
+                // would let the epochs of two row-parallel layers with equal N but different K drift apart -- refuse it.
+                const int mult0 = (flags & Q4_GEMV_SHARE_SM) ? 1 : (a.rt_total >= 2 * sms ? 2 : 1);
+                const int rows_only = a.rt_total < sms * mult0 ? a.rt_total : sms * mult0;
+                if (grid != rows_only || grid > kArMaxCtas) return Q4_ERR_SHAPE;
+            }
             const size_t rest = tail + (size_t)((a.rt_total + grid - 1) / grid) * a.kt * 32;
             const bool compact = dyn_base == kDynBase && !env_aligned && kLutBytes + rest <= 220 * 1024;
             const size_t smem = (compact ? 1 : 2) * (size_t)kLutBytes + rest;

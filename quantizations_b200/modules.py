@@ -105,6 +105,30 @@ class Linear4bit(nn.Linear):
         self.gemv_flags = _lib.Q4_GEMV_PDL
         self.prefetch_next = None  # (packed weight, in_features) of the Linear that runs next: its first tiles are pulled into L2
 
+    # ---- state dict: the packed weight travels with its statistics under bitsandbytes' key names (`weight.absmax`,
+    # `weight.quant_map`, `weight.nested_*`, `weight.quant_state.bitsandbytes__nf4` ...), so that state_dict() / load_state_dict()
+    # / save_pretrained round-trip a quantised module.  The reference has no such hooks: its state dict carries the packed bytes only.
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        qs = getattr(self.weight, "quant_state", None)
+        if qs is not None:
+            for k, v in qs.as_dict(packed=True).items():
+                destination[prefix + "weight." + k] = v if keep_vars else v.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        wkey = prefix + "weight"
+        stat_keys = [k for k in state_dict if k.startswith(wkey + ".")]
+        if stat_keys and wkey in state_dict:
+            packed = state_dict[wkey]
+            stats = {k[len(wkey) + 1:]: state_dict[k] for k in stat_keys}
+            dev = packed.device if packed.is_cuda else (self.weight.device if self.weight.is_cuda else torch.device("cuda"))
+            self.weight = Params4bit.from_prequantized(packed, stats, device=dev, module=self)
+            self.quant_state = self.weight.quant_state
+            state_dict = {k: v for k, v in state_dict.items() if k not in stat_keys}
+            state_dict[wkey] = self.weight.data  # what the generic loader copies into the (already rebuilt) parameter
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
     def set_compute_type(self, x):
         """reference modules.py:112-122: fp32 / bf16 inputs set the compute dtype; fp16 keeps the configured one."""
         if x.dtype in [torch.float32, torch.bfloat16]:

@@ -892,3 +892,36 @@ def test_decode_kernels_do_not_write_outside_their_outputs(q):
                            out=ao.view(1, 1, nh * hd))
     torch.cuda.synchronize()
     assert intact(bk, nkv * L * hd) and intact(bv, nkv * L * hd) and intact(bo, nh * hd)
+
+
+@pytest.mark.parametrize("quant_type,compress", [("nf4", True), ("fp4", False)])
+def test_state_dict_round_trip_of_a_quantised_module(q, quant_type, compress):
+    """ADVICE r1 / SURVEY f2: state_dict() of a quantised Linear4bit carries the statistics under bitsandbytes' key names, and
+    load_state_dict() into a fresh module (Params4bit.from_prequantized underneath) gives the same forward outputs bit for bit;
+    deepcopy and pickle keep the quantisation state as well."""
+    import copy
+    import io
+    import pickle
+
+    torch.manual_seed(3)
+    dt = torch.bfloat16
+    lin = q.Linear4bit(512, 256, bias=True, compute_dtype=dt, compress_statistics=compress, quant_type=quant_type).to(DEV)
+    x1 = torch.randn(1, 1, 512, device=DEV, dtype=dt)
+    x8 = torch.randn(1, 8, 512, device=DEV, dtype=dt)
+    y1, y8 = lin(x1), lin(x8)
+    sd = lin.state_dict()
+    assert f"weight.quant_state.bitsandbytes__{quant_type}" in sd and "weight.absmax" in sd and "weight.quant_map" in sd
+    assert ("weight.nested_absmax" in sd) == compress
+    buf = io.BytesIO()
+    torch.save(sd, buf)
+    buf.seek(0)
+    sd2 = torch.load(buf, map_location="cpu")
+    fresh = q.Linear4bit(512, 256, bias=True, compute_dtype=dt, compress_statistics=compress, quant_type=quant_type, device="meta")
+    fresh.to_empty(device=DEV)
+    missing, unexpected = fresh.load_state_dict(sd2, strict=True, assign=False)
+    assert not missing and not unexpected
+    assert fresh.weight.bnb_quantized and fresh.weight.quant_state.nested == compress
+    assert torch.equal(fresh(x1), y1) and torch.equal(fresh(x8), y8)
+    for clone in (copy.deepcopy(lin), pickle.loads(pickle.dumps(lin))):
+        assert isinstance(clone.weight, q.Params4bit) and clone.weight.quant_state is not None
+        assert torch.equal(clone(x1), y1) and torch.equal(clone(x8), y8)

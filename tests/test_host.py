@@ -155,3 +155,25 @@ def test_swiglu_group_interleaves_four_row_chunks(nested, N, K):
         q.Linear4bitGroup([gate, up, gate], swiglu=True)
     with pytest.raises(ValueError):
         q.Linear4bitGroup([gate, _fake_quantised_linear(N, 2048, 3, nested)], swiglu=True)
+
+
+def test_params4bit_survives_deepcopy_and_pickle():
+    """copy.deepcopy / pickle of a (here: not yet quantised) Linear4bit keep the Params4bit class, its attributes and the
+    module back-reference (the GPU counterpart with a quant_state is tests/test_gpu_parity.py::test_state_dict_round_trip...)."""
+    import copy
+    import io
+    import pickle
+
+    import torch
+
+    import quantizations_b200 as q
+
+    lin = q.Linear4bit(64, 32, bias=True, compute_dtype=torch.bfloat16, quant_type="nf4", compress_statistics=False)
+    c = copy.deepcopy(lin)
+    assert isinstance(c.weight, q.Params4bit) and c.weight is not lin.weight and c.weight.module is c
+    assert (c.weight.quant_type, c.weight.blocksize, c.weight.compress_statistics, c.weight.bnb_quantized) == ("nf4", 64, False, False)
+    buf = io.BytesIO()
+    pickle.dump(lin.weight, buf)
+    buf.seek(0)
+    w = pickle.load(buf)
+    assert isinstance(w, q.Params4bit) and w.quant_type == "nf4" and torch.equal(w.data, lin.weight.data)
