@@ -121,7 +121,6 @@ static cudaError_t launch(int nc, const ring::Args& a, int grid, size_t smem, bo
 {
     switch (nc * 10 + g_wps) {
         case 81: return launch_nc<8, 1>(a, grid, smem, pdl, s);
-        case 161: return launch_nc<16, 1>(a, grid, smem, pdl, s);
         case 162: return launch_nc<16, 2>(a, grid, smem, pdl, s);
         default: printf("unsupported --nc / --wps\n"); exit(1);
     }
