@@ -54,7 +54,10 @@ namespace ring {
 constexpr int kSub = 4;                     // 8-row sub-tiles per ring slot
 constexpr int kSlotBytes = kSub * 2048;     // 32 rows x 256 packed bytes = two 128-byte-wide, 32-row TMA boxes (pair mode: four 16-row boxes)
 constexpr int kSlots = 16;                  // ring depth (a power of two: position / phase of a sequence number are a mask and a shift)
-constexpr int kProdLanes = 4;               // producer lanes issuing slots in lockstep
+#ifndef Q4_RING_PRODLANES
+#define Q4_RING_PRODLANES 4
+#endif
+constexpr int kProdLanes = Q4_RING_PRODLANES;  // producer lanes issuing slots in lockstep
 constexpr int kMaxStages = 8;               // stages per launch (the argument struct must stay under the 4-KB parameter limit)
 constexpr int kConsumerBar = 1;             // named barrier of the consumer warps
 constexpr int kTraceSlots = 16;             // developer trace: globaltimer marks per (stage, CTA)
@@ -574,11 +577,15 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                         // a chunk is one 32-byte sector written by one store instruction of one CTA: its four words arrive together.
                         // Not there yet: back off before asking again -- 75 000 threads polling flat out keep the L2 slices busier
                         // than the stores they are waiting for.
-                        unsigned ns = 32;
+#ifndef Q4_RING_BACKOFF0
+#define Q4_RING_BACKOFF0 32
+#define Q4_RING_BACKOFF_CAP 256
+#endif
+                        unsigned ns = Q4_RING_BACKOFF0;
                         for (long long spin = 0; (uint32_t)(w[j][0] >> 32) != tag || (uint32_t)(w[j][1] >> 32) != tag ||
                                                  (uint32_t)(w[j][2] >> 32) != tag || (uint32_t)(w[j][3] >> 32) != tag; spin++) {
                             __nanosleep(ns);
-                            if (ns < 256) ns *= 2;
+                            if (ns < Q4_RING_BACKOFF_CAP) ns *= 2;
                             ld_relaxed_2xu64(src + (size_t)cc * 4, w[j][0], w[j][1]);
                             ld_relaxed_2xu64(src + (size_t)cc * 4 + 2, w[j][2], w[j][3]);
                             if (spin > (1ll << 24)) __trap();  // a CTA never published: fail loudly instead of hanging the GPU
@@ -639,7 +646,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
 #pragma unroll
         for (int i = 0; i < 32; i++) xr[i] = 0;
         int kt_loaded = -1;
-        constexpr int kAhead = 3;
+        constexpr int kAhead = 3;  // the reload points below (j == 8, j == 12) and the wrap of the fragment ring across sub-tiles are built on 3
         uint32_t wa[8], wb[8];        // packed bytes of (row g, block t4) and (row g, block 4 + t4) of the sub-tile in work
         uint32_t f[kAhead + 1][4];    // looked-up A fragments in flight
 #pragma unroll

@@ -35,7 +35,12 @@ inline bool make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     return fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#ifdef Q4_TMA_L2_PROMOTION
+              Q4_TMA_L2_PROMOTION,
+#else
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+#endif
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace q4
