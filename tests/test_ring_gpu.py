@@ -151,3 +151,33 @@ def test_older_chained_launch_still_matches_through_the_abi(q):
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.equal(o1, y1) and torch.equal(o2, y2) and int(bar.abs().sum()) == 0
+
+
+def test_ring_ragged_k_tile_pair_and_tagged_residual(q):
+    """K % 512 == 256 (tensor-parallel shard sizes): the last k tile is a single TMA box and the stale half of the slot meets
+    zero activations; together with the SwiGLU pair and a residual read through the tagged copy of an earlier stage."""
+    dt = torch.bfloat16
+    torch.manual_seed(0)
+    mk = lambda n, k: q.Linear4bit(k, n, bias=False, compute_dtype=dt, quant_type="nf4").to(DEV)
+    H, I = 1024, 2048 + 256
+    o, gate, up, down = mk(H, H), mk(I, H), mk(I, H), mk(H, I)
+    gu = q.Linear4bitGroup([gate, up])
+    ln = (1 + 0.1 * torch.randn(H, device=DEV)).to(dt)
+    a = torch.randn(1, 1, H, device=DEV, dtype=dt)
+    h0 = torch.randn(1, 1, H, device=DEV, dtype=dt)
+    h = h0.clone()
+    q.gemv_4bit_fused(a, o.weight.data, o.weight.quant_state, residual=h, out=h)
+    g_ref = q.gemv_4bit_fused(h, None, group=gu, rms_weight=ln)
+    q.gemv_4bit_fused(g_ref[..., I:], down.weight.data, down.weight.quant_state, gate=g_ref[..., :I], residual=h, out=h)
+    h_ref = h.clone()
+    h = h0.clone()
+    g_u = torch.full((1, 1, 2 * I), float("nan"), device=DEV, dtype=dt)
+    stages = []
+    q.gemv_4bit_fused(a, o.weight.data, o.weight.quant_state, residual=h, out=h, _defer=stages)
+    q.gemv_4bit_fused(h, None, group=gu, rms_weight=ln, out=g_u, _defer=stages)
+    q.gemv_4bit_fused(g_u[..., I:], down.weight.data, down.weight.quant_state, gate=g_u[..., :I], residual=h, out=h, _defer=stages)
+    for rep in range(2):
+        h.copy_(h0)
+        assert _ring_launch(q, [f for f, _ in stages]) == 0
+        torch.cuda.synchronize()
+        assert _close(h, h_ref) and _close(g_u, g_ref)
