@@ -90,13 +90,18 @@ def quantize_model(model: torch.nn.Module, quantization_config, device="cuda", m
              for name, m in model.named_modules() if type(m) is torch.nn.Linear}
     replace_with_bnb_linear(model, quantization_config, modules_to_not_convert=list(modules_to_not_convert))
     ns = namespace()
-    for name, m in model.named_modules():
+    for name, m in list(model.named_modules()):
         if isinstance(m, ns.nn.Linear4bit):
-            w, b = dense[name]
+            # one layer at a time, and the dense weight is released as soon as it is packed (the replaced nn.Linear modules are gone:
+            # `dense` holds the last reference) -- the peak stays at the dense model's own footprint and falls from there, instead of
+            # dense + quantised (19.7 vs 16.1 GB on Llama-3-8B, profiles/r01c_hf_generate.json)
+            w, b = dense.pop(name)
             old = m.weight
             m.weight = ns.nn.Params4bit(w.to(device), requires_grad=False, **old.__dict__).to(device)
             if b is not None:
                 m.bias = torch.nn.Parameter(b.to(device), requires_grad=False)
+            del w, b, old
+    dense.clear()
     return model.to(device)
 
 
