@@ -109,7 +109,8 @@ int q4_dequantize_blockwise_4bit(const uint8_t* A, const q4_absmax_t* stats, voi
  * prefetch / prefetch_bytes (optional, NULL / 0): a byte range that the NEXT call will stream (typically the packed
  * weight of the following Linear4bit).  It is pulled into the 126 MB L2 with TMA bulk prefetches while this call
  * computes, so HBM never idles between dependent launches.  Purely a hint: results do not depend on it. */
-enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2, Q4_GEMV_SHARE_SM = 4, Q4_ATTN_EARLY_CACHE = 8, Q4_GEMV_SWIGLU = 16 };
+enum { Q4_GEMV_DEFAULT = 0, Q4_GEMV_EXACT_F32 = 1, Q4_GEMV_PDL = 2, Q4_GEMV_SHARE_SM = 4, Q4_ATTN_EARLY_CACHE = 8, Q4_GEMV_SWIGLU = 16,
+       Q4_GEMV_BATCH_TC5 = 32 /* q4_gemv_4bit_batch: take the tcgen05 kernel instead of the default mma.sync one */ };
 int q4_gemv_4bit(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias,
                  void* out, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* prefetch,
                  int64_t prefetch_bytes, void* stream);
@@ -184,9 +185,12 @@ int q4_gemv_4bit_fused(const q4_gemv_fused_t* args, void* stream);
 
 /* Small batch (2 <= tokens <= 16: speculative / multi-sequence decode) in ONE pass over the packed weight:
  *     out[t, r] = sum_k x[t, k] * code[nib(B[r,k])] * absmax[(r*K + k) / 64]   (+ bias[r])
- * x [tokens, K], out [tokens, N] row-major contiguous, bias [N].  Runs the tcgen05 decode kernel with the N columns of the MMA as
- * the tokens, so the cost is that of one GEMV pass whatever `tokens` is; needs the table image (`lut`) and the split-K workspace
- * (see q4_gemv_fused_t), blocksize 64 and K % 256 == 0; Q4_ERR_SHAPE otherwise (callers then use q4_gemm_4bit). */
+ * x [tokens, K], out [tokens, N] row-major contiguous, bias [N].  The reference sends more than one token to a full dequantise +
+ * dense GEMM (modules.py:56-64).  Default kernel (q4_gemv_tokens.cu): mma.sync with the 8 B columns as tokens and the 16 A rows as
+ * weight rows, each quantisation block = 4 MMAs scaled by its absmax; the cost is that of one GEMV pass for up to 8 tokens, two
+ * passes for 9..16.  Needs the table image (`lut`), blocksize 64, K % 256 == 0, N % 16 == 0; `workspace` may be null.  Other
+ * shapes, or flags & Q4_GEMV_BATCH_TC5: the tcgen05 decode kernel (needs the split-K workspace, see q4_gemv_fused_t);
+ * Q4_ERR_SHAPE if neither covers the call (callers then use q4_gemm_4bit). */
 int q4_gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
                        int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, void* workspace,
                        int64_t workspace_bytes, void* stream);

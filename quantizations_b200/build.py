@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--compiler-options", "-fPIC", "-Xptxas", "-v"] + ARCH
 
-SOURCES = ["q4_quantize.cu", "q4_dequantize.cu", "q4_gemv.cu", "q4_gemv_ring.cu", "q4_gemm.cu", "q4_attention.cu", "pythonInterface.cpp"]
+SOURCES = ["q4_quantize.cu", "q4_dequantize.cu", "q4_gemv.cu", "q4_gemv_ring.cu", "q4_gemv_tokens.cu", "q4_gemm.cu", "q4_attention.cu", "pythonInterface.cpp"]
 
 
 def _deps() -> list:

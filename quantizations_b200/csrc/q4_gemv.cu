@@ -566,7 +566,8 @@ int gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, cuda
     return 0;
 }
 
-// 2..16 tokens in one pass over the packed weight (tcgen05 kernel, N columns of the MMA = tokens): x [tokens, K], out [tokens, N]
+// 2..16 tokens in one pass over the packed weight: x [tokens, K], out [tokens, N].  Default: q4_gemv_tokens.cu (mma.sync, the B columns
+// are the tokens); Q4_GEMV_BATCH_TC5 or a shape that kernel refuses: the tcgen05 kernel (N columns of the MMA = tokens)
 int gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
                     int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, void* workspace,
                     int64_t workspace_bytes, cudaStream_t stream)
@@ -574,14 +575,20 @@ int gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, c
     if (!valid_blocksize(blocksize)) return Q4_ERR_BLOCKSIZE;
     if (N < 0 || K < 0 || (K & 1) || tokens < 1 || tokens > 16) return Q4_ERR_SHAPE;
     if (N == 0) return 0;
-    if (!x || !B || !code || !out || !lut || !workspace) return Q4_ERR_NULL;
+    if (!x || !B || !code || !out || !lut) return Q4_ERR_NULL;
     if (int e = check_stats(stats)) return e;
+    if (!(flags & Q4_GEMV_BATCH_TC5)) {
+        // default: the mma.sync kernel with the tokens on the B columns (q4_gemv_tokens.cu); shapes it does not cover go on
+        const int rc = gemv_4bit_tokens(x, B, stats, code, bias, out, tokens, N, K, blocksize, dtype, flags, lut, stream);
+        if (rc != Q4_ERR_SHAPE) return rc;
+    }
+    if (!workspace) return Q4_ERR_NULL;
     GemvPrologue pro;
     pro.lut = lut;
     pro.workspace = workspace;
     pro.workspace_bytes = workspace_bytes;
     pro.tokens = tokens;
-    flags &= ~Q4_GEMV_EXACT_F32;
+    flags &= ~(Q4_GEMV_EXACT_F32 | Q4_GEMV_BATCH_TC5);
     switch (dtype) {
         case Q4_F16:
             return gemv_dispatch<__half>((const __half*)x, B, stats, code, (const __half*)bias, (__half*)out, N, K, blocksize, flags, nullptr,

@@ -34,6 +34,8 @@ int gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_
 int gemv_4bit_batch(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
                     int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, void* workspace,
                     int64_t workspace_bytes, cudaStream_t stream);
+int gemv_4bit_tokens(const void* x, const uint8_t* B, const q4_absmax_t* stats, const float* code, const void* bias, void* out,
+                     int tokens, int64_t N, int64_t K, int blocksize, int dtype, int flags, const void* lut, cudaStream_t stream);
 int gemv_lut_build(const float* code, const float* code2, int dtype, void* lut, cudaStream_t stream);
 int decode_attention(const void* qkv, const void* cos_tab, const void* sin_tab, void* k_cache, void* v_cache, const long long* pos,
                      void* out, int nh, int nkv, int hd, int max_len, int dtype, int flags, cudaStream_t stream);

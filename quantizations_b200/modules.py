@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .core import Params4bit, QuantState, _dequantize_4bit_into, _on_device, fused_gemm_supported, gemm_4bit, gemv_4bit
+from .core import Params4bit, QuantState, _dequantize_4bit_into, _on_device, fused_gemm_supported, gemm_4bit, gemv_4bit, gemv_4bit_batch
 
 
 def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: torch.Tensor = None, bias=None,
@@ -28,18 +28,22 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: 
         return gemv_4bit(A, B, out, state=quant_state, bias=bias, flags=flags, prefetch=prefetch)
     M = A.numel() // A.shape[-1]
     if M <= _SMALL_BATCH_GEMV_ROWS and A.dtype in (torch.float16, torch.bfloat16) and quant_state.blocksize == 64:
-        # 2..4 tokens (speculative / multi-sequence decode): one decode GEMV per token is still cheaper than any
-        # path that touches a dense weight -- each launch streams the packed bytes once at GEMV speed (~5-12 us on the Llama-3-8B
-        # shapes against 24-52 us for the fused GEMM at M=16, profiles/r01b_prefill_gemm.txt); the packed matrix stays L2-resident
-        # between the launches.
-        A2 = A.reshape(M, A.shape[-1])
-        if not A2.is_contiguous():
-            A2 = A2.contiguous()
-        res = out if out is not None else torch.empty(A.shape[:-1] + (quant_state.shape[0],), dtype=A.dtype, device=A.device)
-        res2 = res.view(M, quant_state.shape[0])
-        for m in range(M):
-            gemv_4bit(A2[m:m + 1], B, res2[m:m + 1], state=quant_state, bias=bias, flags=flags)
-        return res
+        n, k = quant_state.shape
+        if k % 256 == 0 and n % 16 == 0 and (bias is None or bias.dtype == A.dtype):
+            # 2..16 tokens (speculative / multi-sequence decode): ONE pass over the packed weight with the tokens on
+            # the MMA's B columns (csrc/q4_gemv_tokens.cu) -- the price of a batch-1 GEMV for up to 8 tokens, of two for 9..16,
+            # against 24-52 us for the fused GEMM at M=16 (profiles/r01b_prefill_gemm.txt)
+            return gemv_4bit_batch(A, B, quant_state, bias=bias, out=out, flags=flags)
+        if M <= 4:
+            # shapes that kernel does not cover: one decode GEMV per token is still cheaper than any path that touches a dense weight
+            A2 = A.reshape(M, A.shape[-1])
+            if not A2.is_contiguous():
+                A2 = A2.contiguous()
+            res = out if out is not None else torch.empty(A.shape[:-1] + (quant_state.shape[0],), dtype=A.dtype, device=A.device)
+            res2 = res.view(M, quant_state.shape[0])
+            for m in range(M):
+                gemv_4bit(A2[m:m + 1], B, res2[m:m + 1], state=quant_state, bias=bias, flags=flags)
+            return res
     if _use_fused_gemm(A, quant_state, bias):
         return gemm_4bit(A, B, quant_state, bias=bias, out=out)
     W = torch.empty(quant_state.shape, dtype=A.dtype, device=A.device)
@@ -47,7 +51,7 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out: 
     return torch.nn.functional.linear(A, W, bias)
 
 
-_SMALL_BATCH_GEMV_ROWS = 4
+_SMALL_BATCH_GEMV_ROWS = 16
 
 
 def _use_fused_gemm(A, quant_state, bias) -> bool:

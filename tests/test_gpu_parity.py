@@ -754,14 +754,15 @@ def test_fused_decode_attention_matches_torch_attention_path(q):
 
 @pytest.mark.parametrize("M", [2, 4])
 def test_small_batch_runs_one_decode_gemv_per_token(q, M):
-    """2..4 tokens go through the decode GEMV row by row (modules.matmul_4bit): identical to calling the module on each token."""
+    """2..4 tokens on a shape the one-pass small-batch kernel does not cover (rows not a multiple of 16) go through the decode GEMV
+    row by row (modules.matmul_4bit): identical to calling the module on each token.  (Covered shapes: tests/test_tokens_gpu.py.)"""
     torch.manual_seed(11)
-    lin = q.Linear4bit(1024, 768, bias=True, compute_dtype=torch.bfloat16, quant_type="nf4").to(DEV)
-    lin.bias.data = torch.randn(768, device=DEV, dtype=torch.bfloat16)
+    lin = q.Linear4bit(1024, 776, bias=True, compute_dtype=torch.bfloat16, quant_type="nf4").to(DEV)
+    lin.bias.data = torch.randn(776, device=DEV, dtype=torch.bfloat16)
     x = torch.randn(1, M, 1024, device=DEV, dtype=torch.bfloat16)
     n0 = q._lib.launch_count()
     y = lin(x)
-    assert q._lib.launch_count() - n0 == M and y.shape == (1, M, 768)
+    assert q._lib.launch_count() - n0 == M and y.shape == (1, M, 776)
     for m in range(M):
         assert torch.equal(y[:, m], lin(x[:, m:m + 1])[:, 0])
 
@@ -823,7 +824,7 @@ def test_chained_gemvs_equal_separate_launches(q, dtype):
 @pytest.mark.parametrize("shape", [(4096, 4096), (1000, 512)])
 @pytest.mark.parametrize("M", [2, 7, 16])
 def test_small_batch_tcgen05_gemv_matches_per_token_gemv(q, shape, M):
-    """q4_gemv_4bit_batch (the tcgen05 decode kernel with the MMA's N columns as tokens): one pass over the packed weight for
+    """q4_gemv_4bit_batch with Q4_GEMV_BATCH_TC5 (the tcgen05 decode kernel with the MMA's N columns as tokens): one pass over the packed weight for
     2..16 tokens gives what the per-token decode GEMV gives, bias included, ragged last row tile included."""
     N, K = shape
     torch.manual_seed(17)
@@ -831,7 +832,7 @@ def test_small_batch_tcgen05_gemv_matches_per_token_gemv(q, shape, M):
     packed, st = q.quantize_4bit(W, quant_type="nf4")
     bias = torch.randn(N, device=DEV, dtype=torch.bfloat16)
     x = torch.randn(1, M, K, device=DEV, dtype=torch.bfloat16)
-    y = q.gemv_4bit_batch(x, packed, st, bias=bias)
+    y = q.gemv_4bit_batch(x, packed, st, bias=bias, flags=q._lib.Q4_GEMV_BATCH_TC5)
     ref = torch.cat([q.gemv_4bit(x[:, m:m + 1], packed, state=st, bias=bias) for m in range(M)], dim=1)
     assert y.shape == (1, M, N)
     assert (y.float() - ref.float()).abs().max().item() <= 1e-2 * ref.float().abs().max().item()
