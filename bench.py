@@ -598,12 +598,27 @@ def gemv_sweep(device, peak, q, pool_bytes=640 << 20, launches=96, replays=10):
             structs.append(_lib.GemvFused(x.data_ptr(), None, None, 0.0, lin.weight.data_ptr(), ctypes.pointer(st.native_stats()), None, None, 1,
                                           st.code.data_ptr(), None, y.data_ptr(), N, K, st.blocksize, _lib.Q4_BF16, _lib.Q4_GEMV_PDL, None, 0,
                                           st.lut(dt).data_ptr(), None, 0))
-        with torch.cuda.stream(stream):
+        # small batch (speculative / multi-sequence decode): M tokens in ONE pass over the packed weight (q4_gemv_4bit_batch)
+        xm = torch.randn(8, K, device=device, dtype=dt)
+        ym = torch.empty(8, N, device=device, dtype=dt)
+
+        def issue_single():
+            for i in range(launches):
+                rc = L.q4_gemv_4bit_fused(ctypes.byref(structs[i % nw]), stream.cuda_stream)
+                if rc:
+                    _lib.check(rc, "q4_gemv_4bit_fused")
+
+        def issue_tokens(M):
             def issue():
                 for i in range(launches):
-                    rc = L.q4_gemv_4bit_fused(ctypes.byref(structs[i % nw]), stream.cuda_stream)
+                    st = lins[i % nw].weight.quant_state
+                    rc = L.q4_gemv_4bit_batch(xm.data_ptr(), lins[i % nw].weight.data_ptr(), st.native_stats(), st.code.data_ptr(), None, ym.data_ptr(),
+                                              M, N, K, st.blocksize, _lib.Q4_BF16, _lib.Q4_GEMV_PDL, st.lut(dt).data_ptr(), None, 0, stream.cuda_stream)
                     if rc:
-                        _lib.check(rc, "q4_gemv_4bit_fused")
+                        _lib.check(rc, "q4_gemv_4bit_batch")
+            return issue
+
+        def time_graph(issue):
             issue()
             torch.cuda.synchronize(device)
             g = torch.cuda.CUDAGraph()
@@ -618,15 +633,24 @@ def gemv_sweep(device, peak, q, pool_bytes=640 << 20, launches=96, replays=10):
                 g.replay()
             e1.record()
             torch.cuda.synchronize(device)
-            us = e0.elapsed_time(e1) * 1e3 / (replays * launches)
+            del g
+            return e0.elapsed_time(e1) * 1e3 / (replays * launches)
+
+        with torch.cuda.stream(stream):
+            us = time_graph(issue_single)
+            us4, us8 = time_graph(issue_tokens(4)), time_graph(issue_tokens(8))
         b = algo_bytes(N, K)
         out[f"{N}x{K}"] = {"us": round(us, 3), "achieved": round(b / us / 1e3, 1), "unit": "GB/s", "frac": round(b / us / 1e3 / peak, 4),
-                           "algorithmic_bytes": b, "pool_weights": nw}
-        del lins, structs, g
+                           "algorithmic_bytes": b, "pool_weights": nw,
+                           "tokens4_us": round(us4, 3), "tokens8_us": round(us8, 3), "tokens4_vs_1": round(us4 / us, 3)}
+        del lins, structs
         torch.cuda.empty_cache()
     return {"workload": "single Linear4bit NF4 + double-quant GEMV, bf16, bs=1; one q4_gemv_4bit_fused launch per Linear, "
                         f"{launches} stream-ordered launches per CUDA-graph replay (programmatic dependent launch), weights rotating over a pool > L2",
-            "kernel": "q4::gemv_mma_kernel<bf16, nested>", "shapes": out}
+            "kernel": "q4::gemv_mma_kernel<bf16, nested>",
+            "small_batch": "tokens4_us / tokens8_us: 4 / 8 tokens in ONE pass over the packed weight (q4_gemv_4bit_batch -> q4::tok::gemv_tokens_kernel), "
+                           "measured the same way; the reference sends > 1 token to dequantise + dense GEMM (modules.py:56-64)",
+            "shapes": out}
 
 
 def blockwise_rates(device, peak, N=14336, K=4096, pool=6, iters=30):
