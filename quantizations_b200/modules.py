@@ -5,7 +5,6 @@ reference: /root/reference/modules.py:28-64 (matmul_4bit), :67-151 (Linear4bit).
 from __future__ import annotations
 
 import os
-import weakref
 
 import torch
 import torch.nn as nn
@@ -129,6 +128,7 @@ class Linear4bit(nn.Linear):
             dev = packed.device if packed.is_cuda else (self.weight.device if self.weight.is_cuda else torch.device("cuda"))
             self.weight = Params4bit.from_prequantized(packed, stats, device=dev, module=self)
             self.quant_state = self.weight.quant_state
+            _drop_decode_cache(self)
             state_dict = {k: v for k, v in state_dict.items() if k not in stat_keys}
             state_dict[wkey] = self.weight.data  # what the generic loader copies into the (already rebuilt) parameter
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
@@ -163,42 +163,80 @@ class Linear4bit(nn.Linear):
 
 
 _FAST_DTYPES = (torch.float16, torch.bfloat16)
-_DECODE_CACHE = weakref.WeakKeyDictionary()  # Linear4bit -> cached launch descriptor of its single-vector forward
+
+
+def _none():
+    return None
+
+
+class _DecodeLaunch:
+    """Cached launch descriptor (q4_gemv_fused_t) of a Linear4bit's single-vector forward.  Lives in the module's __dict__ (one
+    dictionary probe per call) but never travels with it: it deep-copies and pickles as None (ctypes descriptors hold raw pointers)."""
+    __slots__ = ("weight", "qs", "wptr", "dtype", "flags", "f", "ref", "keep", "fn", "N", "pf")
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_none, ())
+
+
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream  # the current stream's handle as an int, without building a Stream object
+    _cur_device = torch._C._cuda_getDevice
+except AttributeError:  # a torch build without the private accessors
+    _raw_stream = lambda idx: torch.cuda.current_stream(idx).cuda_stream  # noqa: E731
+    _cur_device = torch.cuda.current_device
 
 
 def _linear4bit_decode(self, x, weight, bias):
     """Single-vector forward with a cached launch descriptor (q4_gemv_fused_t): everything that does not change between calls --
     weight, statistics, tables -- is bound once, so a call costs one allocation, three pointer stores and the launch.  Under HF
-    generate() the host side of 224 Linear calls per token is what batch-1 decode waits for.  Same launch as core.gemv_4bit."""
+    generate() the host side of 224 Linear calls per token is what batch-1 decode waits for (tests/perf/hf_generate_tps.py), so
+    the per-call Python is kept to identity checks.  Same launch as core.gemv_4bit."""
     qs = weight.quant_state
-    if qs.blocksize != 64:
-        return None
-    key = (weight.data_ptr(), id(qs), qs.absmax.data_ptr(), x.dtype, self.gemv_flags)
-    c = _DECODE_CACHE.get(self)  # kept outside the module: ctypes descriptors must not be deep-copied / pickled with it
-    if c is None or c[0] != key:
+    c = self.__dict__.get("_q4_decode")
+    if (c is None or c.weight is not weight or c.qs is not qs or c.dtype != x.dtype or c.flags != self.gemv_flags
+            or c.wptr != weight.data_ptr()):
+        if qs.blocksize != 64:
+            return None
         import ctypes
 
         from .core import _DTYPE_CODE, _ws_args
 
         stats, lut = qs.native_stats(), qs.lut(x.dtype)
-        f = _lib.GemvFused(None, None, None, 0.0, weight.data_ptr(), ctypes.pointer(stats), None, None, 1, qs.code.data_ptr(), None, None,
-                           qs.shape[0], qs.shape[1], 64, _DTYPE_CODE[x.dtype], self.gemv_flags, None, 0, lut.data_ptr(),
-                           *_ws_args(x.device))
-        c = _DECODE_CACHE[self] = (key, f, ctypes.byref(f), (stats, lut), _lib.lib().q4_gemv_4bit_fused, qs.shape[0])
-    f = c[1]
-    out = torch.empty(x.shape[:-1] + (c[5],), dtype=x.dtype, device=x.device)
+        c = _DecodeLaunch()
+        c.weight, c.qs, c.wptr, c.dtype, c.flags = weight, qs, weight.data_ptr(), x.dtype, self.gemv_flags
+        c.f = _lib.GemvFused(None, None, None, 0.0, weight.data_ptr(), ctypes.pointer(stats), None, None, 1, qs.code.data_ptr(), None, None,
+                             qs.shape[0], qs.shape[1], 64, _DTYPE_CODE[x.dtype], self.gemv_flags, None, 0, lut.data_ptr(),
+                             *_ws_args(x.device))
+        c.ref, c.keep, c.fn, c.N, c.pf = ctypes.byref(c.f), (stats, lut), _lib.lib().q4_gemv_4bit_fused, qs.shape[0], None
+        self.__dict__["_q4_decode"] = c
+    f = c.f
+    out = torch.empty(x.shape[:-1] + (c.N,), dtype=x.dtype, device=x.device)
     f.x, f.out, f.bias = x.data_ptr(), out.data_ptr(), (None if bias is None else bias.data_ptr())
     nxt = self.prefetch_next
-    if nxt is not None:
-        t, k = nxt if isinstance(nxt, tuple) else (nxt, 0)
-        f.prefetch, f.prefetch_bytes, f.prefetch_K = t.data_ptr(), t.numel() * t.element_size(), k
+    if nxt is not c.pf:
+        if nxt is not None:
+            t, k = nxt if isinstance(nxt, tuple) else (nxt, 0)
+            f.prefetch, f.prefetch_bytes, f.prefetch_K = t.data_ptr(), t.numel() * t.element_size(), k
+        else:
+            f.prefetch, f.prefetch_bytes, f.prefetch_K = None, 0, 0
+        c.pf = nxt
+    idx = x.device.index
+    if idx == _cur_device():
+        rc = c.fn(c.ref, _raw_stream(idx))
     else:
-        f.prefetch, f.prefetch_bytes, f.prefetch_K = None, 0, 0
-    with _on_device(x.device):
-        rc = c[4](c[2], torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(idx):
+            rc = c.fn(c.ref, _raw_stream(idx))
     if rc:
         _lib.check(rc, "gemv_4bit")
     return out
+
+
+def _drop_decode_cache(module):
+    """After anything that re-lays a module's weight or statistics in place (grouping, load_state_dict)."""
+    module.__dict__.pop("_q4_decode", None)
 
 
 class Linear4bitGroup(nn.Module):
@@ -259,6 +297,7 @@ class Linear4bitGroup(nn.Module):
                 qs.state2._stats = None
                 o_a2 += n_a2
             qs._stats = None
+            _drop_decode_cache(lin)
             o_p, o_a = o_p + n_p, o_a + n_a
         self.code, self.blocksize, self.nested = first.code, 64, nested
         if nested:

@@ -61,7 +61,10 @@ def main():
     res = {}
     for which in a.which.split(","):
         torch.cuda.empty_cache()
-        model = build(a.layers, dev)
+        torch.cuda.reset_peak_memory_stats()
+        # "ours" is built on the host and quantised layer by layer on its way to the GPU (what from_pretrained(load_in_4bit=True) does):
+        # the dense model never exists in device memory
+        model = build(a.layers, "cpu" if which == "ours" else dev)
         if which.startswith("ours"):
             from transformers import BitsAndBytesConfig
 
@@ -90,6 +93,7 @@ def main():
             del model
             continue
         kw = dict(max_new_tokens=60, min_new_tokens=60, do_sample=False, use_cache=True, pad_token_id=0)
+        load_peak = torch.cuda.max_memory_allocated()
         with torch.no_grad():
             out = model.generate(ids, **kw)  # warm-up
             torch.cuda.synchronize()
@@ -100,7 +104,8 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(time.perf_counter() - t0)
         assert out.shape == (1, 92)
-        res[which] = {"tps": round(60 / (sum(ts) / len(ts)), 1), "best_tps": round(60 / min(ts), 1), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2)}
+        res[which] = {"tps": round(60 / (sum(ts) / len(ts)), 1), "best_tps": round(60 / min(ts), 1), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2),
+                      "load_peak_mem_GB": round(load_peak / 1e9, 2)}
         print(which, res[which], flush=True)
         del model
         torch.cuda.reset_peak_memory_stats()

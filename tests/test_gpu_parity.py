@@ -926,3 +926,29 @@ def test_state_dict_round_trip_of_a_quantised_module(q, quant_type, compress):
     for clone in (copy.deepcopy(lin), pickle.loads(pickle.dumps(lin))):
         assert isinstance(clone.weight, q.Params4bit) and clone.weight.quant_state is not None
         assert torch.equal(clone(x1), y1) and torch.equal(clone(x8), y8)
+
+
+def test_linear4bit_copies_and_pickles_after_a_decode_forward(q):
+    """The cached launch descriptor of the single-vector forward (raw pointers in a ctypes struct) lives in the module's __dict__ but
+    must not travel: a deep copy / pickle of a module that has already run drops it and rebuilds its own on first use; re-laying the
+    weight (Linear4bitGroup) invalidates it."""
+    import copy
+    import pickle
+
+    torch.manual_seed(2)
+    lin = q.Linear4bit(512, 256, bias=True, compute_dtype=torch.bfloat16, quant_type="nf4").to(DEV)
+    x = torch.randn(1, 1, 512, device=DEV, dtype=torch.bfloat16)
+    y = lin(x)
+    assert "_q4_decode" in lin.__dict__
+    twin = copy.deepcopy(lin)
+    assert twin.__dict__.get("_q4_decode") is None
+    assert twin.weight.data_ptr() != lin.weight.data_ptr()
+    assert torch.equal(twin(x), y)
+    again = pickle.loads(pickle.dumps(lin))
+    assert again.__dict__.get("_q4_decode") is None and torch.equal(again(x), y)
+    other = q.Linear4bit(512, 128, bias=False, compute_dtype=torch.bfloat16, quant_type="nf4").to(DEV)
+    lin.bias = None
+    y0, y1 = lin(x), other(x)
+    q.Linear4bitGroup([lin, other])
+    assert "_q4_decode" not in lin.__dict__
+    assert torch.equal(lin(x), y0) and torch.equal(other(x), y1)
