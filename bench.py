@@ -333,7 +333,7 @@ def run_ours(args, rank, world, device):
                 _lib.check(rc, "q4_gemv_4bit_chain")
 
     use_chain = args.chain and args.group and not side and (comm is None or fused_ar is not None) and len(units) % 4 == 0
-    # the persistent ring kernel (q4_gemv_4bit_ring): up to eight dependent GEMVs (two decoder layers) per launch
+    # the persistent ring kernel (q4_gemv_4bit_ring): up to 32 dependent GEMVs (eight decoder layers) per launch
     # (tensor-parallel: measured slower than single launches at tp2 -- 1.03 vs 0.94 ms/step -- so there it is opt-in: --ring-tp)
     use_ring = args.ring and not use_chain and args.group and not side and (comm is None or (fused_ar is not None and args.ring_tp))
     ring_arrays = []
@@ -932,7 +932,7 @@ def main():
                          "launch per (grouped) Linear; measured SLOWER on B200 (1.65 vs 1.47 ms/step: DESIGN.md 4.1c), hence opt-in")
     ap.add_argument("--no-ring", dest="ring", action="store_false",
                     help="single GPU: one launch per (grouped) Linear (q4_gemv_4bit_fused) instead of the persistent ring kernel "
-                         "(q4_gemv_4bit_ring: eight dependent GEMVs per launch, weights streamed through a TMA ring across stage boundaries)")
+                         "(q4_gemv_4bit_ring: up to 32 dependent GEMVs per launch, weights streamed through a TMA ring across stage boundaries)")
     ap.add_argument("--ring-tp", action="store_true", help="tensor-parallel runs: the ring kernel with the all-reduce in its row-parallel stages' epilogues")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="tensor-parallel runs: NCCL all-reduce after the row-parallel GEMVs (the baseline) instead of the fused epilogue exchange")

@@ -212,7 +212,8 @@ int q4_gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, v
  *   - stage i+1's x == stage i's out (the first K values are consumed), or
  *   - stage i is a grouped gate/up pair (nmat == 2, equal halves) and stage i+1 has x_gate == stage i's out and x == out + rows/2:
  *     the gate/up epilogue then publishes silu(gate) * up itself (stage i's out is still written in full);
- *   - a stage's bias may be memory the PREVIOUS kernel wrote, or exactly the out of an earlier stage (the residual stream);
+ *   - a stage's bias may be memory the PREVIOUS kernel wrote, or exactly the out of an earlier stage at most 6 stages back (the
+ *     residual stream);
  *   - stage 0's x / x_gate, and any stage's rms_weight, are memory the previous kernel wrote.
  * Row-parallel stages may carry q4_allreduce_t: the sum over the tensor-parallel ranks then runs in the stage's epilogue, before bias
  * and before the outputs are handed to the next stage.
@@ -223,7 +224,7 @@ int q4_gemv_4bit_chain(const q4_gemv_fused_t* stages, int n, void* barrier_ws, v
  * ONCE by the caller, owned by one stream at a time (it carries the exchange words and the per-CTA launch epochs, so replayed CUDA
  * graphs stay in step).  flags of stage 0 apply to the launch (Q4_GEMV_PDL).  The grid is one CTA per SM and its CTAs wait for each
  * other: it must not be launched while a kernel that waits for IT holds SMs. */
-#define Q4_GEMV_RING_MAX_STAGES 8
+#define Q4_GEMV_RING_MAX_STAGES 32
 #define Q4_GEMV_RING_WS_BYTES (73728 + 8 * 131072)
 int q4_gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_t workspace_bytes, void* stream);
 

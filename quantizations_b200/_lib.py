@@ -16,7 +16,7 @@ Q4_GENERAL8BIT, Q4_FP4, Q4_NF4 = 0, 1, 2
 Q4_GEMV_DEFAULT, Q4_GEMV_EXACT_F32, Q4_GEMV_PDL, Q4_GEMV_SHARE_SM, Q4_ATTN_EARLY_CACHE, Q4_GEMV_SWIGLU = 0, 1, 2, 4, 8, 16
 Q4_GEMV_BATCH_TC5 = 32
 Q4_ERR_SHAPE, Q4_ERR_ALIGN = -4, -6  # include/quantizations_b200.h: q4_status
-Q4_GEMV_RING_MAX_STAGES, Q4_GEMV_RING_WS_BYTES = 8, 73728 + 8 * 131072
+Q4_GEMV_RING_MAX_STAGES, Q4_GEMV_RING_WS_BYTES = 32, 73728 + 8 * 131072
 Q4_GEMV_LUT_BYTES = 65536
 Q4_GEMV_WORKSPACE_BYTES = 8 << 20
 

@@ -849,7 +849,7 @@ class gemv_4bit_chain:
         with _on_device(dev):
             i = 0
             while i < len(stages):
-                # the persistent ring kernel takes up to eight dependent stages; what it does not support (Q4_ERR_SHAPE / Q4_ERR_ALIGN,
+                # the persistent ring kernel takes up to 32 dependent stages; what it does not support (Q4_ERR_SHAPE / Q4_ERR_ALIGN,
                 # nothing launched) goes to the older chained launch, four stages at a time
                 if _USE_RING:
                     part = stages[i:i + _lib.Q4_GEMV_RING_MAX_STAGES]

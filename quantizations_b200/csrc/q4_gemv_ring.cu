@@ -195,6 +195,7 @@ int gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_
             for (int j = i - 1; j >= 0; j--) {
                 if (!overlaps(f.bias, f.rows * esz, stages[j].out, stages[j].rows * esz)) continue;
                 if (f.bias != stages[j].out || f.rows > stages[j].rows || c.st[j].pair || stages[j].rows > ring::kXchMaxRows) return Q4_ERR_SHAPE;
+                if (i - j > ring::kXchBufs - 2) return Q4_ERR_SHAPE;  // its exchange buffer (stage % kXchBufs) would be in use again
                 st.bias_stage = j;
                 break;
             }
@@ -245,4 +246,4 @@ int gemv_4bit_ring(const q4_gemv_fused_t* stages, int n, void* workspace, int64_
 
 static_assert(q4::ring::kWsBytes == Q4_GEMV_RING_WS_BYTES, "header constant out of date");
 static_assert(q4::ring::kMaxStages == Q4_GEMV_RING_MAX_STAGES, "header constant out of date");
-static_assert(sizeof(q4::ring::Args) <= 4096, "kernel parameters exceed the 4-KB limit");
+static_assert(sizeof(q4::ring::Args) <= 32764, "kernel parameters exceed the 32-KB limit (CUDA >= 12.1, sm_70+)");

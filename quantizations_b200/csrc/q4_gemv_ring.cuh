@@ -58,16 +58,18 @@ constexpr int kSlots = 16;                  // ring depth (a power of two: posit
 #define Q4_RING_PRODLANES 4
 #endif
 constexpr int kProdLanes = Q4_RING_PRODLANES;  // producer lanes issuing slots in lockstep
-constexpr int kMaxStages = 8;               // stages per launch (the argument struct must stay under the 4-KB parameter limit)
+constexpr int kMaxStages = 32;              // stages per launch (32 x 384-byte descriptors: inside the 32-KB kernel-parameter limit of CUDA >= 12.1;
+                                            // their plans fill what is left of shared memory beside the table, the ring and the activation)
+constexpr int kXchBufs = 8;                 // exchange buffers: stage s publishes into buffer s % 8 (see the epilogue for why 8 is plenty)
 constexpr int kConsumerBar = 1;             // named barrier of the consumer warps
 constexpr int kTraceSlots = 16;             // developer trace: globaltimer marks per (stage, CTA)
 // workspace layout (Q4_GEMV_RING_WS_BYTES, zeroed once by the caller, owned by one stream at a time)
 constexpr int kWsEpochOff = 1024;           // u32 [kWsMaxCtas]: stages run so far, per CTA (the tags of both exchanges)
 constexpr int kWsFixOff = 8192;             // {f32, u32} [kWsMaxCtas][32]: partial sums of the row group a CTA shares with its predecessor
 constexpr int kWsMaxCtas = 256;
-constexpr int kWsXchOff = kWsFixOff + kWsMaxCtas * kSub * 8 * 8;  // {2 x T, u32 tag} [kMaxStages][kXchMaxRows / 2]: stage outputs
+constexpr int kWsXchOff = kWsFixOff + kWsMaxCtas * kSub * 8 * 8;  // {2 x T, u32 tag} [kXchBufs][kXchMaxRows / 2]: stage outputs
 constexpr int kXchMaxRows = 32768;
-constexpr int kWsBytes = kWsXchOff + kMaxStages * kXchMaxRows * 4;
+constexpr int kWsBytes = kWsXchOff + kXchBufs * kXchMaxRows * 4;
 
 struct Stage {
     alignas(64) CUtensorMap map;  // packed weight as u8 [rows, K/2], box {128 bytes, 32 rows (pair mode: 16)}, SWIZZLE_128B
@@ -110,16 +112,16 @@ struct Args {
 };
 
 // what a CTA needs to know about its share of a stage; computed once per launch (consumer warp `stage`), read by everybody
-struct Plan {                 // 48 bytes: eight of them have to fit beside the table, the ring and a 14336-element activation
+struct Plan {                 // 12 bytes: 32 of them have to fit beside the table, the ring and a 14336-element activation
     int S0;                   // the CTA's range of the flat slot list: [S0, S0 + nloc)
-    int base_seq;             // ring sequence number of its first slot (slots taken in earlier stages)
     unsigned short nloc;
-    unsigned short head;      // its first `head` slots belong to a row group that began in the previous CTA
     unsigned short rg_own0;   // row groups it owns (= holds the first k tile of): [rg_own0, rg_own0 + nrows_own / 32)
     unsigned short nrows_own;
-    unsigned short rg[8];     // per consumer warp group: row group, k tile and local index of its first slot
-    unsigned char kt[8], i0[8];
+    unsigned char head;       // its first `head` slots belong to a row group that began in the previous CTA
+    unsigned char base;       // ring sequence number of its first slot (slots taken in earlier stages) mod 32: position and phase of a
+                              // slot in the 16-deep ring, and the consumer group / producer lane it falls to, depend on nothing else
 };
+static_assert(sizeof(Plan) == 12, "plan size");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -354,11 +356,11 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         s_misc[0] = 0;
         mark(0, 0);
     }
-    if (warp < c.n) {  // kMaxStages <= consumer warps
-        // ---- the plan of stage `warp` (all the integer divisions of the launch happen here, once, off the critical path)
-        const Stage& a = c.st[warp];
+    for (int ps = warp; ps < c.n && warp < NC; ps += NC) {
+        // ---- the plan of stage `ps` (the integer divisions of the CTA's ranges happen here, once per launch, off the critical path)
+        const Stage& a = c.st[ps];
         int base = 0;
-        for (int s = 0; s < warp; s++) {
+        for (int s = 0; s < ps; s++) {
             int u0, u1;
             cta_range(c.st[s], bx, u0, u1);
             base += u1 - u0;
@@ -366,23 +368,15 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         int S0, S1;
         cta_range(a, bx, S0, S1);
         const int nloc = S1 - S0, KT = a.KT;
-        Plan& p = s_plan[warp];
         if (lane == 0) {
+            Plan& p = s_plan[ps];
             p.S0 = S0;
             p.nloc = (unsigned short)nloc;
-            p.base_seq = base;
-            p.head = (unsigned short)((nloc > 0 && (S0 % KT) != 0) ? (KT - S0 % KT < nloc ? KT - S0 % KT : nloc) : 0);
+            p.base = (unsigned char)(base & 31);
+            p.head = (unsigned char)((nloc > 0 && (S0 % KT) != 0) ? (KT - S0 % KT < nloc ? KT - S0 % KT : nloc) : 0);
             const int rg_own0 = (S0 + KT - 1) / KT, rg_own1 = (S1 + KT - 1) / KT;
             p.rg_own0 = (unsigned short)rg_own0;
             p.nrows_own = (unsigned short)(nloc > 0 ? (rg_own1 - rg_own0) * (kSub * 8) : 0);
-        }
-        if (lane < NP) {
-            int i0 = lane - (base % NP);
-            if (i0 < 0) i0 += NP;
-            const int S = S0 + i0;
-            p.i0[lane] = (unsigned char)i0;
-            p.rg[lane] = (unsigned short)(S / KT);
-            p.kt[lane] = (unsigned char)(S - (S / KT) * KT);
         }
     }
     __syncthreads();
@@ -407,7 +401,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             // so a ring position is always filled by the same lane, fill after fill: its parity wait can never alias an older phase.
             for (int s = 0; s < c.n; s++) {
                 const Stage& a = c.st[s];
-                const int S0 = s_plan[s].S0, n = s_plan[s].nloc, base = s_plan[s].base_seq;
+                const int S0 = s_plan[s].S0, n = s_plan[s].nloc, base = s_plan[s].base;
                 const int KT = a.KT, halfK = a.K >> 1;
                 if (lane == 0) {
                     asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map) : "memory");
@@ -484,7 +478,9 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         // parity wait can never alias an older phase.  Within a stage the group's k tile is constant whenever NP % KT == 0.
         // Everything that moves from slot to slot is a running value advanced by per-stage constants (no multiplications, no
         // parameter reads in the loop): the flat index i, its row group / k tile, and the index `sb` of the lane's absmax pair.
-        int ci = pl.i0[grp], crg = pl.rg[grp], ckt = pl.kt[grp];
+        int ci = grp - (int)(pl.base % NP);  // ring sequence numbers q with q % NP == grp are this group's: local index of its first slot
+        if (ci < 0) ci += NP;
+        int crg = (S0 + ci) / KT, ckt = (S0 + ci) - crg * KT;
         int left = ci < nloc ? (nloc - ci + NP - 1) / NP : 0;  // slots this warp group still takes in this stage
         const int d_rg = a.d_rg, d_kt = a.d_kt;                // NP / KT, NP % KT (host)
         const int row_mul = a.pair ? kSub * 4 : kSub * 8;
@@ -503,7 +499,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
         int pos;
         uint32_t ph;
         {
-            const int seq = pl.base_seq + ci;
+            const int seq = (int)pl.base + ci;
             pos = seq & (D - 1);
             ph = (uint32_t)(seq / D) & 1u;
         }
@@ -554,7 +550,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             // and arrival are one load.  All of a thread's loads are issued before the first is examined: one round trip when the data
             // is there.  A thread owns whole 16-byte chunks (8 activations), exactly as in the plain staging, so the sum of squares of
             // the RMSNorm is accumulated in the same order.
-            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xch0) + (size_t)(stage - 1) * (kXchMaxRows / 2);
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xch0) + (size_t)((stage - 1) & (kXchBufs - 1)) * (kXchMaxRows / 2);
             const uint32_t tag = epoch_base + (uint32_t)stage;  // the previous stage's epoch
             constexpr int kU = 4;
             float ss = 0.0f;
@@ -843,7 +839,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
             }
             if (a.bias) {
                 const int r = sub_row(a, rg, v >> 3) + (v & 7);
-                if (a.bias_stage >= 0) pre_bias = ld_relaxed_u64(reinterpret_cast<const unsigned long long*>(xch0) + (size_t)a.bias_stage * (kXchMaxRows / 2) + (r >> 1));
+                if (a.bias_stage >= 0) pre_bias = ld_relaxed_u64(reinterpret_cast<const unsigned long long*>(xch0) + (size_t)(a.bias_stage & (kXchBufs - 1)) * (kXchMaxRows / 2) + (r >> 1));
                 else if (r < R) pre_bias = __ldcg(reinterpret_cast<const unsigned short*>(a.bias) + r);
             }
         }
@@ -916,7 +912,7 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                     float bv;
                     if (a.bias_stage >= 0) {
                         // written by other CTAs in an earlier stage of this launch: its tagged copy says when it is there
-                        const unsigned long long* bsrc = reinterpret_cast<const unsigned long long*>(xch0) + (size_t)a.bias_stage * (kXchMaxRows / 2) + (r >> 1);
+                        const unsigned long long* bsrc = reinterpret_cast<const unsigned long long*>(xch0) + (size_t)(a.bias_stage & (kXchBufs - 1)) * (kXchMaxRows / 2) + (r >> 1);
                         unsigned long long w = i == tid ? pre_bias : ld_relaxed_u64(bsrc);
                         const uint32_t btag = epoch_base + (uint32_t)a.bias_stage + 1u;
                         for (long long spin = 0; (uint32_t)(w >> 32) != btag; spin++) {
@@ -933,7 +929,10 @@ gemv_ring_kernel(const __grid_constant__ Args c)
                 }
                 if (valid && !a.skip_out) reinterpret_cast<T*>(a.out)[r] = y;
                 if (a.publish) {
-                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(xch0) + (size_t)stage * (kXchMaxRows / 2);
+                    // buffer stage % 8: a CTA that publishes stage s has read ALL of stage s - 1's output, so every CTA has published
+                    // s - 1 and therefore read all of s - 2: nothing older than two stages is still being read (a residual comes from
+                    // at most a few stages back, checked on the host), and a stale word carries another epoch tag anyway
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(xch0) + (size_t)(stage & (kXchBufs - 1)) * (kXchMaxRows / 2);
                     const float yf = Elem<T>::to_f32(y);
                     if (a.publish == 1) {
                         const float yo = __shfl_xor_sync(0xffffffffu, yf, 1);
