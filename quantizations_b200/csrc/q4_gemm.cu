@@ -12,8 +12,9 @@
 // per 64-wide k-block, A = dequantised weight tile, B = activation tile, both K-major fp16/bf16, SWIZZLE_128B.
 //
 // Warp roles (256 threads, one output tile per CTA):
-//   warp 0      TMA producer: per stage, 2-D TMA of the activation tile (swizzle 128B) and of the PACKED weight tile
-//               (128 rows x 32 bytes, no swizzle) into shared memory, completion on full_tma[stage].
+//   warp 0      TMA producer, activations: per stage a 2-D TMA of the activation tile (swizzle 128B), completion on full_tma[stage].
+//   warp 3      TMA producer, weights: the PACKED weight tile (128 rows x 32 bytes, no swizzle) of every k-block into its own, deeper
+//               ring (kPackedStages x 4 KB) on full_p / empty_p -- the dequantise warps never wait for HBM.
 //   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 16 each) per stage into TMEM, then tcgen05.commit
 //               releases the stage (empty[stage]); after the last k-block a commit signals the epilogue (tmem_full).
 //   warp 2      TMEM allocation / deallocation.
@@ -105,6 +106,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr)
 }
 
 constexpr int kSets = 3;         // dequantise warp sets (4 warps each); set j handles k-blocks j, j+kSets, ...
+constexpr int kPackedStages = 8; // ring of PACKED weight tiles (4 KB each), deeper than the A / activation stages: see the kernel
 constexpr int kThreads = 128 + 128 * kSets;
 
 struct Args {
@@ -124,7 +126,7 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// shared memory plan (dynamic, 1024-byte aligned): [A tiles: stages x 16 KB][B tiles: stages x bn*128][packed: stages x 4 KB]
+// shared memory plan (dynamic, 1024-byte aligned): [A tiles: stages x 16 KB][B tiles: stages x bn*128][packed: kPackedStages x 4 KB]
 // [byte-pair table 256 x 4 B x 32 lanes = 32 KB][code2 table 1 KB][256 staged words][barriers][tmem base].
 // With split-K the stage memory doubles as the leader's reduction buffer after the main loop: (splits-1) x [bn][128] fp32.
 template <typename T, bool NESTED>
@@ -136,12 +138,12 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     uint8_t* s_a = smem;                                   // stages x [128 rows x 128 B], swizzled
     uint8_t* s_b = s_a + stages * (kTileRows * 128);       // stages x [bn rows x 128 B], swizzled by TMA
     uint8_t* s_p = s_b + stages * (bn * 128);              // stages x [128 rows x 32 B] packed
-    uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_p + stages * (kTileRows * 32));  // [256][32] pair words
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_p + kPackedStages * (kTileRows * 32));  // [256][32] pair words
     float* s_code2 = reinterpret_cast<float*>(s_lut + 256 * 32);                     // [256]
     uint32_t* s_words = reinterpret_cast<uint32_t*>(s_code2 + 256);                  // [256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_words + 256);
-    // barrier order: full_tma[stages], full_a[stages], empty[stages], tmem_full
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
+    // barrier order: full_tma[stages], full_a[stages], empty[stages], tmem_full, full_p[kPackedStages], empty_p[kPackedStages]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1 + 2 * kPackedStages);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kTileRows;   // first weight row of this tile
@@ -154,6 +156,13 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     auto full_a = [&](int s) { return smem_u32(bars + stages + s); };
     auto empty = [&](int s) { return smem_u32(bars + 2 * stages + s); };
     const uint32_t tmem_full = smem_u32(bars + 3 * stages);
+    // progress counters next to the TMEM base: [0] packed tiles issued by the weight producer, [1] k-blocks whose MMAs have completed.
+    // The dequantise sets poll THESE instead of waiting on the ring barriers by parity: a set takes every kSets-th k-block, so it skips
+    // phases of a barrier, and a parity wait two phases early passes at once (seen on B200 as tiles dequantised from the packed
+    // bytes of k-block i + 8).  The counters are written by threads that see every phase in order.
+    volatile int* s_flags = reinterpret_cast<volatile int*>(s_tmem + 2);
+    auto full_p = [&](int s) { return smem_u32(bars + 3 * stages + 1 + s); };
+    auto empty_p = [&](int s) { return smem_u32(bars + 3 * stages + 1 + kPackedStages + s); };
 
     // ---- one-time setup
     if (warp == 0 && lane == 0) {
@@ -167,10 +176,17 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             mbar_init(empty(s), 1);
         }
         mbar_init(tmem_full, 1);
+        for (int s = 0; s < kPackedStages; s++) {
+            mbar_init(full_p(s), 1);
+            mbar_init(empty_p(s), 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_flags[0] = 0;
+        s_flags[1] = 0;
     }
     if (warp == 2) {
-        const uint32_t ncols = bn < 32 ? 32 : bn;  // power of two >= 32 (bn is 16,32,64,128,256)
+        uint32_t ncols = 32;  // power of two >= max(32, bn)
+        while ((int)ncols < bn) ncols *= 2;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -190,16 +206,39 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
 
+    // Two independent producers.  A stage's life used to be TMA flight (~1000 clk) -> dequantise (~900) -> MMA (~540) -> commit, with
+    // activation tile, packed tile and A tile tied to the same three stages: ~2450 clk / 3 = what a k-block took (1185 clk measured,
+    // tensor pipe 47 % busy).  The packed bytes are 4 KB per k-block, so THEIR ring can be eight deep: the dequantise warps then find
+    // their input long since landed, start on a k-block the moment its A stage is free (the lookups even before that), and run while
+    // the activation tile of the same k-block is still in flight.
     if (warp == 0) {
-        // ===== TMA producer
+        // ===== TMA producer, activation tiles
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(bn * 128 + kTileRows * 32);
+            const uint32_t bytes = (uint32_t)(bn * 128);
             for (int i = 0; i < nkb; i++) {
                 const int s = i % stages, kb = kb_lo + i;
                 if (i >= stages) mbar_wait(empty(s), ((i / stages) - 1) & 1);
                 mbar_expect_tx(full_tma(s), bytes);
                 tma_load_2d(smem_u32(s_b + s * (bn * 128)), &map_x, kb * kBK, tok0, full_tma(s));
-                tma_load_2d(smem_u32(s_p + s * (kTileRows * 32)), &map_w, kb * 32, row0, full_tma(s));
+            }
+        }
+    } else if (warp == 3) {
+        // ===== TMA producer, packed weight tiles
+        if (lane == 0) {
+            for (int i = 0; i < nkb; i++) {
+                const int s = i % kPackedStages, kb = kb_lo + i;
+                if (i >= kPackedStages) mbar_wait(empty_p(s), ((i / kPackedStages) - 1) & 1);
+                mbar_expect_tx(full_p(s), kTileRows * 32);
+                tma_load_2d(smem_u32(s_p + s * (kTileRows * 32)), &map_w, kb * 32, row0, full_p(s));
+                s_flags[0] = i + 1;  // fill i is under way: full_p(s) is in the phase that this fill completes
+            }
+        }
+    } else if (warp == 2) {
+        // ===== MMA progress: sees every phase of the empty barriers in order and publishes the count
+        if (lane == 0) {
+            for (int i = 0; i < nkb; i++) {
+                mbar_wait(empty(i % stages), (i / stages) & 1);
+                s_flags[1] = i + 1;
             }
         }
     } else if (warp == 1) {
@@ -243,15 +282,16 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 else am = __ldg(a.s.absmax + blk);
             }
             const uint32_t am2 = pack2<__half>(am, am);
-            if (i >= stages) mbar_wait(empty(s), ((i / stages) - 1) & 1);  // A tile of this stage no longer read by the MMA
-            mbar_wait(full_tma(s), ph);                                    // packed bytes have landed
-            const uint4* pk = reinterpret_cast<const uint4*>(s_p + s * (kTileRows * 32) + t * 32);
+            const int sp = i % kPackedStages;
+            while (s_flags[0] <= i) __nanosleep(20);        // the fill has been issued: the barrier is in its phase (as a rule long ago)
+            mbar_wait(full_p(sp), (i / kPackedStages) & 1);  // ... and the packed bytes have landed
+            const uint4* pk = reinterpret_cast<const uint4*>(s_p + sp * (kTileRows * 32) + t * 32);
             const uint4 p0 = pk[0], p1 = pk[1];
             const uint32_t wd[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
             uint8_t* arow = s_a + s * (kTileRows * 128) + t * 128;
+            uint32_t h[8][4];  // the row's 64 dequantised weights: computed before the A stage is known to be free
 #pragma unroll
             for (int c = 0; c < 8; c++) {  // 16-byte chunk c = 8 weights = one packed word
-                uint32_t h[4];
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const uint32_t byte = (wd[c] >> (8 * b)) & 0xFFu;
@@ -260,13 +300,19 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                     if constexpr (std::is_same<T, __nv_bfloat16>::value) {
                         // bf16 has 8 mantissa bits: multiply in fp32 and round once, like the reference's dequantize
                         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
-                        h[b] = pack2<T>(f.x * am, f.y * am);
+                        h[c][b] = pack2<T>(f.x * am, f.y * am);
                     } else {
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h[b]) : "r"(v), "r"(am2));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h[c][b]) : "r"(v), "r"(am2));
                     }
                 }
-                *reinterpret_cast<uint4*>(arow + ((c ^ (t & 7)) * 16)) = make_uint4(h[0], h[1], h[2], h[3]);
             }
+            mbar_arrive(empty_p(sp));  // the thread's 32 packed bytes have been consumed (the lookups above depend on them)
+            if (i >= stages) {  // A tile of this stage no longer read by the MMA of k-block i - stages
+                while (s_flags[1] < i - stages + 1) __nanosleep(20);
+                __threadfence_block();
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(arow + ((c ^ (t & 7)) * 16)) = make_uint4(h[c][0], h[c][1], h[c][2], h[c][3]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             mbar_arrive(full_a(s));
         }
@@ -358,20 +404,54 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        const uint32_t ncols = bn < 32 ? 32 : bn;
+        uint32_t ncols = 32;
+        while ((int)ncols < bn) ncols *= 2;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
 
-static int pick_bn(int64_t M)
+constexpr size_t kFixedSmem = 256 * 32 * 4 + 1024 + 1024 + (3 * 8 + 1 + 2 * kPackedStages) * 8 + 64 + (size_t)kPackedStages * kTileRows * 32;
+
+// How a launch is cut: tokens per tile (bn), pipeline stages, split-K factor.
+//  * One CTA fits per SM, so the launch runs in ceil(tiles x splits / SMs) waves, and a k-block costs a CTA about the same time
+//    (~0.55 us measured) whatever bn is: the time of a launch is ~ waves x (k-blocks per CTA).  Hence: the widest token tile, and
+//  * split-K over a thread-block cluster while tiles x splits stays within ONE wave (112 tiles x 2 would run as two waves and
+//    measured twice the time of the unsplit launch), each CTA keeps >= 4 k-blocks and the reduction buffer fits the stage memory.
+//  * Up to 128 tokens: the smallest power of two that holds them.  Beyond: any multiple of 16 up to 256 is a legal UMMA N; the
+//    cost model picks among them.
+struct Cut {
+    int bn, stages, splits;
+    int64_t cost;
+};
+static Cut plan_cut(int bn, int64_t M, int64_t N, int64_t K, int sms)
 {
-    if (M <= 16) return 16;
-    if (M <= 32) return 32;
-    if (M <= 64) return 64;
-    if (M <= 128) return 128;
-    return 256;
+    Cut c;
+    c.bn = bn;
+    const size_t per_stage = kTileRows * 128 + (size_t)bn * 128;  // A tile + activation tile
+    c.stages = (int)((225 * 1024 - kFixedSmem) / per_stage);
+    if (c.stages > 8) c.stages = 8;
+    const int64_t tiles = ((N + kTileRows - 1) / kTileRows) * ((M + bn - 1) / bn);
+    c.splits = 1;
+    while (c.splits < 8 && tiles * c.splits * 2 <= sms && (K / kBK) / (c.splits * 2) >= 4 &&
+           (size_t)(c.splits * 2 - 1) * bn * kTileRows * 4 <= c.stages * per_stage)
+        c.splits *= 2;
+    const int64_t waves = (tiles * c.splits + sms - 1) / sms;
+    // + prologue / epilogue of a tile, in k-blocks; ties go to the narrower tile (more stages fit, shorter ramp: 4096x4096 at 256
+    // tokens measured 30 us with two 128-token tiles against 38 us with one 256-token tile, both split in two)
+    c.cost = waves * ((K / kBK + c.splits - 1) / c.splits + 6) * 1024 + bn;
+    return c;
+}
+static Cut pick_cut(int64_t M, int64_t N, int64_t K, int sms)
+{
+    if (M <= 128) return plan_cut(M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128, M, N, K, sms);
+    Cut best = plan_cut(256, M, N, K, sms);
+    for (int bn = 240; bn >= 128; bn -= 16) {
+        const Cut c = plan_cut(bn, M, N, K, sms);
+        if (c.cost < best.cost) best = c;
+    }
+    return best;
 }
 
 template <typename T>
@@ -380,23 +460,14 @@ static int launch(const T* X, const uint8_t* B, const q4_absmax_t* st, const flo
 {
     const AbsmaxView v = make_view(st);
     const bool nested = st->qabsmax != nullptr;
-    const int bn = pick_bn(M);
-    const size_t per_stage = kTileRows * 128 + (size_t)bn * 128 + kTileRows * 32;
-    const size_t fixed = 256 * 32 * 4 + 1024 + 1024 + 8 * 64 + 64;
-    int stages = (int)((200 * 1024 - fixed) / per_stage);
-    if (stages > 8) stages = 8;
-    if (stages < 2) return Q4_ERR_SHAPE;
-    const size_t smem = stages * per_stage + fixed + 1024;
-
-    // split-K over a thread-block cluster when the tile grid cannot fill the GPU (small token counts): the largest power
-    // of two <= 8 that keeps tiles * splits <= ~2 CTAs per SM, leaves >= 4 k-blocks per CTA and fits the reduction buffer
-    const int64_t tiles = ((N + kTileRows - 1) / kTileRows) * ((M + bn - 1) / bn);
+    static const int env_bn = getenv("Q4_GEMM_BN") ? atoi(getenv("Q4_GEMM_BN")) : 0;
     static const int env_splits = getenv("Q4_GEMM_SPLITS") ? atoi(getenv("Q4_GEMM_SPLITS")) : 0;
-    int splits = 1;
-    while (splits < 8 && tiles * splits * 2 <= 2 * sm_count() && (K / kBK) / (splits * 2) >= 4 &&
-           (size_t)(splits * 2 - 1) * bn * kTileRows * 4 <= stages * per_stage)
-        splits *= 2;
-    if (env_splits) splits = env_splits;
+    const Cut cut = env_bn ? plan_cut(env_bn, M, N, K, sm_count()) : pick_cut(M, N, K, sm_count());
+    const int bn = cut.bn, stages = cut.stages;
+    const int splits = env_splits ? env_splits : cut.splits;
+    if (stages < 2) return Q4_ERR_SHAPE;
+    const size_t per_stage = kTileRows * 128 + (size_t)bn * 128;
+    const size_t smem = stages * per_stage + kFixedSmem + 1024;
 
     CUtensorMap map_x, map_w;
     const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -418,7 +489,7 @@ static int launch(const T* X, const uint8_t* B, const q4_absmax_t* st, const flo
     a.stages = stages;
     a.splits = splits;
     auto kern = nested ? gemm_dequant_tcgen05_kernel<T, true> : gemm_dequant_tcgen05_kernel<T, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((N + kTileRows - 1) / kTileRows), (unsigned)((M + bn - 1) / bn), (unsigned)splits);

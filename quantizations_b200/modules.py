@@ -55,9 +55,9 @@ _SMALL_BATCH_GEMV_ROWS = 16
 
 def _use_fused_gemm(A, quant_state, bias) -> bool:
     """Prefill dispatch.  Q4_PREFILL=fused|cublas forces a path; `auto` (default) takes the fused tcgen05 kernel where it
-    measured faster than dequantise + cuBLAS on B200 (profiles/): up to 64 tokens on every Llama-3 shape, up to 128 tokens on
-    the 14336-wide ones; beyond that the dense GEMM dominates and cuBLAS' 2-CTA kernels are still ahead of this round's
-    single-CTA pipeline."""
+    measured faster than dequantise + cuBLAS on B200 (profiles/r02_prefill_gemm.txt): up to 64 tokens on every Llama-3 shape,
+    up to 256 tokens when out_features >= in_features (4096x4096, 14336x4096, q/k/v), up to 512 on the 14336-wide ones; beyond
+    that the dense GEMM dominates and cuBLAS' 2-CTA kernels are still ahead of this kernel's single-CTA pipeline."""
     if not fused_gemm_supported(A, quant_state) or not (bias is None or bias.dtype == A.dtype):
         return False
     mode = os.environ.get("Q4_PREFILL", "auto")
@@ -67,7 +67,11 @@ def _use_fused_gemm(A, quant_state, bias) -> bool:
         return False
     M = A.numel() // A.shape[-1]
     n, k = quant_state.shape
-    return M <= 64 or (M <= 128 and n * k >= 32 * 1024 * 1024)
+    if M <= 64:
+        return True
+    if n < k:
+        return False
+    return M <= 256 or (M <= 512 and n * k >= 32 * 1024 * 1024)
 
 
 class Linear4bit(nn.Linear):
