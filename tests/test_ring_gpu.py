@@ -181,3 +181,67 @@ def test_ring_ragged_k_tile_pair_and_tagged_residual(q):
         assert _ring_launch(q, [f for f, _ in stages]) == 0
         torch.cuda.synchronize()
         assert _close(h, h_ref) and _close(g_u, g_ref)
+
+
+def test_ring_thirty_two_stages_with_residuals_and_too_distant_residual(q):
+    """32 stages in ONE launch (the exchange buffers are reused modulo 8): a residual stream updated in place every second stage
+    (`bias` = the out of the stage two back, read from its tagged copy), checked against 32 single launches; twice, so that a
+    buffer is reused across launches as well.  A residual more than six stages back would find its exchange buffer overwritten:
+    refused with Q4_ERR_SHAPE."""
+    torch.manual_seed(13)
+    dt = torch.bfloat16
+    H = 2048
+    lins = []
+    for i in range(32):
+        lin = q.Linear4bit(H, H, bias=False, compute_dtype=dt, quant_type="nf4", device="meta")
+        W = (torch.randn(H, H, device=DEV) * (0.5 / H ** 0.5)).to(dt)
+        lin.weight = q.Params4bit(W, requires_grad=False, quant_type="nf4", module=lin).to(DEV)
+        lins.append(lin)
+    x0 = torch.randn(1, 1, H, device=DEV, dtype=dt)
+
+    def reference():
+        h = x0.clone()      # residual stream
+        t = x0.clone()      # what the next stage consumes
+        for i, lin in enumerate(lins):
+            if i % 2 == 0:  # plain stage
+                t = q.gemv_4bit(t, lin.weight.data, state=lin.weight.quant_state)
+            else:           # h += W t, and the next stage consumes h
+                q.gemv_4bit_fused(t, lin.weight.data, lin.weight.quant_state, residual=h, out=h)
+                t = h
+        return h.clone()
+
+    ref = reference()
+    h = torch.empty_like(x0)
+    tmp = [torch.empty(1, 1, H, device=DEV, dtype=dt) for _ in range(16)]
+
+    def build():
+        stages, t = [], x0
+        for i, lin in enumerate(lins):
+            if i % 2 == 0:
+                q.gemv_4bit_fused(t, lin.weight.data, lin.weight.quant_state, out=tmp[i // 2], _defer=stages)
+                t = tmp[i // 2]
+            else:
+                q.gemv_4bit_fused(t, lin.weight.data, lin.weight.quant_state, residual=h, out=h, _defer=stages)
+                t = h
+        return stages
+
+    stages = build()
+    for _ in range(2):
+        h.copy_(x0)
+        n0 = q._lib.launch_count()
+        rc = _ring_launch(q, [f for f, _ in stages])
+        assert rc == 0, q._lib.lib().q4_error_string(rc)
+        assert q._lib.launch_count() - n0 == 1
+        torch.cuda.synchronize()
+        assert _close(h, ref, 2e-2)  # 32 dependent stages: rounding flips propagate
+    # residual eight stages back: stage 9's bias = stage 1's out
+    far = []
+    t = x0
+    outs = [torch.empty(1, 1, H, device=DEV, dtype=dt) for _ in range(10)]
+    for i in range(10):
+        kw = {"residual": outs[1]} if i == 9 else {}
+        q.gemv_4bit_fused(t, lins[i].weight.data, lins[i].weight.quant_state, out=outs[i], _defer=far, **kw)
+        t = outs[i]
+    n0 = q._lib.launch_count()
+    assert _ring_launch(q, [f for f, _ in far]) == q._lib.Q4_ERR_SHAPE
+    assert q._lib.launch_count() == n0
