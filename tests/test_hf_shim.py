@@ -88,3 +88,73 @@ def test_graph_generate_replays_the_eager_static_cache_loop():
         ref = model.generate(ids, max_new_tokens=1, do_sample=False, pad_token_id=0)
     assert torch.equal(eager, graph)
     assert int(ref[0, -1]) == int(graph[0, 0])
+
+
+@pytest.mark.gpu
+def test_transformers_own_conversion_ops_build_and_reload_our_weights():
+    """What from_pretrained(quantization_config=BitsAndBytesConfig(load_in_4bit=True)) does per weight, without `accelerate` (absent in
+    this image, so from_pretrained itself cannot run): transformers' OWN conversion ops -- integrations/bitsandbytes.py
+    `Bnb4bitQuantize.convert` (dense checkpoint tensor -> bnb.nn.Params4bit(value, **old.__dict__).to(device)) and
+    `Bnb4bitDeserialize.convert` (pre-quantised checkpoint: packed weight + the bnb statistics keys ->
+    bnb.nn.Params4bit.from_prequantized) -- executed unmodified with `bitsandbytes` resolving to this engine.  The quantised model
+    must decode like its dense twin, and a model rebuilt from the state dict of the first (the serialised bnb key set) must
+    reproduce it bit for bit.  Reference: core.py:91-190 (Params4bit), modules.py:67-151."""
+    from transformers import BitsAndBytesConfig
+    from transformers.integrations.bitsandbytes import Bnb4bitDeserialize, Bnb4bitQuantize
+
+    from quantizations_b200 import hf
+    import quantizations_b200 as q
+
+    dev = "cuda:0"
+    cfg = BitsAndBytesConfig(load_in_4bit=True, bnb_4bit_quant_type="nf4", bnb_4bit_use_double_quant=True,
+                             bnb_4bit_compute_dtype=torch.bfloat16)
+    dense = _tiny().to(torch.bfloat16)
+    checkpoint = {k: v.clone() for k, v in dense.state_dict().items()}
+
+    def skeleton():
+        m = _tiny().to(torch.bfloat16)
+        hf.replace_with_bnb_linear(m, cfg, modules_to_not_convert=["lm_head"])
+        return m
+
+    # ---- dense checkpoint -> quantise on load
+    model = skeleton()
+    op = Bnb4bitQuantize(None)
+    names = [n for n, m in model.named_modules() if isinstance(m, q.Linear4bit)]
+    assert len(names) == 14  # 2 layers x (q, k, v, o, gate, up, down)
+    for n in names:
+        out = op.convert({n + ".weight": [checkpoint[n + ".weight"].to(dev)]}, full_layer_name=n + ".weight", model=model)
+        (key, value), = out.items()
+        assert key == n + ".weight" and isinstance(value, q.Params4bit) and value.dtype == torch.uint8 and value.quant_state is not None
+        mod = model.get_submodule(n)
+        mod.weight = value
+    rest = {k: v for k, v in checkpoint.items() if not any(k == n + ".weight" for n in names)}
+    missing, unexpected = model.load_state_dict(rest, strict=False)
+    assert not unexpected and all(any(k.startswith(n + ".weight") for n in names) for k in missing)
+    model.to(dev)
+    twin = dense.to(dev)
+    for n in names:
+        m = model.get_submodule(n)
+        twin.get_submodule(n).weight.data = q.dequantize_4bit(m.weight.data, m.weight.quant_state).t().contiguous().to(torch.bfloat16)
+    ids = torch.arange(3, 19, device=dev).view(1, -1)
+    with torch.no_grad():
+        lq, ld = model(ids[:, :1]).logits.float(), twin(ids[:, :1]).logits.float()
+        assert (lq - ld).abs().max().item() <= 3e-2 * ld.abs().max().item()
+
+    # ---- pre-quantised checkpoint (the state dict of the model above: bnb's key names) -> deserialise on load
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    assert any(k.endswith("weight.quant_state.bitsandbytes__nf4") for k in sd) and any(k.endswith("weight.nested_absmax") for k in sd)
+    again = skeleton()
+    dop = Bnb4bitDeserialize(None)
+    for n in names:
+        pre = n + ".weight"
+        inp = {"weight": [sd[pre].to(dev)]}
+        inp.update({k[len(n) + 1:]: [v.to(dev)] for k, v in sd.items() if k.startswith(pre + ".")})
+        out = dop.convert(inp, model=again, full_layer_name=pre)
+        value = out["weight"]
+        assert isinstance(value, q.Params4bit) and value.quant_state is not None
+        again.get_submodule(n).weight = value
+    again.load_state_dict({k: v for k, v in sd.items() if not any(k.startswith(n + ".weight") for n in names)}, strict=False)
+    again.to(dev)
+    with torch.no_grad():
+        assert torch.equal(again(ids[:, :1]).logits, model(ids[:, :1]).logits)
+        assert torch.equal(again(ids).logits, model(ids).logits)
