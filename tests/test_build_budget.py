@@ -39,3 +39,19 @@ def test_blockwise_kernels_register_budget():
     assert q and all(regs <= 64 and spill == 0 for regs, spill in q.values()), q   # four 256-thread CTAs per SM
     d = {k: v for k, v in _kernels("q4_dequantize.o.log").items() if "dequantize_4bit_kernel" in k}
     assert d and all(regs <= 64 and spill == 0 for regs, spill in d.values()), d
+
+
+def test_ring_tokens_and_gemm_register_budget():
+    """The persistent ring GEMV is compiled for 640 threads per CTA (96 registers, raised to 112 for the consumers by setmaxnreg): its
+    nested instantiations must not spill more than they do today -- every value that lives across the slot loop costs more than it saves.  The
+    small-batch kernel runs 512 threads at 128 registers, the prefill GEMM 512 threads (three dequantise sets) below 128."""
+    ring = {k: v for k, v in _kernels("q4_gemv_ring.o.log").items() if "gemv_ring_kernel" in k}
+    assert ring and all(regs <= 96 for regs, _ in ring.values()), ring
+    # <T, NESTED = 1, 16, 2> keeps one 4-byte value on the stack outside the slot loop (4 bytes stored, 8 loaded); anything more is a
+    # value that lives across the loop
+    assert all(spill <= 16 for k, (_, spill) in ring.items() if "Lb1ELi16ELi2E" in k), ring
+    assert all(spill == 0 for k, (_, spill) in ring.items() if "Lb0ELi16ELi2E" in k), ring
+    tok = {k: v for k, v in _kernels("q4_gemv_tokens.o.log").items() if "gemv_tokens_kernel" in k}
+    assert len(tok) == 4 and all(regs <= 128 and spill == 0 for regs, spill in tok.values()), tok
+    gemm = {k: v for k, v in _kernels("q4_gemm.o.log").items() if "gemm_dequant_tcgen05_kernel" in k}
+    assert len(gemm) == 4 and all(regs <= 128 and spill == 0 for regs, spill in gemm.values()), gemm
