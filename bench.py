@@ -214,6 +214,58 @@ def run_ours(args, rank, world, device):
                 raise RuntimeError(f"tp_check: ranks hold different bits after the fused all-reduce of {m.name_}")
         tp_check = {"status": "ok", "units": len(picked), "max_rel_err_vs_nccl": worst, "bit_identical_across_ranks": True}
 
+    # ---- what one all-reduce costs (SURVEY 8e "Reporting"): the same row-parallel GEMV of a shard, 32 launches per CUDA-graph replay, with
+    #      the all-reduce fused into its epilogue and without; and NCCL's all-reduce of the same 8 KB vector, stream-ordered, for comparison
+    ar_latency = None
+    if fused_ar is not None and not getattr(args, "no_ar_latency", False):
+        from quantizations_b200 import graphs as _graphs
+
+        ar_latency = {}
+        row_units = [m for m in units if m.parallel == "row"]
+        for m in row_units[:2]:  # o_proj and down_proj shards of the first layer
+            st = m.weight.quant_state
+            xk = torch.randn(1, 1, m.in_features, device=device, dtype=dtype)
+            yk = torch.empty(1, 1, m.out_features, device=device, dtype=dtype)
+
+            def timed(kw):
+                def body():
+                    for _ in range(32):
+                        q.gemv_4bit_fused(xk, m.weight.data, st, out=yk, **kw)
+                g = _graphs.capture(body)
+                comm.barrier()
+                g.replay()
+                torch.cuda.synchronize(device)
+                comm.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize(device)
+                t = torch.tensor([e0.elapsed_time(e1) * 1e3 / (5 * 32)], device=device)
+                comm.all_reduce(t, op=comm.ReduceOp.MAX)
+                return t.item()
+
+            with_ar, without = timed({"allreduce": fused_ar}), timed({})
+            ar_latency[f"{m.name_} {m.out_features}x{m.in_features}"] = {"gemv_with_fused_allreduce_us": round(with_ar, 3), "gemv_alone_us": round(without, 3),
+                                                                         "allreduce_us": round(with_ar - without, 3)}
+        v = torch.randn(cfg["hidden"], device=device, dtype=dtype)
+        for _ in range(5):
+            comm.all_reduce(v)
+        torch.cuda.synchronize(device)
+        comm.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(64):
+            comm.all_reduce(v)
+        e1.record()
+        torch.cuda.synchronize(device)
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / 64], device=device)
+        comm.all_reduce(t, op=comm.ReduceOp.MAX)
+        ar_latency["nccl_all_reduce_us"] = round(t.item(), 3)
+        ar_latency["note"] = ("per-launch times, max over ranks, CUDA events around 5 replays of a 32-launch graph (L2-resident shard: latency, not bandwidth); "
+                              f"NCCL: 64 stream-ordered all_reduce calls of {cfg['hidden']} bf16 values")
+
     pdl = _lib.Q4_GEMV_PDL if args.pdl else 0
     # ---- data flow of a step: a decode token's Linear4bit forwards are DEPENDENT -- every Linear consumes what the previous one
     #      produced (q/k/v <- the previous layer's down_proj, o_proj <- the first in_features values of q/k/v [attention is not part
@@ -553,6 +605,8 @@ def run_ours(args, rank, world, device):
     }
     if tp_check is not None:
         res["tp_check"] = tp_check
+    if ar_latency is not None:
+        res["allreduce"] = ar_latency
     if ring_check is not None:
         res["ring_check"] = ring_check
     if world == 1 and not args.no_blockwise:
@@ -946,6 +1000,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-blockwise", action="store_true", help="skip the quantize / dequantize kernel rates")
     ap.add_argument("--no-sweep", action="store_true", help="skip the per-shape GEMV sweep (BASELINE configs[1])")
+    ap.add_argument("--no-ar-latency", action="store_true", help="skip the per-all-reduce latency measurement at --gpus > 1")
     ap.add_argument("--no-tp70b", action="store_true", help="skip the Llama-3-70B leg (BASELINE configs[4]: the 70B Linear stack and decode at this --gpus)")
     ap.add_argument("--no-decode", action="store_true", help="skip the end-to-end Llama-3-8B decode tok/s leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -986,6 +1041,7 @@ def main():
             torch.cuda.empty_cache()
             a70 = copy.copy(args)
             a70.model, a70.no_cpu, a70.no_blockwise, a70.no_sweep, a70.no_tp70b = "llama3-70b", True, True, True, True
+            a70.no_ar_latency = True
             a70.steps = min(args.steps, 10)
             r70 = run_ours(a70, rank, world, device)
             if rank == 0:

@@ -14,3 +14,8 @@ d = json.loads([l for l in open("gpurun_out/r2y2_bench_tp2%s.json" % sys.argv[1]
 print(sys.argv[1], d["ms_per_step"], d["value"], d.get("tp_check"), d.get("ring_check"), d["gpu_launches"])
 P
 done
+python - <<'P'
+import json
+d = json.loads([l for l in open("gpurun_out/r2y2_bench_tp2.json") if l.startswith("{")][-1])
+print(json.dumps(d.get("allreduce"), indent=1))
+P
