@@ -283,7 +283,10 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             }
             const uint32_t am2 = pack2<__half>(am, am);
             const int sp = i % kPackedStages;
-            while (s_flags[0] <= i) __nanosleep(20);        // the fill has been issued: the barrier is in its phase (as a rule long ago)
+            for (long long spin = 0; s_flags[0] <= i; spin++) {  // the fill has been issued: the barrier is in its phase (as a rule long ago)
+                __nanosleep(20);
+                if (spin > (1ll << 26)) __trap();  // fail loudly instead of hanging the GPU
+            }
             mbar_wait(full_p(sp), (i / kPackedStages) & 1);  // ... and the packed bytes have landed
             const uint4* pk = reinterpret_cast<const uint4*>(s_p + sp * (kTileRows * 32) + t * 32);
             const uint4 p0 = pk[0], p1 = pk[1];
@@ -308,7 +311,10 @@ gemm_dequant_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             }
             mbar_arrive(empty_p(sp));  // the thread's 32 packed bytes have been consumed (the lookups above depend on them)
             if (i >= stages) {  // A tile of this stage no longer read by the MMA of k-block i - stages
-                while (s_flags[1] < i - stages + 1) __nanosleep(20);
+                for (long long spin = 0; s_flags[1] < i - stages + 1; spin++) {
+                    __nanosleep(20);
+                    if (spin > (1ll << 26)) __trap();
+                }
                 __threadfence_block();
             }
 #pragma unroll
