@@ -69,6 +69,23 @@ def test_tokens_kernel_matches_per_token_gemv_at_llama_sizes(q, shape, M):
     assert torch.equal(y, q.gemv_4bit_batch(x, packed, st))
 
 
+@pytest.mark.parametrize("N,K,M", [(40000, 512, 3), (128256, 1024, 8), (20480, 2304, 16)])
+def test_tokens_kernel_many_row_tiles_per_cta(q, N, K, M):
+    """More row tiles per CTA than the kernel holds partial sums for at once (8): the pass loop, the ring restart between passes and the
+    last, shorter pass (an lm_head-sized matrix: 128256 rows = 8016 tiles on 148 CTAs = 7 passes), K that leaves warps without chunks
+    (512 = 2 chunks) and K whose chunks do not divide by the 16 warps (2304 = 9 chunks)."""
+    torch.manual_seed(N + K + M)
+    W = (torch.randn(N, K, device=DEV) * K ** -0.5).to(torch.bfloat16)
+    packed, st = q.quantize_4bit(W, quant_type="nf4")
+    del W
+    bias = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    y = q.gemv_4bit_batch(x, packed, st, bias=bias)
+    ref = torch.cat([q.gemv_4bit(x[m:m + 1].view(1, 1, K), packed, state=st, bias=bias).view(1, N) for m in range(M)], dim=0)
+    assert (y.float() - ref.float()).abs().max().item() <= 1e-2 * ref.float().abs().max().item()
+    assert torch.equal(y, q.gemv_4bit_batch(x, packed, st, bias=bias))
+
+
 def test_linear4bit_sends_2_to_16_tokens_through_one_pass(q):
     """modules.matmul_4bit: 2..16 tokens = one launch per 8 tokens; shapes the kernel does not cover (N % 16, K % 256) keep the old
     routes (per-token GEMVs up to 4 tokens, the fused GEMM beyond); results agree with the module applied token by token."""
