@@ -385,7 +385,7 @@ def test_linear4bit_module_decode_and_prefill(q):
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("quant_type,nested", [("fp4", True), ("nf4", True), ("nf4", False)])
 @pytest.mark.parametrize("M,N,K", [(16, 128, 64), (1, 256, 256), (33, 384, 512), (100, 200, 1024), (128, 1024, 4096),
-                                   (300, 512, 2048), (17, 4096, 4096), (64, 1024, 14336)])
+                                   (300, 512, 2048), (17, 4096, 4096), (64, 1024, 14336), (700, 640, 1024), (1000, 1024, 2048)])
 def test_fused_gemm_vs_fp64_truth(q, oracle, dtype, quant_type, nested, M, N, K):
     """gemm_4bit (dequantise fused into tcgen05 MMA) against an fp64 product of the ORACLE's dequantised weight.
     tolerance: max|y - truth| <= 1e-2 * max|truth|; ragged M and N (not multiples of the 16..256 x 128 tiles) included."""
