@@ -404,6 +404,50 @@ int main(int argc, char** argv)
                 }
             }
         }
+        // is the lateness systematic?  per CTA index and per SM: mean of (all warps done - median over the CTAs) over every traced stage
+        {
+            std::vector<double> late_cta(G, 0.0), late_sm(1024, 0.0), skew_by_stage(ring::kMaxStages, 0.0);
+            std::vector<int> n_cta(G, 0), n_sm(1024, 0), n_stage(ring::kMaxStages, 0);
+            for (size_t li = 1; li < nl; li++)
+                for (int st = 0; st < launches[li].n; st++) {
+                    std::vector<double> v;
+                    for (int b = 0; b < G; b++) {
+                        const unsigned long long t = h[li * trace_n + ((size_t)st * G + b) * ring::kTraceSlots + 8];
+                        if (t) v.push_back((double)t);
+                    }
+                    if ((int)v.size() < G / 2) continue;
+                    std::vector<double> sv = v;
+                    std::sort(sv.begin(), sv.end());
+                    const double med = sv[sv.size() / 2];
+                    skew_by_stage[st % 4] += (sv.back() - med) / 1e3;
+                    n_stage[st % 4]++;
+                    for (int b = 0; b < G; b++) {
+                        const unsigned long long* t = &h[li * trace_n + ((size_t)st * G + b) * ring::kTraceSlots];
+                        if (!t[8]) continue;
+                        const double d = ((double)t[8] - med) / 1e3;
+                        late_cta[b] += d; n_cta[b]++;
+                        const int sm = (int)(t[9] & 1023);
+                        late_sm[sm] += d; n_sm[sm]++;
+                    }
+                }
+            printf("mean (slowest CTA - median CTA) of 'all warps done', us, by stage position in the layer:");
+            for (int k = 0; k < 4; k++) printf(" %d: %.2f", k, n_stage[k] ? skew_by_stage[k] / n_stage[k] : 0.0);
+            printf("\n");
+            std::vector<std::pair<double, int>> oc, os;
+            for (int b = 0; b < G; b++) if (n_cta[b]) oc.push_back({late_cta[b] / n_cta[b], b});
+            for (int m = 0; m < 1024; m++) if (n_sm[m]) os.push_back({late_sm[m] / n_sm[m], m});
+            std::sort(oc.rbegin(), oc.rend());
+            std::sort(os.rbegin(), os.rend());
+            printf("latest CTA indices (mean lateness us):");
+            for (int k = 0; k < 12 && k < (int)oc.size(); k++) printf(" %d:%.2f", oc[k].second, oc[k].first);
+            printf("\nearliest CTA indices:");
+            for (int k = 0; k < 6 && k < (int)oc.size(); k++) printf(" %d:%.2f", oc[oc.size() - 1 - k].second, oc[oc.size() - 1 - k].first);
+            printf("\nlatest SMs (mean lateness us):");
+            for (int k = 0; k < 12 && k < (int)os.size(); k++) printf(" %d:%.2f", os[k].second, os[k].first);
+            printf("\nearliest SMs:");
+            for (int k = 0; k < 6 && k < (int)os.size(); k++) printf(" %d:%.2f", os[os.size() - 1 - k].second, os[os.size() - 1 - k].first);
+            printf("\n");
+        }
     }
     return 0;
 }
