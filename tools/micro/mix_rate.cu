@@ -126,7 +126,7 @@ int main()
     run<1, 3, 4>("lookups + HMMA + packed, body x4 (~10 KB)", 512);
     run<1, 3, 8>("lookups + HMMA + packed, body x8 (~20 KB)", 512);
     run<1, 3, 16>("lookups + HMMA + packed, body x16 (~40 KB)", 512);
-    for (int threads : {512}) {
+    for (int threads : {256, 384, 512}) {  // 8 / 12 / 16 warps: can fewer, fatter warps keep the shared-memory pipe as busy?
         run<0, 3>("lookups + HMMA", threads);
         run<1, 3>("lookups + HMMA + packed LDS.128", threads);
         run<3, 3>("lookups + packed LDS.128, no HMMA", threads);
